@@ -1,0 +1,18 @@
+"""B200-native batched calibration solve (one hot path of jskinn/deep-attention-visual-odometry).
+
+Host-side mirror of the reference's Python interface for that path; every numeric entry point
+dispatches to hand-written sm_100a CUDA through the C-ABI in include/davo_b200.h.  There is no CPU
+fallback: calling a compute function without the built library or without a CUDA device raises.
+"""
+from . import synthetic  # noqa: F401
+from . import _lib  # noqa: F401
+from .objectives import AnalyticObjective, CalibrationObjective, DistortionObjective, JointPoseObjective
+from .solvers import BFGSSolver, SolveInfo, line_search_wolfe_conditions
+from .camera_model import compute_distorted_camera_model, compute_distorted_camera_model_and_jacobian
+from .least_squares_utils import find_error, find_error_gradient, find_residuals
+
+__all__ = [
+    "AnalyticObjective", "BFGSSolver", "CalibrationObjective", "DistortionObjective", "JointPoseObjective",
+    "SolveInfo", "compute_distorted_camera_model", "compute_distorted_camera_model_and_jacobian", "find_error",
+    "find_error_gradient", "find_residuals", "line_search_wolfe_conditions", "synthetic",
+]

@@ -1,0 +1,251 @@
+// davo_abi.cu — the extern "C" boundary declared in include/davo_b200.h: argument validation,
+// descriptor -> typed device parameters, dispatch to the kernel launchers.  No torch types, no
+// allocation, no host synchronisation.
+#include <atomic>
+
+#include "davo_common.cuh"
+#include "launch.h"
+
+namespace davo {
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static bool is_analytic(int model) { return model >= DAVO_MODEL_SPHERE && model <= DAVO_MODEL_DISTANCE; }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_desc(const davo_problem_desc* d) {
+    if (!d) return DAVO_ERR_NULL_POINTER;
+    if (d->B < 0 || d->N < 0 || d->n < 1 || d->V < 1) return DAVO_ERR_BAD_SHAPE;
+    if (d->dtype != DAVO_F32 && d->dtype != DAVO_F64) return DAVO_ERR_UNSUPPORTED;
+    if (d->max_iters < 0 || d->max_ls_iters < 0) return DAVO_ERR_BAD_ARGUMENT;
+    if (d->model == DAVO_MODEL_DISTORT10) {
+        if (d->n != 10 || d->V != 1) return DAVO_ERR_BAD_SHAPE;
+    } else if (d->model == DAVO_MODEL_JOINT) {
+        if (d->n != 10 + 6 * d->V) return DAVO_ERR_BAD_SHAPE;
+    } else if (is_analytic(d->model)) {
+        if (d->model == DAVO_MODEL_ROSENBROCK && d->n != 2) return DAVO_ERR_BAD_SHAPE;
+        if (d->n > kSlots) return DAVO_ERR_UNSUPPORTED;
+    } else {
+        return DAVO_ERR_UNSUPPORTED;
+    }
+    return DAVO_OK;
+}
+
+static int check_data(const davo_problem_desc* d, const void* data0, const void* data1, const void* w) {
+    if (d->B == 0) return DAVO_OK;
+    if (d->model == DAVO_MODEL_DISTORT10) {
+        if (!data0) return DAVO_ERR_NULL_POINTER;
+        if (!aligned16(data0)) return DAVO_ERR_MISALIGNED;  // bulk-TMA source rows
+    } else if (d->model == DAVO_MODEL_JOINT) {
+        if (!data0 || !data1) return DAVO_ERR_NULL_POINTER;
+        if (!aligned16(data0) || !aligned16(data1)) return DAVO_ERR_MISALIGNED;
+    } else if (d->model == DAVO_MODEL_DISTANCE) {
+        if (!data0) return DAVO_ERR_NULL_POINTER;
+    }
+    if (d->has_weights && !w) return DAVO_ERR_NULL_POINTER;
+    return DAVO_OK;
+}
+
+template <typename T>
+static SolveParams<T> make_params(const davo_problem_desc* d, const void* data0, const void* data1, const void* w) {
+    SolveParams<T> p{};
+    p.B = d->B; p.N = d->N; p.V = d->V; p.n = d->n; p.model = d->model;
+    p.max_iters = d->max_iters; p.max_ls = d->max_ls_iters; p.strong = d->strong; p.has_w = d->has_weights;
+    // thresholds are rounded to the arithmetic type exactly like torch rounds a Python float that meets a tensor
+    p.c1 = static_cast<T>(d->sufficient_decrease);
+    p.c2 = static_cast<T>(d->curvature);
+    p.thr = static_cast<T>(d->error_threshold);
+    p.min_step = static_cast<T>(d->minimum_step);
+    p.data0 = static_cast<const T*>(data0);
+    p.data1 = static_cast<const T*>(data1);
+    p.w = d->has_weights ? static_cast<const T*>(w) : nullptr;
+    return p;
+}
+}  // namespace davo
+
+using namespace davo;
+
+extern "C" {
+
+int davo_abi_version(void) { return DAVO_ABI_VERSION; }
+
+const char* davo_strerror(int status) {
+    switch (status) {
+        case DAVO_OK: return "ok";
+        case DAVO_ERR_NULL_POINTER: return "a required pointer is NULL";
+        case DAVO_ERR_BAD_SHAPE: return "B, N, V, n are inconsistent with the model";
+        case DAVO_ERR_UNSUPPORTED: return "model / n / N / dtype is outside what this build supports";
+        case DAVO_ERR_MISALIGNED: return "a vector-loaded buffer is not 16-byte aligned";
+        case DAVO_ERR_CUDA: return "CUDA launch or runtime error";
+        case DAVO_ERR_BAD_ARGUMENT: return "bad argument";
+        default: return "unknown davo status";
+    }
+}
+
+int64_t davo_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, const void* data1,
+                           const void* weights, const void* x0, void* x_out, void* cost_out,
+                           uint8_t* converged_out, int32_t* iters_out, int32_t* fevals_out,
+                           int32_t* reason_out, void* workspace, void* stream) {
+    int st = check_desc(desc);
+    if (st) return st;
+    if (desc->B == 0) return DAVO_OK;
+    if (!x0 || !x_out || !workspace) return DAVO_ERR_NULL_POINTER;
+    if ((st = check_data(desc, data0, data1, weights))) return st;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (desc->dtype == DAVO_F32) {
+        SolveParams<float> p = make_params<float>(desc, data0, data1, weights);
+        p.x0 = static_cast<const float*>(x0); p.x_out = static_cast<float*>(x_out);
+        p.cost_out = static_cast<float*>(cost_out); p.converged_out = converged_out;
+        p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
+        p.queue = static_cast<unsigned*>(workspace);
+        return desc->model == DAVO_MODEL_JOINT ? launch_solve_joint_f32(p, s) : launch_solve_warp_f32(p, s);
+    }
+    SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
+    p.x0 = static_cast<const double*>(x0); p.x_out = static_cast<double*>(x_out);
+    p.cost_out = static_cast<double*>(cost_out); p.converged_out = converged_out;
+    p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
+    p.queue = static_cast<unsigned*>(workspace);
+    return desc->model == DAVO_MODEL_JOINT ? launch_solve_joint_f64(p, s) : launch_solve_warp_f64(p, s);
+}
+
+int davo_eval_cost_grad(const davo_problem_desc* desc, const void* data0, const void* data1,
+                        const void* weights, const void* x, void* cost, void* grad, void* stream) {
+    int st = check_desc(desc);
+    if (st) return st;
+    if (desc->B == 0) return DAVO_OK;
+    if (!x) return DAVO_ERR_NULL_POINTER;
+    if ((st = check_data(desc, data0, data1, weights))) return st;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (desc->dtype == DAVO_F32) {
+        SolveParams<float> p = make_params<float>(desc, data0, data1, weights);
+        p.x0 = static_cast<const float*>(x); p.cost_out = static_cast<float*>(cost);
+        p.x_out = static_cast<float*>(grad);
+        return desc->model == DAVO_MODEL_JOINT ? launch_eval_joint_f32(p, s) : launch_eval_warp_f32(p, s);
+    }
+    SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
+    p.x0 = static_cast<const double*>(x); p.cost_out = static_cast<double*>(cost);
+    p.x_out = static_cast<double*>(grad);
+    return desc->model == DAVO_MODEL_JOINT ? launch_eval_joint_f64(p, s) : launch_eval_warp_f64(p, s);
+}
+
+int davo_line_search(const davo_problem_desc* desc, const void* data0, const void* data1,
+                     const void* weights, const void* x, const void* direction, const void* base_cost,
+                     const void* base_grad, void* alpha_out, int32_t* fevals_out, void* stream) {
+    int st = check_desc(desc);
+    if (st) return st;
+    if (desc->B == 0) return DAVO_OK;
+    if (!x || !direction || !base_cost || !base_grad || !alpha_out) return DAVO_ERR_NULL_POINTER;
+    if ((st = check_data(desc, data0, data1, weights))) return st;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (desc->dtype == DAVO_F32) {
+        SolveParams<float> p = make_params<float>(desc, data0, data1, weights);
+        p.x0 = static_cast<const float*>(x); p.dir = static_cast<const float*>(direction);
+        p.base_cost = static_cast<const float*>(base_cost); p.base_grad = static_cast<const float*>(base_grad);
+        p.alpha_out = static_cast<float*>(alpha_out); p.fevals_out = fevals_out;
+        return desc->model == DAVO_MODEL_JOINT ? launch_line_search_joint_f32(p, s) : launch_line_search_warp_f32(p, s);
+    }
+    SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
+    p.x0 = static_cast<const double*>(x); p.dir = static_cast<const double*>(direction);
+    p.base_cost = static_cast<const double*>(base_cost); p.base_grad = static_cast<const double*>(base_grad);
+    p.alpha_out = static_cast<double*>(alpha_out); p.fevals_out = fevals_out;
+    return desc->model == DAVO_MODEL_JOINT ? launch_line_search_joint_f64(p, s) : launch_line_search_warp_f64(p, s);
+}
+
+int davo_stage_matches(const davo_problem_desc* desc, const void* points_3d, const void* obs,
+                       const void* pose, void* staged, void* stream) {
+    if (!desc) return DAVO_ERR_NULL_POINTER;
+    if (desc->B < 0 || desc->N < 0) return DAVO_ERR_BAD_SHAPE;
+    if (desc->B == 0 || desc->N == 0) return DAVO_OK;
+    if (!points_3d || !obs || !staged) return DAVO_ERR_NULL_POINTER;
+    if (!aligned16(staged)) return DAVO_ERR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (desc->dtype == DAVO_F32)
+        return launch_stage<float>(desc->B, desc->N, static_cast<const float*>(points_3d),
+                                   static_cast<const float*>(obs), static_cast<const float*>(pose),
+                                   static_cast<float*>(staged), s);
+    if (desc->dtype == DAVO_F64)
+        return launch_stage<double>(desc->B, desc->N, static_cast<const double*>(points_3d),
+                                    static_cast<const double*>(obs), static_cast<const double*>(pose),
+                                    static_cast<double*>(staged), s);
+    return DAVO_ERR_UNSUPPORTED;
+}
+
+static int project_impl(const davo_problem_desc* desc, const void* pts, const void* th, void* J, void* u, void* v,
+                        void* stream, bool want_j) {
+    if (!desc) return DAVO_ERR_NULL_POINTER;
+    if (desc->B < 0 || desc->N < 0) return DAVO_ERR_BAD_SHAPE;
+    if (desc->B == 0 || desc->N == 0) return DAVO_OK;
+    if (!pts || !th || !u || !v || (want_j && !J)) return DAVO_ERR_NULL_POINTER;
+    if (want_j && !aligned16(J)) return DAVO_ERR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (desc->dtype == DAVO_F32)
+        return launch_project<float>(desc->B, desc->N, static_cast<const float*>(pts), static_cast<const float*>(th),
+                                     static_cast<float*>(u), static_cast<float*>(v),
+                                     want_j ? static_cast<float*>(J) : nullptr, s);
+    if (desc->dtype == DAVO_F64)
+        return launch_project<double>(desc->B, desc->N, static_cast<const double*>(pts),
+                                      static_cast<const double*>(th), static_cast<double*>(u),
+                                      static_cast<double*>(v), want_j ? static_cast<double*>(J) : nullptr, s);
+    return DAVO_ERR_UNSUPPORTED;
+}
+
+int davo_project(const davo_problem_desc* desc, const void* points_3d, const void* params16, void* u, void* v,
+                 void* stream) {
+    return project_impl(desc, points_3d, params16, nullptr, u, v, stream, false);
+}
+
+int davo_project_jacobian(const davo_problem_desc* desc, const void* points_3d, const void* params16, void* J,
+                          void* u, void* v, void* stream) {
+    return project_impl(desc, points_3d, params16, J, u, v, stream, true);
+}
+
+int davo_least_squares(int32_t dtype, int32_t B, int32_t R, int32_t P, const void* residuals,
+                       const void* jacobian, const void* weights, void* error, void* gradient, void* stream) {
+    if (B < 0 || R < 0 || P < 0) return DAVO_ERR_BAD_SHAPE;
+    if (B == 0) return DAVO_OK;
+    if (!residuals || (!error && !gradient) || (gradient && !jacobian)) return DAVO_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == DAVO_F32)
+        return launch_least_squares<float>(B, R, P, static_cast<const float*>(residuals),
+                                           static_cast<const float*>(jacobian), static_cast<const float*>(weights),
+                                           static_cast<float*>(error), static_cast<float*>(gradient), s);
+    if (dtype == DAVO_F64)
+        return launch_least_squares<double>(B, R, P, static_cast<const double*>(residuals),
+                                            static_cast<const double*>(jacobian),
+                                            static_cast<const double*>(weights), static_cast<double*>(error),
+                                            static_cast<double*>(gradient), s);
+    return DAVO_ERR_UNSUPPORTED;
+}
+
+int davo_bfgs_update(int32_t dtype, int32_t k, int32_t n, void* H, const void* s_, const void* y, void* stream) {
+    if (k < 0 || n < 1) return DAVO_ERR_BAD_SHAPE;
+    if (k == 0) return DAVO_OK;
+    if (!H || !s_ || !y) return DAVO_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == DAVO_F32)
+        return launch_bfgs_update<float>(k, n, static_cast<float*>(H), static_cast<const float*>(s_),
+                                         static_cast<const float*>(y), s);
+    if (dtype == DAVO_F64)
+        return launch_bfgs_update<double>(k, n, static_cast<double*>(H), static_cast<const double*>(s_),
+                                          static_cast<const double*>(y), s);
+    return DAVO_ERR_UNSUPPORTED;
+}
+
+int davo_bfgs_initial_scale(int32_t dtype, int32_t k, int32_t n, const void* s_, const void* y, void* scale,
+                            void* stream) {
+    if (k < 0 || n < 1) return DAVO_ERR_BAD_SHAPE;
+    if (k == 0) return DAVO_OK;
+    if (!s_ || !y || !scale) return DAVO_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == DAVO_F32)
+        return launch_bfgs_initial_scale<float>(k, n, static_cast<const float*>(s_), static_cast<const float*>(y),
+                                                static_cast<float*>(scale), s);
+    if (dtype == DAVO_F64)
+        return launch_bfgs_initial_scale<double>(k, n, static_cast<const double*>(s_),
+                                                 static_cast<const double*>(y), static_cast<double*>(scale), s);
+    return DAVO_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

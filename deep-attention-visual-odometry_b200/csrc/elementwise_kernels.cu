@@ -1,0 +1,349 @@
+// elementwise_kernels.cu — the HBM-bound pieces either side of the solve: staging of matches, the
+// 16-parameter forward model (+ Jacobian), explicit least-squares reductions and the stand-alone
+// BFGS update.  One CTA per problem, threads over matches (coalesced), per-problem constants in
+// shared memory.
+//
+// Reference lines (relative to /root/reference/deep_attention_visual_odometry/):
+//   camera_model/distorted_camera_model.py:24-103,106-111   forward model
+//   camera_model/distorted_camera_model.py:114-385          Jacobian layout [B,2N,16] (values re-derived)
+//   solvers/least_squares_utils.py:16-48                    find_error / find_error_gradient
+//   autograd_solvers/bfgs_solver.py:217-233, 235-303        eq. 6.20 / eq. 6.17
+#include "davo_common.cuh"
+#include "launch.h"
+
+namespace davo {
+
+// R = Rz Ry Rx (distorted_camera_model.py:29-55) and optionally dR/drx, dR/dry, dR/drz.
+template <typename T>
+__device__ void euler_matrices(T rx, T ry, T rz, T* Rm, T* dRx, T* dRy, T* dRz) {
+    const T sx = sin(rx), cx = cos(rx), sy = sin(ry), cy = cos(ry), sz = sin(rz), cz = cos(rz);
+    Rm[0] = cy * cz; Rm[1] = sx * sy * cz - cx * sz; Rm[2] = cx * sy * cz + sx * sz;
+    Rm[3] = cy * sz; Rm[4] = sx * sy * sz + cx * cz; Rm[5] = cx * sy * sz - sx * cz;
+    Rm[6] = -sy;     Rm[7] = sx * cy;                Rm[8] = cx * cy;
+    if (dRx) {
+        dRx[0] = 0; dRx[1] = cx * sy * cz + sx * sz;  dRx[2] = -sx * sy * cz + cx * sz;
+        dRx[3] = 0; dRx[4] = cx * sy * sz - sx * cz;  dRx[5] = -sx * sy * sz - cx * cz;
+        dRx[6] = 0; dRx[7] = cx * cy;                 dRx[8] = -sx * cy;
+        dRy[0] = -sy * cz; dRy[1] = sx * cy * cz; dRy[2] = cx * cy * cz;
+        dRy[3] = -sy * sz; dRy[4] = sx * cy * sz; dRy[5] = cx * cy * sz;
+        dRy[6] = -cy;      dRy[7] = -sx * sy;     dRy[8] = -cx * sy;
+        dRz[0] = -cy * sz; dRz[1] = -sx * sy * sz - cx * cz; dRz[2] = -cx * sy * sz + sx * cz;
+        dRz[3] = cy * cz;  dRz[4] = sx * sy * cz - cx * sz;  dRz[5] = cx * sy * cz + sx * sz;
+        dRz[6] = 0; dRz[7] = 0; dRz[8] = 0;
+    }
+}
+
+// X' = R X + t with the reference's un-fused left-to-right sums; z' == 0 -> += 1e-8 (:38-57).
+template <typename T>
+__device__ __forceinline__ void transform_point(const T* Rm, const T* t, T X, T Y, T Z, T& xp, T& yp, T& zp) {
+    xp = add_rn(add_rn(add_rn(mul_rn(X, Rm[0]), mul_rn(Y, Rm[1])), mul_rn(Z, Rm[2])), t[0]);
+    yp = add_rn(add_rn(add_rn(mul_rn(X, Rm[3]), mul_rn(Y, Rm[4])), mul_rn(Z, Rm[5])), t[1]);
+    zp = add_rn(add_rn(add_rn(mul_rn(X, Rm[6]), mul_rn(Y, Rm[7])), mul_rn(Z, Rm[8])), t[2]);
+    if (zp == T(0)) zp += T(1e-8);
+}
+
+// ---- staging: {x'/z', y'/z', u*, v*} per match ---------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) stage_kernel(int B, int N, const T* __restrict__ pts,
+                                                    const T* __restrict__ obs, const T* __restrict__ pose,
+                                                    T* __restrict__ staged) {
+    using V4 = typename Vec4<T>::type;
+    __shared__ T Rm[9];
+    __shared__ T tr[3];
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (pose) {
+                const T* ps = pose + 6 * (size_t)b;
+                euler_matrices<T>(ps[0], ps[1], ps[2], Rm, nullptr, nullptr, nullptr);
+                tr[0] = ps[3]; tr[1] = ps[4]; tr[2] = ps[5];
+            } else {
+                euler_matrices<T>(T(0), T(0), T(0), Rm, nullptr, nullptr, nullptr);
+                tr[0] = tr[1] = tr[2] = T(0);
+            }
+        }
+        __syncthreads();
+        const T* P = pts + 3 * (size_t)b * N;
+        const T* O = obs + 2 * (size_t)b * N;
+        V4* S = reinterpret_cast<V4*>(staged) + (size_t)b * N;
+        for (int m = threadIdx.x; m < N; m += blockDim.x) {
+            T xp, yp, zp;
+            transform_point<T>(Rm, tr, P[3 * m], P[3 * m + 1], P[3 * m + 2], xp, yp, zp);
+            V4 out;
+            out.x = div_rn(xp, zp);
+            out.y = div_rn(yp, zp);
+            out.z = O[2 * m];
+            out.w = O[2 * m + 1];
+            S[m] = out;
+        }
+    }
+}
+
+template <typename T>
+int launch_stage(int B, int N, const T* pts, const T* obs, const T* pose, T* staged, cudaStream_t s) {
+    if (B == 0 || N == 0) return DAVO_OK;
+    const int grid = B < 148 * 64 ? B : 148 * 64;
+    stage_kernel<T><<<grid, 256, 0, s>>>(B, N, pts, obs, pose, staged);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+}
+template int launch_stage<float>(int, int, const float*, const float*, const float*, float*, cudaStream_t);
+template int launch_stage<double>(int, int, const double*, const double*, const double*, double*, cudaStream_t);
+
+// ---- 16-parameter forward model and Jacobian ------------------------------------------------------
+template <typename T, bool kJac>
+__global__ void __launch_bounds__(128) project_kernel(int B, int N, const T* __restrict__ pts,
+                                                      const T* __restrict__ th16, T* __restrict__ u_out,
+                                                      T* __restrict__ v_out, T* __restrict__ J) {
+    __shared__ T th[16];
+    __shared__ T Rm[9], dR[3][9];
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 16) th[threadIdx.x] = th16[16 * (size_t)b + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0)
+            euler_matrices<T>(th[DAVO_RX], th[DAVO_RY], th[DAVO_RZ], Rm, kJac ? dR[0] : nullptr, dR[1], dR[2]);
+        __syncthreads();
+        const T cx = th[0], cy = th[1], k1 = th[2], k2 = th[3], k3 = th[4], p1 = th[5], p2 = th[6], fx = th[7],
+                sk = th[8], fy = th[9];
+        for (int m = threadIdx.x; m < N; m += blockDim.x) {
+            const T* X = pts + 3 * ((size_t)b * N + m);
+            const T X0 = X[0], X1 = X[1], X2 = X[2];
+            T xp, yp, zp;
+            transform_point<T>(Rm, th + DAVO_TX, X0, X1, X2, xp, yp, zp);
+            // un-fused, in the reference's order, so the float32 forward agrees to the last bit or two
+            const T a = div_rn(xp, zp), bb = div_rn(yp, zp);
+            const T u = add_rn(mul_rn(fx, a), mul_rn(sk, bb));                   // :59-61
+            const T v = mul_rn(fy, bb);                                          // :62
+            const T r2 = add_rn(mul_rn(u, u), mul_rn(v, v));                     // :64
+            const T uv = mul_rn(u, v);                                           // :65
+            const T rad = add_rn(add_rn(add_rn(T(1), mul_rn(k1, r2)), mul_rn(mul_rn(k2, r2), r2)),
+                                 mul_rn(mul_rn(mul_rn(k3, r2), r2), r2));        // :66-74
+            const T A = add_rn(r2, mul_rn(mul_rn(T(2), u), u));
+            const T Bv = add_rn(r2, mul_rn(mul_rn(T(2), v), v));
+            const T up = add_rn(add_rn(add_rn(mul_rn(u, rad), mul_rn(mul_rn(T(2), p1), uv)), mul_rn(p2, A)), cx);
+            const T vp = add_rn(add_rn(add_rn(mul_rn(v, rad), mul_rn(mul_rn(T(2), p2), uv)), mul_rn(p1, Bv)), cy);
+            u_out[(size_t)b * N + m] = up;
+            v_out[(size_t)b * N + m] = vp;
+            if (kJac) {
+                const T r4 = r2 * r2, r6 = r4 * r2;
+                const T radp = k1 + T(2) * k2 * r2 + T(3) * k3 * r4;
+                const T Duu = rad + T(2) * u * u * radp + T(2) * p1 * v + T(6) * p2 * u;
+                const T Dvv = rad + T(2) * v * v * radp + T(6) * p1 * v + T(2) * p2 * u;
+                const T Duv = T(2) * uv * radp + T(2) * p1 * u + T(2) * p2 * v;
+                const T iz = T(1) / zp;
+                T ju[16], jv[16];
+                ju[0] = 1; jv[0] = 0;
+                ju[1] = 0; jv[1] = 1;
+                ju[2] = u * r2; jv[2] = v * r2;
+                ju[3] = u * r4; jv[3] = v * r4;
+                ju[4] = u * r6; jv[4] = v * r6;
+                ju[5] = T(2) * uv; jv[5] = Bv;
+                ju[6] = A; jv[6] = T(2) * uv;
+                ju[7] = Duu * a;  jv[7] = Duv * a;
+                ju[8] = Duu * bb; jv[8] = Duv * bb;
+                ju[9] = Duv * bb; jv[9] = Dvv * bb;
+                const T ux = Duu * fx * iz, uy = (Duu * sk + Duv * fy) * iz, uz = -(Duu * u + Duv * v) * iz;
+                const T vx = Duv * fx * iz, vy = (Duv * sk + Dvv * fy) * iz, vz = -(Duv * u + Dvv * v) * iz;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const T dX = dR[k][0] * X0 + dR[k][1] * X1 + dR[k][2] * X2;
+                    const T dY = dR[k][3] * X0 + dR[k][4] * X1 + dR[k][5] * X2;
+                    const T dZ = dR[k][6] * X0 + dR[k][7] * X1 + dR[k][8] * X2;
+                    ju[10 + k] = ux * dX + uy * dY + uz * dZ;
+                    jv[10 + k] = vx * dX + vy * dY + vz * dZ;
+                }
+                ju[13] = ux; ju[14] = uy; ju[15] = uz;
+                jv[13] = vx; jv[14] = vy; jv[15] = vz;
+                using V4 = typename Vec4<T>::type;
+                V4* Ju = reinterpret_cast<V4*>(J + 16 * ((size_t)b * 2 * N + m));          // rows 0..N-1: u'
+                V4* Jv = reinterpret_cast<V4*>(J + 16 * ((size_t)b * 2 * N + N + m));      // rows N..2N-1: v'
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    V4 a4, b4;
+                    a4.x = ju[4 * q]; a4.y = ju[4 * q + 1]; a4.z = ju[4 * q + 2]; a4.w = ju[4 * q + 3];
+                    b4.x = jv[4 * q]; b4.y = jv[4 * q + 1]; b4.z = jv[4 * q + 2]; b4.w = jv[4 * q + 3];
+                    Ju[q] = a4;
+                    Jv[q] = b4;
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+int launch_project(int B, int N, const T* pts, const T* th16, T* u, T* v, T* J, cudaStream_t s) {
+    if (B == 0 || N == 0) return DAVO_OK;
+    const int grid = B < 148 * 64 ? B : 148 * 64;
+    if (J) project_kernel<T, true><<<grid, 128, 0, s>>>(B, N, pts, th16, u, v, J);
+    else   project_kernel<T, false><<<grid, 128, 0, s>>>(B, N, pts, th16, u, v, nullptr);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+}
+template int launch_project<float>(int, int, const float*, const float*, float*, float*, float*, cudaStream_t);
+template int launch_project<double>(int, int, const double*, const double*, double*, double*, double*, cudaStream_t);
+
+// ---- explicit least squares: error[B] = sum w r^2, gradient[B,P] = sum 2 w r J --------------------
+constexpr int kLsqThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kLsqThreads) least_squares_kernel(int B, int R, int P, const T* __restrict__ res,
+                                                                    const T* __restrict__ jac,
+                                                                    const T* __restrict__ w, T* __restrict__ err,
+                                                                    T* __restrict__ grad) {
+    __shared__ T red[kLsqThreads];
+    const int t = threadIdx.x;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const T* r = res + (size_t)b * R;
+        const T* ww = w ? w + (size_t)b * R : nullptr;
+        if (err) {
+            T e = T(0);
+            for (int i = t; i < R; i += kLsqThreads) {
+                const T sq = r[i] * r[i];
+                e += ww ? ww[i] * sq : sq;                      // least_squares_utils.py:24-28
+            }
+            __syncthreads();
+            red[t] = e;
+            __syncthreads();
+            for (int s = kLsqThreads / 2; s > 0; s >>= 1) {
+                if (t < s) red[t] += red[t + s];
+                __syncthreads();
+            }
+            if (t == 0) err[b] = red[0];
+        }
+        if (grad && jac) {
+            // a thread keeps one parameter column: the stride over the flat [R,P] index is a multiple of P
+            for (int p0 = 0; p0 < P; p0 += kLsqThreads) {
+                const int Pc = (P - p0) < kLsqThreads ? (P - p0) : kLsqThreads;  // columns in this chunk
+                const int groups = kLsqThreads / Pc;
+                const int gi = t / Pc, pc = t % Pc;
+                T acc = T(0);
+                if (gi < groups) {
+                    const T* Jb = jac + (size_t)b * R * P + p0 + pc;
+                    for (int i = gi; i < R; i += groups) {
+                        T gr = T(2) * r[i];                     // :43
+                        if (ww) gr = ww[i] * gr;                // :44-45
+                        acc = fma_t(gr, Jb[(size_t)i * P], acc);
+                    }
+                }
+                __syncthreads();
+                red[t] = acc;
+                __syncthreads();
+                if (t < Pc) {
+                    T sum = T(0);
+                    for (int g2 = 0; g2 < groups; ++g2) sum += red[g2 * Pc + t];
+                    grad[(size_t)b * P + p0 + t] = sum;
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+int launch_least_squares(int B, int R, int P, const T* res, const T* jac, const T* w, T* err, T* grad,
+                         cudaStream_t s) {
+    if (B == 0) return DAVO_OK;
+    const int grid = B < 148 * 16 ? B : 148 * 16;
+    least_squares_kernel<T><<<grid, kLsqThreads, 0, s>>>(B, R, P, res, jac, w, err, grad);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+}
+template int launch_least_squares<float>(int, int, int, const float*, const float*, const float*, float*, float*, cudaStream_t);
+template int launch_least_squares<double>(int, int, int, const double*, const double*, const double*, double*, double*, cudaStream_t);
+
+// ---- stand-alone BFGS update: one warp per problem, H staged in shared memory ---------------------
+template <typename T>
+__global__ void __launch_bounds__(128) bfgs_update_kernel(int K, int n, T* __restrict__ H, const T* __restrict__ s_,
+                                                          const T* __restrict__ y_) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int ld = n + 1;  // padded row stride: a lane walking a row does not collide with its neighbours
+    T* base = reinterpret_cast<T*>(raw) + (size_t)warp * ((size_t)n * ld + 5 * (size_t)n);
+    T* Hs = base;
+    T* s = Hs + (size_t)n * ld;
+    T* y = s + n;
+    T* yH = y + n;
+    T* Hy = yH + n;
+    T* sr = Hy + n;
+    for (int b = blockIdx.x * warps + warp; b < K; b += gridDim.x * warps) {
+        T* Hg = H + (size_t)b * n * n;
+        __syncwarp();
+        for (int i = lane; i < n * n; i += 32) Hs[(i / n) * ld + (i % n)] = Hg[i];
+        for (int i = lane; i < n; i += 32) {
+            s[i] = s_[(size_t)b * n + i];
+            y[i] = y_[(size_t)b * n + i];
+        }
+        __syncwarp();
+        T c = T(0);                                           // func_inverse_curvature.py:8-11
+        for (int j = 0; j < n; ++j) c = add_rn(c, mul_rn(s[j], y[j]));
+        T rho = div_rn(T(1), c);
+        if (c <= T(0)) rho = T(0);
+        for (int j = lane; j < n; j += 32) {                  // y^T H, bfgs_solver.py:268-270
+            T a = T(0);
+            for (int i = 0; i < n; ++i) a = add_rn(a, mul_rn(y[i], Hs[i * ld + j]));
+            yH[j] = a;
+        }
+        for (int i = lane; i < n; i += 32) {                  // H y, :293-295
+            T a = T(0);
+            for (int j = 0; j < n; ++j) a = add_rn(a, mul_rn(Hs[i * ld + j], y[j]));
+            Hy[i] = a;
+            sr[i] = mul_rn(s[i], rho);                        // :277
+        }
+        __syncwarp();
+        T q = T(0);                                           // :271-274
+        for (int j = 0; j < n; ++j) q = add_rn(q, mul_rn(yH[j], mul_rn(y[j], rho)));
+        const T onepq = add_rn(T(1), q);
+        for (int e = lane; e < n * n; e += 32) {              // :278-303
+            const int i = e / n, j = e % n;
+            const T sop = mul_rn(mul_rn(sr[i], s[j]), onepq);
+            const T sgp = mul_rn(sr[i], yH[j]);
+            const T gsp = mul_rn(Hy[i], sr[j]);
+            Hg[e] = sub_rn(sub_rn(add_rn(Hs[i * ld + j], sop), sgp), gsp);
+        }
+    }
+}
+
+template <typename T>
+int launch_bfgs_update(int k, int n, T* H, const T* s_, const T* y, cudaStream_t s) {
+    if (k == 0) return DAVO_OK;
+    if (n < 1 || n > 96) return DAVO_ERR_UNSUPPORTED;
+    const size_t per_warp = ((size_t)n * (n + 1) + 5 * (size_t)n) * sizeof(T);
+    const int warps = (4 * per_warp <= 160 * 1024) ? 4 : 1;
+    const size_t smem = warps * per_warp;
+    auto kernel = bfgs_update_kernel<T>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DAVO_ERR_CUDA;
+    int grid = (k + warps - 1) / warps;
+    if (grid > 148 * 8) grid = 148 * 8;
+    kernel<<<grid, warps * 32, smem, s>>>(k, n, H, s_, y);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+}
+template int launch_bfgs_update<float>(int, int, float*, const float*, const float*, cudaStream_t);
+template int launch_bfgs_update<double>(int, int, double*, const double*, const double*, cudaStream_t);
+
+template <typename T>
+__global__ void bfgs_initial_scale_kernel(int K, int n, const T* __restrict__ s, const T* __restrict__ y,
+                                          T* __restrict__ scale) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= K) return;
+    T den = T(0), num = T(0);                                  // bfgs_solver.py:229-232
+    for (int j = 0; j < n; ++j) den = add_rn(den, mul_rn(y[(size_t)b * n + j], y[(size_t)b * n + j]));
+    den = (den < T(1e-5)) ? T(1e-5) : den;
+    for (int j = 0; j < n; ++j) num = add_rn(num, mul_rn(s[(size_t)b * n + j], y[(size_t)b * n + j]));
+    T sc = div_rn(num, den);
+    scale[b] = (sc < T(1e-4)) ? T(1e-4) : sc;
+}
+
+template <typename T>
+int launch_bfgs_initial_scale(int k, int n, const T* s_, const T* y, T* scale, cudaStream_t s) {
+    if (k == 0) return DAVO_OK;
+    bfgs_initial_scale_kernel<T><<<(k + 127) / 128, 128, 0, s>>>(k, n, s_, y, scale);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+}
+template int launch_bfgs_initial_scale<float>(int, int, const float*, const float*, float*, cudaStream_t);
+template int launch_bfgs_initial_scale<double>(int, int, const double*, const double*, double*, cudaStream_t);
+
+}  // namespace davo

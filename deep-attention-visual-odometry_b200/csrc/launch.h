@@ -1,0 +1,36 @@
+// launch.h — host-side launcher declarations shared by the .cu translation units and the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include "davo_common.cuh"
+
+namespace davo {
+
+void count_launch();  // increments the process-wide counter behind davo_launch_count()
+
+int launch_solve_warp_f32(const SolveParams<float>& p, cudaStream_t s);
+int launch_solve_warp_f64(const SolveParams<double>& p, cudaStream_t s);
+int launch_line_search_warp_f32(const SolveParams<float>& p, cudaStream_t s);
+int launch_line_search_warp_f64(const SolveParams<double>& p, cudaStream_t s);
+int launch_eval_warp_f32(const SolveParams<float>& p, cudaStream_t s);
+int launch_eval_warp_f64(const SolveParams<double>& p, cudaStream_t s);
+
+int launch_solve_joint_f32(const SolveParams<float>& p, cudaStream_t s);
+int launch_solve_joint_f64(const SolveParams<double>& p, cudaStream_t s);
+int launch_eval_joint_f32(const SolveParams<float>& p, cudaStream_t s);
+int launch_eval_joint_f64(const SolveParams<double>& p, cudaStream_t s);
+int launch_line_search_joint_f32(const SolveParams<float>& p, cudaStream_t s);
+int launch_line_search_joint_f64(const SolveParams<double>& p, cudaStream_t s);
+
+template <typename T>
+int launch_stage(int B, int N, const T* pts, const T* obs, const T* pose, T* staged, cudaStream_t s);
+template <typename T>
+int launch_project(int B, int N, const T* pts, const T* th16, T* u, T* v, T* J, cudaStream_t s);
+template <typename T>
+int launch_least_squares(int B, int R, int P, const T* res, const T* jac, const T* w, T* err, T* grad,
+                         cudaStream_t s);
+template <typename T>
+int launch_bfgs_update(int k, int n, T* H, const T* s_, const T* y, cudaStream_t s);
+template <typename T>
+int launch_bfgs_initial_scale(int k, int n, const T* s_, const T* y, T* scale, cudaStream_t s);
+
+}  // namespace davo

@@ -1,0 +1,129 @@
+// solve_kernels.cu — persistent warp-per-problem kernels (solve, line search, cost+gradient).
+//
+// Grid: resident CTAs per SM (occupancy query) x SM count, capped by the work available.  Each warp
+// pulls problem indices from an atomic counter in the caller's workspace, so a warp whose problem
+// retires early immediately starts the next one; warps never wait for each other (no CTA barrier
+// after set-up).
+#include "davo_common.cuh"
+#include "objectives.cuh"
+#include "solver_warp.cuh"
+#include "launch.h"
+
+namespace davo {
+
+constexpr int kWarpsPerCta = 4;
+
+template <typename T>
+__host__ __device__ constexpr size_t warp_lines_bytes() {
+    return 2 * kSlots * sizeof(T) + 16;  // trial-point line, broadcast line, mbarrier
+}
+
+template <typename T, typename Obj>
+__host__ __device__ inline size_t warp_smem_stride(int N, bool has_w) {
+    size_t b = Obj::slab_bytes(N, has_w) + warp_lines_bytes<T>();
+    return (b + 127) & ~size_t(127);
+}
+
+enum class Mode { kSolve, kLineSearch, kEval };
+
+template <typename T, int NP, typename Obj, Mode kMode>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) warp_problem_kernel(const SolveParams<T> p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned char* mine = smem + (size_t)warp * warp_smem_stride<T, Obj>(p.N, p.has_w != 0);
+    const size_t slab = Obj::slab_bytes(p.N, p.has_w != 0);
+    T* xt_line = reinterpret_cast<T*>(mine + slab);
+    T* bc_line = xt_line + kSlots;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(bc_line + kSlots);
+    if (Obj::kUsesSmemMatches) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+    }
+    Obj obj(p, mine, bar, lane);
+    const int n = p.n;
+    const int c = lane >> 1;
+    const bool own = c < n;
+    const unsigned total_warps = gridDim.x * kWarpsPerCta;
+    unsigned b_static = blockIdx.x * kWarpsPerCta + warp;
+    for (;;) {
+        unsigned b = 0;
+        if (kMode == Mode::kSolve) {  // iteration counts vary 10x between problems: dynamic queue
+            if (lane == 0) b = atomicAdd(p.queue, 1u);
+            b = __shfl_sync(kFull, b, 0);
+        } else {                      // uniform work per problem: static round-robin
+            b = b_static;
+            b_static += total_warps;
+        }
+        if (b >= (unsigned)p.B) break;
+        obj.bind((int)b);
+        if (kMode == Mode::kSolve) {
+            solve_one_warp<T, NP, Obj>(obj, p, (int)b, xt_line, bc_line, lane);
+        } else if (kMode == Mode::kLineSearch) {
+            const size_t o = (size_t)b * n + c;
+            const T x = own ? p.x0[o] : T(0);
+            const T d = own ? p.dir[o] : T(0);
+            const T g = own ? p.base_grad[o] : T(0);
+            const LineSearchResult<T> r = line_search_warp(obj, p, x, d, p.base_cost[b], g, xt_line, lane);
+            if (lane == 0) {
+                p.alpha_out[b] = r.alpha;
+                if (p.fevals_out) p.fevals_out[b] = r.probes;
+            }
+        } else {
+            const T x = own ? p.x0[(size_t)b * n + c] : T(0);
+            T f, g;
+            eval_at(obj, x, xt_line, lane, f, g);
+            if (lane == 0 && p.cost_out) p.cost_out[b] = f;
+            if (p.x_out && own && !(lane & 1)) p.x_out[(size_t)b * n + c] = g;  // x_out doubles as grad out
+        }
+    }
+}
+
+template <typename T, int NP, typename Obj, Mode kMode>
+static int launch_warp_kernel(const SolveParams<T>& p, cudaStream_t stream) {
+    auto kernel = warp_problem_kernel<T, NP, Obj, kMode>;
+    const size_t smem = warp_smem_stride<T, Obj>(p.N, p.has_w != 0) * kWarpsPerCta;
+    int dev = 0, sms = 0, max_optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;  // N too large for a warp-resident slab
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DAVO_ERR_CUDA;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerCta * 32, smem) != cudaSuccess ||
+        per_sm < 1)
+        return DAVO_ERR_CUDA;
+    long long grid = (long long)per_sm * sms;
+    const long long need = ((long long)p.B + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (kMode == Mode::kSolve && cudaMemsetAsync(p.queue, 0, sizeof(unsigned), stream) != cudaSuccess)
+        return DAVO_ERR_CUDA;
+    kernel<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+}
+
+template <typename T, Mode kMode>
+static int dispatch_model(const SolveParams<T>& p, cudaStream_t stream) {
+    if (p.model == DAVO_MODEL_DISTORT10) return launch_warp_kernel<T, 10, Distort10Objective<T>, kMode>(p, stream);
+    if (p.model >= DAVO_MODEL_SPHERE && p.model <= DAVO_MODEL_DISTANCE) {
+        if (p.n > kSlots) return DAVO_ERR_UNSUPPORTED;
+        return launch_warp_kernel<T, kSlots, AnalyticObjective<T>, kMode>(p, stream);
+    }
+    return DAVO_ERR_UNSUPPORTED;
+}
+
+int launch_solve_warp_f32(const SolveParams<float>& p, cudaStream_t s) { return dispatch_model<float, Mode::kSolve>(p, s); }
+int launch_solve_warp_f64(const SolveParams<double>& p, cudaStream_t s) { return dispatch_model<double, Mode::kSolve>(p, s); }
+int launch_line_search_warp_f32(const SolveParams<float>& p, cudaStream_t s) { return dispatch_model<float, Mode::kLineSearch>(p, s); }
+int launch_line_search_warp_f64(const SolveParams<double>& p, cudaStream_t s) { return dispatch_model<double, Mode::kLineSearch>(p, s); }
+int launch_eval_warp_f32(const SolveParams<float>& p, cudaStream_t s) { return dispatch_model<float, Mode::kEval>(p, s); }
+int launch_eval_warp_f64(const SolveParams<double>& p, cudaStream_t s) { return dispatch_model<double, Mode::kEval>(p, s); }
+
+}  // namespace davo

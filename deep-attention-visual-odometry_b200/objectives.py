@@ -1,0 +1,173 @@
+"""Objective descriptors: what the reference passes to BFGSSolver as a Python closure.
+
+The reference solver takes ``error_function(params[k,n], mask[(B..)]) -> err[k]`` and differentiates
+it with autograd (autograd_solvers/bfgs_solver.py:131-135).  A Python closure cannot run inside a
+CUDA kernel, so the B200 solver takes a *descriptor*: an object that owns the device buffers of the
+problem set and names the objective the kernels have compiled in.  A descriptor is also callable with
+the reference's convention (cost and its autograd gradient both come from the CUDA evaluator
+``davo_eval_cost_grad``), so the reference's own solver can drive it on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _to_device(t, dtype, device, non_blocking=True):
+    if t is None:
+        return None
+    t = torch.as_tensor(t)
+    return t.to(device=device, dtype=dtype, non_blocking=non_blocking).contiguous()
+
+
+class _EvalFunction(torch.autograd.Function):
+    """cost = objective(params) with d cost / d params from the analytic J^T r kernel."""
+
+    @staticmethod
+    def forward(ctx, params, objective, index):
+        cost, grad = objective.evaluate(params, index=index, want_grad=True)
+        ctx.save_for_backward(grad)
+        return cost
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad_out.unsqueeze(-1) * grad, None, None
+
+
+class CalibrationObjective:
+    """Base class: B independent problems of one compiled-in model."""
+
+    model: str = ""
+    views: int = 1
+
+    def __init__(self, batch_shape, n, N, dtype, device):
+        self.batch_shape = tuple(batch_shape)
+        self.B = 1
+        for s in self.batch_shape:
+            self.B *= int(s)
+        self.n, self.N, self.dtype, self.device = int(n), int(N), dtype, device
+        self.data0 = self.data1 = self.weights = None
+
+    # ---- what the solver needs -------------------------------------------------------------------
+    def desc(self, B=None, **kw) -> _lib.ProblemDesc:
+        return _lib.make_desc(self.B if B is None else B, self.N, self.views, self.n, self.model, self.dtype,
+                              has_weights=self.weights is not None, **kw)
+
+    def _select(self, index):
+        """Rows of the problem set for a subset of problems (the reference's `mask`)."""
+        if index is None:
+            return self.data0, self.data1, self.weights
+        pick = lambda t: None if t is None else t[index].contiguous()  # buffers are stored flat: [B, ...]
+        return pick(self.data0), pick(self.data1), pick(self.weights)
+
+    def evaluate(self, params: torch.Tensor, index=None, want_grad: bool = True):
+        """cost[k] (and grad[k,n]) for params[k,n] on the problems `index` (all when None)."""
+        _lib.require_cuda()
+        p = params.detach().to(device=self.device, dtype=self.dtype).reshape(-1, self.n).contiguous()
+        d0, d1, w = self._select(index)
+        k = p.shape[0]
+        cost = torch.empty(k, dtype=self.dtype, device=self.device)
+        grad = torch.empty(k, self.n, dtype=self.dtype, device=self.device) if want_grad else None
+        desc = self.desc(B=k)
+        st = _lib.lib().davo_eval_cost_grad(ctypes.byref(desc), _lib.ptr(d0), _lib.ptr(d1), _lib.ptr(w), _lib.ptr(p),
+                                            _lib.ptr(cost), _lib.ptr(grad), _lib.stream_ptr())
+        _lib.check(st, "davo_eval_cost_grad")
+        return cost, grad
+
+    # ---- the reference's calling convention ------------------------------------------------------
+    def __call__(self, params: torch.Tensor, mask: torch.Tensor | None = None) -> torch.Tensor:
+        index = None
+        if mask is not None and mask.numel() == self.B and mask.dtype == torch.bool:
+            index = mask.reshape(-1).to(self.device).nonzero(as_tuple=True)[0]
+        lead = params.shape[:-1]
+        out = _EvalFunction.apply(params.reshape(-1, self.n), self, index)
+        return out.reshape(lead).to(params.device)
+
+
+class DistortionObjective(CalibrationObjective):
+    """Fit (cx,cy,k1,k2,k3,p1,p2,fx,s,fy) of the 16-parameter camera model with the pose fixed.
+
+    error = sum_matches w * |compute_distorted_camera_model(points_3d, [x | pose]) - observed|^2
+    (camera_model/distorted_camera_model.py:24-111, solvers/least_squares_utils.py:4-28).  The
+    constructor runs ``davo_stage_matches`` once: {x'/z', y'/z', u*, v*} per match, 16 B in float32.
+
+    points_3d [(B..),N,3], observed_2d [(B..),N,2], pose [(B..),6]=(rx,ry,rz,tx,ty,tz) or None
+    (identity), weights [(B..),N] or None.  Host tensors are copied to the current CUDA device.
+    """
+
+    model = "distort10"
+
+    def __init__(self, points_3d, observed_2d, pose=None, weights=None, dtype=None, device=None):
+        device = _lib.require_cuda() if device is None else torch.device(device)
+        points_3d = torch.as_tensor(points_3d)
+        dtype = dtype or points_3d.dtype
+        batch_shape, N = points_3d.shape[:-2], points_3d.shape[-2]
+        super().__init__(batch_shape, 10, N, dtype, device)
+        if tuple(observed_2d.shape) != tuple(batch_shape) + (N, 2):
+            raise ValueError(f"observed_2d must be {tuple(batch_shape) + (N, 2)}, got {tuple(observed_2d.shape)}")
+        if points_3d.shape[-1] != 3:
+            raise ValueError("points_3d must end in a dimension of 3")
+        pts = _to_device(points_3d, dtype, device).reshape(self.B, N, 3)
+        obs = _to_device(observed_2d, dtype, device).reshape(self.B, N, 2)
+        ps = None if pose is None else _to_device(pose, dtype, device).reshape(self.B, 6)
+        self.weights = None if weights is None else _to_device(weights, dtype, device).reshape(self.B, N)
+        self.data0 = torch.empty(self.B, N, 4, dtype=dtype, device=device)
+        desc = self.desc()
+        with torch.cuda.device(device):
+            st = _lib.lib().davo_stage_matches(ctypes.byref(desc), _lib.ptr(pts), _lib.ptr(obs), _lib.ptr(ps),
+                                               _lib.ptr(self.data0), _lib.stream_ptr())
+        _lib.check(st, "davo_stage_matches")
+
+    @classmethod
+    def from_staged(cls, staged: torch.Tensor, weights=None):
+        """Wrap an already staged [(B..),N,4] device buffer (no copy)."""
+        self = cls.__new__(cls)
+        CalibrationObjective.__init__(self, staged.shape[:-2], 10, staged.shape[-2], staged.dtype, staged.device)
+        self.data0 = staged.contiguous().reshape(self.B, self.N, 4)
+        self.weights = None if weights is None else weights.to(staged.device, staged.dtype).reshape(self.B, self.N)
+        return self
+
+
+class JointPoseObjective(CalibrationObjective):
+    """Fit the 10 intrinsics plus (rx,ry,rz,tx,ty,tz) of each of V views: n = 10 + 6V.
+
+    points_3d [(B..),N,3] are world points shared by the views; observed_2d [(B..),V,N,2].
+    """
+
+    model = "joint"
+
+    def __init__(self, points_3d, observed_2d, weights=None, dtype=None, device=None):
+        device = _lib.require_cuda() if device is None else torch.device(device)
+        points_3d = torch.as_tensor(points_3d)
+        observed_2d = torch.as_tensor(observed_2d)
+        dtype = dtype or points_3d.dtype
+        batch_shape, N = points_3d.shape[:-2], points_3d.shape[-2]
+        V = observed_2d.shape[-3]
+        if tuple(observed_2d.shape) != tuple(batch_shape) + (V, N, 2):
+            raise ValueError(f"observed_2d must be {tuple(batch_shape) + (V, N, 2)}, got {tuple(observed_2d.shape)}")
+        super().__init__(batch_shape, 10 + 6 * V, N, dtype, device)
+        self.views = V
+        self.data0 = _to_device(points_3d, dtype, device).reshape(self.B, N, 3)
+        self.data1 = _to_device(observed_2d, dtype, device).reshape(self.B, V, N, 2)
+        self.weights = None if weights is None else _to_device(weights, dtype, device).reshape(self.B, V, N)
+
+
+class AnalyticObjective(CalibrationObjective):
+    """The reference's analytic test objectives (tests/autograd_solvers/reference_functions.py:20-62,
+    test_bfgs_solver.py:33-46, line_search/test_wolffe_conditions.py:214-305), compiled into the solver
+    so that the reference's solver tests can be mirrored on the GPU path."""
+
+    def __init__(self, name: str, batch_shape, n: int, dtype=torch.float32, target=None, device=None):
+        device = _lib.require_cuda() if device is None else torch.device(device)
+        if name not in _lib.MODEL_IDS or _lib.MODEL_IDS[name] < 16:
+            raise ValueError(f"unknown analytic objective {name!r}")
+        super().__init__(batch_shape, n, 0, dtype, device)
+        self.model = name
+        if name == "distance":
+            if target is None:
+                raise ValueError("the 'distance' objective needs a target")
+            self.data0 = _to_device(target, dtype, device).expand(self.batch_shape + (n,)).contiguous().reshape(self.B, n)

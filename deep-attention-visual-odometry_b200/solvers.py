@@ -1,0 +1,168 @@
+"""BFGSSolver and line_search_wolfe_conditions with the reference's signatures, executed by the
+persistent sm_100a solve kernel through the C-ABI (include/davo_b200.h).
+
+Reference: deep_attention_visual_odometry/autograd_solvers/bfgs_solver.py:26-303 and
+autograd_solvers/line_search/wolfe_conditions.py:23-253.
+"""
+from __future__ import annotations
+
+import ctypes
+import warnings
+from typing import NamedTuple
+
+import torch
+from torch.nn import Module
+
+from . import _lib
+from .objectives import CalibrationObjective
+
+
+class SolveInfo(NamedTuple):
+    """Per-problem outputs the reference keeps internal (north_star: 'cost and convergence mask out')."""
+
+    parameters: torch.Tensor  # (B..) x n
+    cost: torch.Tensor        # (B..)   objective at the returned parameters
+    converged: torch.Tensor   # (B..)   bool, cost <= error_threshold
+    iterations: torch.Tensor  # (B..)   int32, accepted steps (line searches taken part in)
+    evaluations: torch.Tensor # (B..)   int32, objective evaluations the reference would have made
+    reason: torch.Tensor      # (B..)   int32, 0 threshold / 1 step size / 2 iteration cap / 3 NaN cost
+
+
+def _require_descriptor(error_function) -> CalibrationObjective:
+    if not isinstance(error_function, CalibrationObjective):
+        raise TypeError(
+            "the B200 solver runs the objective inside a CUDA kernel and needs a CalibrationObjective "
+            "descriptor (DistortionObjective, JointPoseObjective, AnalyticObjective), not an arbitrary Python "
+            f"callable (got {type(error_function).__name__}); there is no CPU / autograd fallback")
+    return error_function
+
+
+class BFGSSolver(Module):
+    """Drop-in for the reference's BFGSSolver (autograd_solvers/bfgs_solver.py:26-78): same constructor
+    arguments and defaults, same ``forward(parameters, error_function) -> parameters`` contract, batch
+    dimensions ``(B..)`` of any rank.  ``error_function`` must be a CalibrationObjective descriptor.
+
+    Eval-mode semantics: the stochastic training-time behaviours (drop-path, return_second_last) and
+    differentiating through the solve are not implemented and raise NotImplementedError.
+    """
+
+    def __init__(self, sufficient_decrease: float = 1e-4, curvature: float = 0.9, error_threshold: float = 1e-4,
+                 iterations: int = 1000, minimum_step: float = 1e-8, drop_path_p: float = 0.1,
+                 return_second_last: bool = False, training_iterations: int = None,
+                 training_error_threshold: float = None):
+        super().__init__()
+        self.sufficient_decrease = float(sufficient_decrease)
+        self.curvature = float(curvature)
+        self.error_threshold = float(error_threshold)
+        self.iterations = int(iterations)
+        self.minimum_step = float(minimum_step)
+        self.drop_path_p = float(drop_path_p)
+        self.return_second_last = bool(return_second_last)
+        self.training_iterations = int(training_iterations) if training_iterations is not None else self.iterations
+        self.training_error_threshold = (float(training_error_threshold) if training_error_threshold is not None
+                                         else self.error_threshold)
+
+    def forward(self, parameters: torch.Tensor, error_function, return_info: bool = False):
+        obj = _require_descriptor(error_function)
+        if parameters.requires_grad:
+            raise NotImplementedError("differentiating through the solve (create_graph) is not implemented")
+        if self.training:
+            if self.drop_path_p > 0.0 or self.return_second_last:
+                raise NotImplementedError(
+                    "training-mode drop-path / return_second_last are not implemented: call .eval() "
+                    "(the reference's default training mode randomly retires 10% of problems per iteration)")
+            error_threshold, iterations = self.training_error_threshold, self.training_iterations
+        else:
+            error_threshold, iterations = self.error_threshold, self.iterations
+        if not 0.0 < self.sufficient_decrease < self.curvature < 1.0:  # wolfe_conditions.py:65-69
+            warnings.warn(f"Line search conditions should satisfy 0 < c1 < c2 < 1. "
+                          f"Got c1={self.sufficient_decrease} and c2={self.curvature}")
+        batch_shape, n = parameters.shape[:-1], parameters.shape[-1]
+        if n != obj.n:
+            raise ValueError(f"parameters have {n} columns, the objective expects {obj.n}")
+        if tuple(batch_shape) != obj.batch_shape and parameters.numel() // n != obj.B:
+            raise ValueError(f"parameters batch {tuple(batch_shape)} does not match the objective's {obj.batch_shape}")
+        device = _lib.require_cuda() if obj.device.type != "cuda" else obj.device
+        B = obj.B
+        with torch.cuda.device(device):
+            x0 = parameters.detach().to(device=device, dtype=obj.dtype, non_blocking=True).reshape(B, n).contiguous()
+            x = torch.empty_like(x0)
+            cost = torch.empty(B, dtype=obj.dtype, device=device)
+            converged = torch.empty(B, dtype=torch.uint8, device=device)
+            iters = torch.empty(B, dtype=torch.int32, device=device)
+            fevals = torch.empty(B, dtype=torch.int32, device=device)
+            reason = torch.empty(B, dtype=torch.int32, device=device)
+            workspace = torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+            desc = obj.desc(iterations=iterations, strong=True, sufficient_decrease=self.sufficient_decrease,
+                            curvature=self.curvature, error_threshold=error_threshold,
+                            minimum_step=self.minimum_step)
+            st = _lib.lib().davo_solve_calibration(
+                ctypes.byref(desc), _lib.ptr(obj.data0), _lib.ptr(obj.data1), _lib.ptr(obj.weights), _lib.ptr(x0),
+                _lib.ptr(x), _lib.ptr(cost), _lib.ptr(converged), _lib.ptr(iters), _lib.ptr(fevals),
+                _lib.ptr(reason), _lib.ptr(workspace), _lib.stream_ptr())
+        _lib.check(st, "davo_solve_calibration")
+        out_dev = parameters.device
+        result = x.reshape(parameters.shape).to(device=out_dev, dtype=parameters.dtype)
+        if not return_info:
+            return result
+        back = lambda t: t.reshape(batch_shape).to(out_dev)
+        return SolveInfo(result, back(cost), back(converged).bool(), back(iters), back(fevals), back(reason))
+
+    # ---- the two static helpers of the reference, on the GPU -----------------------------------------
+    @staticmethod
+    def scale_initial_inverse_hessian(step: torch.Tensor, delta_gradient: torch.Tensor) -> torch.Tensor:
+        """bfgs_solver.py:217-233 (eq. 6.20): max(s.y / max(y.y, 1e-5), 1e-4), shape (B..) x 1."""
+        device = _lib.require_cuda()
+        n = step.shape[-1]
+        dt = step.dtype
+        s = step.detach().to(device).reshape(-1, n).contiguous()
+        y = delta_gradient.detach().to(device=device, dtype=dt).reshape(-1, n).contiguous()
+        out = torch.empty(s.shape[0], dtype=dt, device=device)
+        st = _lib.lib().davo_bfgs_initial_scale(_lib.dtype_code(dt), s.shape[0], n, _lib.ptr(s), _lib.ptr(y),
+                                                _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(st, "davo_bfgs_initial_scale")
+        return out.reshape(step.shape[:-1] + (1,)).to(step.device)
+
+    @staticmethod
+    def update_inverse_hessian(inverse_hessian: torch.Tensor, step: torch.Tensor,
+                               delta_gradient: torch.Tensor) -> torch.Tensor:
+        """bfgs_solver.py:235-303 (eq. 6.17); non-positive curvature leaves H unchanged."""
+        device = _lib.require_cuda()
+        n = step.shape[-1]
+        dt = inverse_hessian.dtype
+        H = inverse_hessian.detach().to(device).reshape(-1, n, n).contiguous().clone()
+        s = step.detach().to(device=device, dtype=dt).reshape(-1, n).contiguous()
+        y = delta_gradient.detach().to(device=device, dtype=dt).reshape(-1, n).contiguous()
+        st = _lib.lib().davo_bfgs_update(_lib.dtype_code(dt), H.shape[0], n, _lib.ptr(H), _lib.ptr(s), _lib.ptr(y),
+                                         _lib.stream_ptr())
+        _lib.check(st, "davo_bfgs_update")
+        return H.reshape(inverse_hessian.shape).to(inverse_hessian.device)
+
+
+def line_search_wolfe_conditions(parameters: torch.Tensor, search_direction: torch.Tensor, base_error: torch.Tensor,
+                                 base_gradient: torch.Tensor, error_function, sufficient_decrease: float = 1e-4,
+                                 curvature: float = 0.9, strong: bool = False, return_probes: bool = False):
+    """Drop-in for autograd_solvers/line_search/wolfe_conditions.py:23-239: alpha of shape (B..)."""
+    obj = _require_descriptor(error_function)
+    if not 0.0 < sufficient_decrease < curvature < 1.0:
+        warnings.warn(f"Line search conditions should satisfy 0 < c1 < c2 < 1. "
+                      f"Got c1={sufficient_decrease} and c2={curvature}")
+    device = obj.device
+    n = parameters.shape[-1]
+    batch_shape = parameters.shape[:-1]
+    prep = lambda t, shape: t.detach().to(device=device, dtype=obj.dtype).reshape(shape).contiguous()
+    B = obj.B
+    with torch.cuda.device(device):
+        x, d, g = prep(parameters, (B, n)), prep(search_direction, (B, n)), prep(base_gradient, (B, n))
+        f0 = prep(base_error, (B,))
+        alpha = torch.empty(B, dtype=obj.dtype, device=device)
+        probes = torch.empty(B, dtype=torch.int32, device=device)
+        desc = obj.desc(strong=strong, sufficient_decrease=sufficient_decrease, curvature=curvature)
+        st = _lib.lib().davo_line_search(ctypes.byref(desc), _lib.ptr(obj.data0), _lib.ptr(obj.data1),
+                                         _lib.ptr(obj.weights), _lib.ptr(x), _lib.ptr(d), _lib.ptr(f0), _lib.ptr(g),
+                                         _lib.ptr(alpha), _lib.ptr(probes), _lib.stream_ptr())
+    _lib.check(st, "davo_line_search")
+    alpha = alpha.reshape(batch_shape).to(device=parameters.device, dtype=parameters.dtype)
+    if return_probes:
+        return alpha, probes.reshape(batch_shape).to(parameters.device)
+    return alpha

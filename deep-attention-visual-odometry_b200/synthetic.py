@@ -1,0 +1,203 @@
+"""Synthetic oracle-match generators for the BASELINE.json configurations (host side, numpy).
+
+The distributions follow SURVEY.md §8(d), which in turn follows the reference's generator
+(data/camera_and_parameters_dataset.py:48-61,85-94,147-151; that file does not parse at HEAD).
+Everything is generated in float64 with ``numpy.random.default_rng(seed)`` and rounded to the
+requested dtype at the end, so the float32 and float64 variants of one seed are the same problems.
+
+This is input generation for tests and bench.py, not part of the solve path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+import hashlib
+
+import numpy as np
+
+# index layout of the 16-parameter model (include/davo_b200.h, DAVO_CX..DAVO_TZ)
+CX, CY, K1, K2, K3, P1, P2, FX, S, FY, RX, RY, RZ, TX, TY, TZ = range(16)
+
+
+def euler_matrix(rx, ry, rz):
+    """R = Rz(rz) Ry(ry) Rx(rx), camera_model/distorted_camera_model.py:38-55.  Inputs [...]; output [...,3,3]."""
+    sx, cx = np.sin(rx), np.cos(rx)
+    sy, cy = np.sin(ry), np.cos(ry)
+    sz, cz = np.sin(rz), np.cos(rz)
+    rows = [
+        [cy * cz, sx * sy * cz - cx * sz, cx * sy * cz + sx * sz],
+        [cy * sz, sx * sy * sz + cx * cz, cx * sy * sz - sx * cz],
+        [-sy, sx * cy, cx * cy],
+    ]
+    return np.stack([np.stack(r, axis=-1) for r in rows], axis=-2)
+
+
+def forward_numpy(points_3d: np.ndarray, params16: np.ndarray):
+    """Float64 numpy statement of camera_model/distorted_camera_model.py:24-103, used only to make
+    noise-free observations.  points_3d [B,N,3], params16 [B,16] -> (u'[B,N], v'[B,N])."""
+    p = params16[:, None, :]
+    rot = euler_matrix(params16[:, RX], params16[:, RY], params16[:, RZ])  # [B,3,3]
+    xp = np.einsum("bij,bnj->bni", rot, points_3d) + params16[:, None, TX : TZ + 1]
+    z = xp[..., 2].copy()
+    z[z == 0] += 1e-8
+    a = xp[..., 0] / z
+    b = xp[..., 1] / z
+    u = p[..., FX] * a + p[..., S] * b
+    v = p[..., FY] * b
+    r2 = u * u + v * v
+    rad = 1.0 + p[..., K1] * r2 + p[..., K2] * r2 * r2 + p[..., K3] * r2 * r2 * r2
+    up = u * rad + 2.0 * p[..., P1] * u * v + p[..., P2] * (r2 + 2 * u * u) + p[..., CX]
+    vp = v * rad + 2.0 * p[..., P2] * u * v + p[..., P1] * (r2 + 2 * v * v) + p[..., CY]
+    return up, vp
+
+
+@dataclass
+class CalibrationBatch:
+    """One batch of independent calibration problems.
+
+    model "distort10": points_3d [B,N,3], obs [B,N,2], pose [B,6] fixed, x0/truth [B,10].
+    model "joint":     points_3d [B,N,3] world points shared by V views, obs [B,V,N,2],
+                       x0/truth [B,10+6V] = intrinsics then (rx,ry,rz,tx,ty,tz) per view.
+    """
+
+    model: str
+    points_3d: np.ndarray
+    obs: np.ndarray
+    pose: np.ndarray | None
+    x0: np.ndarray
+    truth: np.ndarray
+    views: int = 1
+
+    @property
+    def B(self) -> int:
+        return self.points_3d.shape[0]
+
+    @property
+    def N(self) -> int:
+        return self.points_3d.shape[1]
+
+    @property
+    def n(self) -> int:
+        return self.x0.shape[1]
+
+    def astype(self, dtype) -> "CalibrationBatch":
+        cast = lambda a: None if a is None else np.ascontiguousarray(a, dtype=dtype)
+        return CalibrationBatch(self.model, cast(self.points_3d), cast(self.obs), cast(self.pose),
+                                cast(self.x0), cast(self.truth), self.views)
+
+    def slice(self, lo: int, hi: int) -> "CalibrationBatch":
+        cut = lambda a: None if a is None else np.ascontiguousarray(a[lo:hi])
+        return CalibrationBatch(self.model, cut(self.points_3d), cut(self.obs), cut(self.pose),
+                                cut(self.x0), cut(self.truth), self.views)
+
+    def digest(self) -> str:
+        """sha256 over the float32 image of the inputs: golden fixtures store it so that a drifting
+        generator is detected instead of silently comparing different problems."""
+        h = hashlib.sha256()
+        for a in (self.points_3d, self.obs, self.pose, self.x0):
+            if a is not None:
+                h.update(np.ascontiguousarray(a, dtype=np.float32).tobytes())
+        return h.hexdigest()
+
+
+def _points(rng, B, N, fov):
+    z = np.abs(4.0 + rng.standard_normal((B, N))) + 1.0
+    xy = z[..., None] * fov * rng.uniform(-1.0, 1.0, size=(B, N, 2))
+    return np.concatenate([xy, z[..., None]], axis=-1)
+
+
+def _intrinsics(rng, B, k_scale=(0.05, 0.005, 0.0005), p_scale=0.005):
+    th = np.zeros((B, 10))
+    th[:, FX] = rng.uniform(1.0, 1.5, size=B)
+    th[:, FY] = th[:, FX] * (1.0 + 0.02 * rng.standard_normal(B))
+    th[:, CX] = np.clip(0.1 * rng.standard_normal(B), -0.5, 0.5)
+    th[:, CY] = np.clip(0.1 * rng.standard_normal(B), -0.5, 0.5)
+    th[:, K1] = k_scale[0] * rng.standard_normal(B)
+    th[:, K2] = k_scale[1] * rng.standard_normal(B)
+    th[:, K3] = k_scale[2] * rng.standard_normal(B)
+    th[:, P1] = p_scale * rng.standard_normal(B)
+    th[:, P2] = p_scale * rng.standard_normal(B)
+    return th
+
+
+def make_distort10(B: int, N: int = 256, seed: int = 0xB200, dtype=np.float32, fov: float = 0.5,
+                   noise: float = 0.0, ill_conditioned: bool = False, pathological: float = 0.0,
+                   random_pose: bool = False) -> CalibrationBatch:
+    """BASELINE.json configs 2, 4 and 5.
+
+    ill_conditioned=True is config 4: heavy distortion, doubled field of view and a start focal
+    length off by a log-uniform factor in [0.3, 3]; ``pathological`` is the fraction of problems that
+    additionally get points at z -> 0+ (first half) or an ascent-inducing start (second half).
+    """
+    rng = np.random.default_rng(seed)
+    if ill_conditioned:
+        fov = 1.0 if fov == 0.5 else fov
+        truth = _intrinsics(rng, B, k_scale=(0.5, 0.2, 0.1), p_scale=0.05)
+    else:
+        truth = _intrinsics(rng, B)
+    pts = _points(rng, B, N, fov)
+    pose = np.zeros((B, 6))
+    if random_pose:
+        pose[:, :3] = 0.2 * rng.standard_normal((B, 3))
+        pose[:, 3:] = 0.3 * rng.standard_normal((B, 3))
+    x0 = np.zeros((B, 10))
+    if ill_conditioned:
+        f0 = truth[:, FX] * np.exp(rng.uniform(np.log(0.3), np.log(3.0), size=B))
+    else:
+        f0 = truth[:, FX] * (1.0 + 0.2 * rng.uniform(-1.0, 1.0, size=B))
+    x0[:, FX] = f0
+    x0[:, FY] = f0
+    n_path = int(round(pathological * B))
+    if n_path:
+        idx = rng.permutation(B)[:n_path]
+        near, ascent = idx[: n_path // 2], idx[n_path // 2 :]
+        # a handful of points a hair in front of the camera plane: huge a,b -> overflow / NaN paths
+        pts[near[:, None], np.arange(4)[None, :], 2] = 1e-6
+        # a start on the far side of a pole of the radial polynomial: first directions are poor
+        x0[ascent, K1] = 5.0
+        x0[ascent, FX] *= -1.0
+    full = np.concatenate([truth, pose], axis=1)
+    up, vp = forward_numpy(pts, full)
+    obs = np.stack([up, vp], axis=-1)
+    if noise > 0.0:
+        obs = obs + noise * rng.standard_normal(obs.shape)
+    return CalibrationBatch("distort10", pts, obs, pose, x0, truth, 1).astype(dtype)
+
+
+def make_joint(B: int, N: int = 256, V: int = 4, seed: int = 0xB200, dtype=np.float32,
+               fov: float = 0.5, noise: float = 0.0) -> CalibrationBatch:
+    """BASELINE.json config 3: intrinsics + a 6-DoF pose per view, V views of N shared world points."""
+    rng = np.random.default_rng(seed)
+    intr = _intrinsics(rng, B)
+    pts = _points(rng, B, N, fov)
+    poses = np.concatenate([0.2 * rng.standard_normal((B, V, 3)), 0.3 * rng.standard_normal((B, V, 3))], axis=-1)
+    obs = np.empty((B, V, N, 2))
+    for v in range(V):
+        full = np.concatenate([intr, poses[:, v]], axis=1)
+        up, vp = forward_numpy(pts, full)
+        obs[:, v, :, 0] = up
+        obs[:, v, :, 1] = vp
+    if noise > 0.0:
+        obs = obs + noise * rng.standard_normal(obs.shape)
+    x0 = np.zeros((B, 10 + 6 * V))
+    f0 = intr[:, FX] * (1.0 + 0.2 * rng.uniform(-1.0, 1.0, size=B))
+    x0[:, FX] = f0
+    x0[:, FY] = f0
+    start = poses.copy()
+    start[..., :3] += 0.05 * rng.standard_normal((B, V, 3))
+    start[..., 3:] += 0.1 * rng.standard_normal((B, V, 3))
+    x0[:, 10:] = start.reshape(B, 6 * V)
+    truth = np.concatenate([intr, poses.reshape(B, 6 * V)], axis=1)
+    return CalibrationBatch("joint", pts, obs, None, x0, truth, V).astype(dtype)
+
+
+def stage_numpy(batch: CalibrationBatch) -> np.ndarray:
+    """Host statement of davo_stage_matches for tests: [B,N,4] = {x'/z', y'/z', u*, v*} in float64."""
+    assert batch.model == "distort10"
+    pts = batch.points_3d.astype(np.float64)
+    pose = np.zeros((batch.B, 6)) if batch.pose is None else batch.pose.astype(np.float64)
+    rot = euler_matrix(pose[:, 0], pose[:, 1], pose[:, 2])
+    xp = np.einsum("bij,bnj->bni", rot, pts) + pose[:, None, 3:]
+    z = xp[..., 2].copy()
+    z[z == 0] += 1e-8
+    return np.stack([xp[..., 0] / z, xp[..., 1] / z, batch.obs[..., 0].astype(np.float64),
+                     batch.obs[..., 1].astype(np.float64)], axis=-1)

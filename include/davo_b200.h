@@ -1,0 +1,192 @@
+/*
+ * davo_b200.h — C-ABI of the B200-native batched calibration solve.
+ *
+ * This is the drop-in boundary for ONE hot path of jskinn/deep-attention-visual-odometry:
+ * the batched BFGS + strong-Wolfe fit of pinhole intrinsics and radial/tangential
+ * distortion.  The reference has no FFI of its own (it is pure Python/PyTorch), so each
+ * entry point below names the reference Python symbol it replaces (path:line relative to
+ * /root/reference/deep_attention_visual_odometry/).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every data pointer is DEVICE memory owned by the
+ *    caller (PyTorch passes tensor.data_ptr()); the library allocates nothing persistent.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All calls are
+ *    asynchronous with respect to the host and stream-ordered.
+ *  - `dtype` in the descriptor selects the arithmetic type of every data pointer
+ *    (DAVO_F32 / DAVO_F64); integer outputs are int32_t / uint8_t in both cases.
+ *  - return value: DAVO_OK (0) or a negative davo_status; never throws, never aborts.
+ *  - thread-safe and re-entrant (no hidden globals).
+ */
+#ifndef DAVO_B200_H
+#define DAVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAVO_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------------------- */
+typedef enum davo_status {
+    DAVO_OK = 0,
+    DAVO_ERR_NULL_POINTER = -1,
+    DAVO_ERR_BAD_SHAPE = -2,      /* B,N,V,n inconsistent with the model              */
+    DAVO_ERR_UNSUPPORTED = -3,    /* model / n / N / dtype outside what is compiled in */
+    DAVO_ERR_MISALIGNED = -4,     /* a vector-loaded buffer is not 16-byte aligned     */
+    DAVO_ERR_CUDA = -5,           /* launch or runtime error (see cudaGetLastError)    */
+    DAVO_ERR_BAD_ARGUMENT = -6
+} davo_status;
+
+/* ---- arithmetic type ----------------------------------------------------------------- */
+#define DAVO_F32 0
+#define DAVO_F64 1
+
+/* ---- objective models ----------------------------------------------------------------
+ * DISTORT10: fit (cx,cy,k1,k2,k3,p1,p2,fx,s,fy) with the camera pose fixed.
+ *            camera_model/distorted_camera_model.py:24-103 with columns 10..15 constant.
+ *            data0 = staged matches [B,N,4] = {a=x'/z', b=y'/z', u*, v*}; data1 unused.
+ * JOINT:     fit the 10 intrinsics + (rx,ry,rz,tx,ty,tz) for each of V views, n = 10+6V.
+ *            data0 = world points [B,N,3] (shared by the V views);
+ *            data1 = observations [B,V,N,2].
+ * The analytic models restate tests/autograd_solvers/reference_functions.py:20-62 and
+ * tests/autograd_solvers/test_bfgs_solver.py:33-46 so that the reference's solver tests
+ * can be mirrored through this ABI (data0/data1 unused).
+ */
+#define DAVO_MODEL_DISTORT10 0
+#define DAVO_MODEL_JOINT 1
+#define DAVO_MODEL_SPHERE 16        /* sum x^2                                   */
+#define DAVO_MODEL_SPHERE_OFFSET 17 /* sum x^2 + 10                              */
+#define DAVO_MODEL_LOG_SPHERE 18    /* log(1 + sum x^2)                          */
+#define DAVO_MODEL_ROSENBROCK 19    /* (1-x)^2 + 100 (y-x^2)^2, n = 2            */
+#define DAVO_MODEL_COSINE 20        /* (1 - x0/|x|) + (1-|x|)^2                  */
+#define DAVO_MODEL_X2_SINE 21       /* |x|^2 (sin|x| + 2)                        */
+#define DAVO_MODEL_DISTANCE 22      /* |x - target|, data0 = target [B,n]
+                                       (tests/autograd_solvers/line_search/test_wolffe_conditions.py:214-305) */
+
+/* Parameter index layout of the 16-parameter camera model (spatial_maths.camera_model_parameters,
+ * pinned by tests/camera_model/test_distorted_camera_model.py:13-30 and the Jacobian column
+ * order camera_model/distorted_camera_model.py:364-383). */
+#define DAVO_CX 0
+#define DAVO_CY 1
+#define DAVO_K1 2
+#define DAVO_K2 3
+#define DAVO_K3 4
+#define DAVO_P1 5
+#define DAVO_P2 6
+#define DAVO_FX 7
+#define DAVO_S 8
+#define DAVO_FY 9
+#define DAVO_RX 10
+#define DAVO_RY 11
+#define DAVO_RZ 12
+#define DAVO_TX 13
+#define DAVO_TY 14
+#define DAVO_TZ 15
+
+/* ---- termination reason (per problem) ------------------------------------------------- */
+#define DAVO_REASON_THRESHOLD 0 /* cost <= error_threshold      (bfgs_solver.py:143)            */
+#define DAVO_REASON_STEP 1      /* |step| <= minimum_step       (bfgs_solver.py:203-207)        */
+#define DAVO_REASON_CAP 2       /* `iterations` outer iterations (bfgs_solver.py:118)           */
+#define DAVO_REASON_NAN 3       /* cost is NaN: `NaN > thr` is false, the reference retires it  */
+
+/* ---- problem descriptor ---------------------------------------------------------------
+ * Mirrors BFGSSolver.__init__ (autograd_solvers/bfgs_solver.py:49-60) and the arguments of
+ * line_search_wolfe_conditions (autograd_solvers/line_search/wolfe_conditions.py:23-32). */
+typedef struct davo_problem_desc {
+    int32_t B;            /* independent problems                                           */
+    int32_t N;            /* matches per problem per view                                   */
+    int32_t V;            /* views (1 for DISTORT10 and the analytic models)                */
+    int32_t n;            /* fitted parameters per problem                                  */
+    int32_t model;        /* DAVO_MODEL_*                                                   */
+    int32_t dtype;        /* DAVO_F32 | DAVO_F64                                            */
+    int32_t max_iters;    /* `iterations`, default 1000                                     */
+    int32_t max_ls_iters; /* line-search probe cap, 1000 in the reference (wolfe_conditions.py:116) */
+    int32_t strong;       /* 1 = strong Wolfe (what BFGSSolver passes, bfgs_solver.py:189)  */
+    int32_t has_weights;  /* 1 = `weights` [B,V,N] multiplies each squared residual pair    */
+    double sufficient_decrease; /* c1, default 1e-4                                         */
+    double curvature;           /* c2, default 0.9                                          */
+    double error_threshold;     /* default 1e-4                                             */
+    double minimum_step;        /* default 1e-8                                             */
+} davo_problem_desc;
+
+/* Bytes of caller-owned scratch every solve / line-search call needs (work-queue counter). */
+#define DAVO_WORKSPACE_BYTES 256
+
+int davo_abi_version(void);
+const char* davo_strerror(int status);
+
+/* Replaces BFGSSolver.forward in eval mode (autograd_solvers/bfgs_solver.py:80-215) driving the
+ * strong-Wolfe line search (autograd_solvers/line_search/wolfe_conditions.py:23-239) on the
+ * objective selected by desc->model.  One persistent launch; problems are pulled from an
+ * atomic work queue in `workspace`.
+ *   x0        [B,n]   initial parameters
+ *   x_out     [B,n]   fitted parameters (last accepted iterate; may alias x0)
+ *   cost_out  [B]     objective at x_out
+ *   converged_out [B] 1 where cost <= error_threshold
+ *   iters_out [B]     accepted steps (= line searches the problem took part in)
+ *   fevals_out[B]     objective evaluations the reference would have made
+ *   reason_out[B]     DAVO_REASON_* (may be NULL)
+ * Output pointers are written for all B rows. */
+int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, const void* data1,
+                           const void* weights, const void* x0, void* x_out, void* cost_out,
+                           uint8_t* converged_out, int32_t* iters_out, int32_t* fevals_out,
+                           int32_t* reason_out, void* workspace, void* stream);
+
+/* One evaluation of the objective and its gradient for every problem: cost[B], grad[B,n]
+ * (grad may be NULL).  Replaces `error_function(...)` + torch.autograd.grad
+ * (bfgs_solver.py:131-135) == find_error / find_error_gradient
+ * (solvers/least_squares_utils.py:16-48) on the camera-model residuals. */
+int davo_eval_cost_grad(const davo_problem_desc* desc, const void* data0, const void* data1,
+                        const void* weights, const void* x, void* cost, void* grad, void* stream);
+
+/* Replaces line_search_wolfe_conditions (wolfe_conditions.py:23-239) for every problem:
+ * alpha_out[B]; fevals_out[B] (probes made, may be NULL). */
+int davo_line_search(const davo_problem_desc* desc, const void* data0, const void* data1,
+                     const void* weights, const void* x, const void* direction,
+                     const void* base_cost, const void* base_grad, void* alpha_out,
+                     int32_t* fevals_out, void* stream);
+
+/* Stage matches for DISTORT10: rotate/translate points_3d[B,N,3] by the fixed pose
+ * pose[B,6]=(rx,ry,rz,tx,ty,tz) (NULL = identity), divide by z' (z'==0 -> +1e-8,
+ * distorted_camera_model.py:57) and interleave with obs[B,N,2] into staged[B,N,4]. */
+int davo_stage_matches(const davo_problem_desc* desc, const void* points_3d, const void* obs,
+                       const void* pose, void* staged, void* stream);
+
+/* compute_distorted_camera_model (distorted_camera_model.py:106-111):
+ * points_3d[B,N,3], params16[B,16] -> u[B,N], v[B,N]. */
+int davo_project(const davo_problem_desc* desc, const void* points_3d, const void* params16,
+                 void* u, void* v, void* stream);
+
+/* compute_distorted_camera_model_and_jacobian (distorted_camera_model.py:114-385):
+ * additionally J[B,2N,16], rows 0..N-1 = du'/dtheta, N..2N-1 = dv'/dtheta, derived from the
+ * forward model (the reference's hand-written columns fx,s,fy,tx,ty,rx,ry,rz are wrong; see
+ * DESIGN.md). */
+int davo_project_jacobian(const davo_problem_desc* desc, const void* points_3d,
+                          const void* params16, void* J, void* u, void* v, void* stream);
+
+/* find_error / find_error_gradient (solvers/least_squares_utils.py:16-48) on explicit
+ * residuals[B,R] and jacobian[B,R,P] with optional per-residual weights[B,R]:
+ * error[B] = sum w r^2, gradient[B,P] = sum 2 w r J.  jacobian/gradient may be NULL. */
+int davo_least_squares(int32_t dtype, int32_t B, int32_t R, int32_t P, const void* residuals,
+                       const void* jacobian, const void* weights, void* error, void* gradient,
+                       void* stream);
+
+/* BFGSSolver.update_inverse_hessian (bfgs_solver.py:235-303) in place on H[k,n,n] with
+ * s[k,n], y[k,n]; curvature y.s <= 0 leaves H untouched (utils/func_inverse_curvature.py:8-11). */
+int davo_bfgs_update(int32_t dtype, int32_t k, int32_t n, void* H, const void* s, const void* y,
+                     void* stream);
+
+/* BFGSSolver.scale_initial_inverse_hessian (bfgs_solver.py:217-233): scale[k]. */
+int davo_bfgs_initial_scale(int32_t dtype, int32_t k, int32_t n, const void* s, const void* y,
+                            void* scale, void* stream);
+
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t davo_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAVO_B200_H */

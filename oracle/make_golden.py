@@ -1,0 +1,207 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference — TEST INFRASTRUCTURE, build container only.
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden [--only NAME ...]
+
+Every fixture is an output of the reference's own code (ref_harness.py says which functions) on
+inputs produced by davo_b200.synthetic from a seed (large cases: only the seed, the generator
+arguments and a sha256 of the inputs are stored) or stored verbatim (small cases).  The GPU box has
+no /root/reference; tests there compare against these files.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import davo_b200  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+
+syn = davo_b200.synthetic
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# name -> (generator, generator kwargs, torch dtype, solver kwargs)
+SOLVE_CASES = {
+    # gate G64: float64 against the float64 reference
+    "solve_cfg2_f64": ("make_distort10", dict(B=1024, N=256, seed=0xB200), "float64",
+                       dict(error_threshold=1e-12, iterations=1000)),
+    # gate G32: float32 at a threshold every problem reaches before the fp32 noise floor
+    "solve_cfg2_f32": ("make_distort10", dict(B=1024, N=256, seed=0xB200), "float32",
+                       dict(error_threshold=1e-5, iterations=1000)),
+    # the driver's eval threshold (networks/calibration_network.py:44): chaotic in fp32, kept for the record
+    "solve_cfg2_f32_thr1e-7": ("make_distort10", dict(B=256, N=256, seed=0xB200), "float32",
+                               dict(error_threshold=1e-7, iterations=1000)),
+    # noisy observations: optimum cost ~ 2 N sigma^2, retire on step size / cap
+    "solve_cfg2_noisy_f64": ("make_distort10", dict(B=256, N=256, seed=0xB201, noise=1e-3), "float64",
+                             dict(error_threshold=1e-12, iterations=300)),
+    "solve_cfg2_pose_f64": ("make_distort10", dict(B=128, N=96, seed=0xB202, random_pose=True), "float64",
+                            dict(error_threshold=1e-12, iterations=1000)),
+    "solve_cfg3_f64": ("make_joint", dict(B=384, N=256, V=4, seed=0xB200), "float64",
+                       dict(error_threshold=1e-10, iterations=1000)),
+    "solve_cfg3_f32": ("make_joint", dict(B=384, N=256, V=4, seed=0xB200), "float32",
+                       dict(error_threshold=1e-5, iterations=1000)),
+    "solve_cfg3_small_f64": ("make_joint", dict(B=64, N=40, V=2, seed=0xB203), "float64",
+                             dict(error_threshold=1e-10, iterations=1000)),
+    "solve_cfg4_f64": ("make_distort10", dict(B=384, N=256, seed=0xB204, ill_conditioned=True, pathological=0.02),
+                       "float64", dict(error_threshold=1e-10, iterations=1000)),
+    "solve_cfg4_f32": ("make_distort10", dict(B=384, N=256, seed=0xB204, ill_conditioned=True, pathological=0.02),
+                       "float32", dict(error_threshold=1e-5, iterations=1000)),
+}
+
+
+def _save(name, **arrays):
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"  wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB)", flush=True)
+
+
+def gen_solve(name):
+    gen, gkw, dt, skw = SOLVE_CASES[name]
+    np_dt = np.float64 if dt == "float64" else np.float32
+    batch = getattr(syn, gen)(dtype=np_dt, **gkw)
+    obj = rh.make_objective(batch, getattr(torch, dt))
+    t = time.time()
+    r = rh.reference_solve(obj, torch.as_tensor(batch.x0), **skw)
+    dt_s = time.time() - t
+    print(f"  {name}: reference {dt_s:.1f}s, {batch.B / dt_s:.1f} solves/s, iters mean {r['iters'].mean():.1f}, "
+          f"fevals mean {r['fevals'].mean():.1f}, reasons {np.bincount(r['reason'], minlength=4)}", flush=True)
+    meta = dict(generator=gen, generator_kwargs=gkw, dtype=dt, solver_kwargs=skw, digest=batch.digest(),
+                reference_seconds=dt_s, reference_threads=torch.get_num_threads(), torch=torch.__version__)
+    _save(name, meta=json.dumps(meta), x=r["x"], cost=r["cost"], iters=r["iters"], fevals=r["fevals"],
+          reason=r["reason"], converged=r["converged"])
+
+
+def gen_camera_model():
+    rng = np.random.default_rng(11)
+    B, N = 6, 12
+    pts = syn._points(rng, B, N, 0.7)
+    th = np.concatenate([syn._intrinsics(rng, B, k_scale=(0.1, 0.02, 0.004), p_scale=0.02),
+                         0.3 * rng.standard_normal((B, 3)), 0.3 * rng.standard_normal((B, 3))], axis=1)
+    th[:, syn.S] = 0.05 * rng.standard_normal(B)
+    pts[0, 0] = [0.3, -0.2, 0.0]  # with t_z = 0 and no rotation this hits the z' == 0 guard (:57)
+    th[0, 10:] = 0.0
+    u, v = rh.reference_project(torch.tensor(pts), torch.tensor(th))
+    J = rh.reference_project_autograd_jacobian(torch.tensor(pts[1:]), torch.tensor(th[1:]))
+    u32, v32 = rh.reference_project(torch.tensor(pts, dtype=torch.float32), torch.tensor(th, dtype=torch.float32))
+    # cost + gradient of both calibration objectives by autograd of the reference forward
+    b = syn.make_distort10(16, 48, seed=21, dtype=np.float64, random_pose=True)
+    x = b.x0 + 0.01 * rng.standard_normal(b.x0.shape)
+    f, g = rh.reference_cost_grad(rh.make_objective(b), torch.tensor(x))
+    j = syn.make_joint(8, 24, 3, seed=22, dtype=np.float64)
+    xj = j.x0 + 0.01 * rng.standard_normal(j.x0.shape)
+    fj, gj = rh.reference_cost_grad(rh.make_objective(j), torch.tensor(xj))
+    _save("camera_model", points_3d=pts, params16=th, u=u, v=v, u32=u32, v32=v32, J_autograd=J,
+          d10_points=b.points_3d, d10_obs=b.obs, d10_pose=b.pose, d10_x=x, d10_cost=f, d10_grad=g,
+          joint_points=j.points_3d, joint_obs=j.obs, joint_x=xj, joint_cost=fj, joint_grad=gj)
+
+
+def gen_bfgs_update():
+    rng = np.random.default_rng(12)
+    out = {}
+    for n in (3, 10, 34):
+        k = 8
+        A = rng.standard_normal((k, n, n))
+        H = A @ A.transpose(0, 2, 1) / n + np.eye(n)
+        s = rng.standard_normal((k, n))
+        y = np.einsum("ki,kij->kj", s, H) + 0.3 * rng.standard_normal((k, n))  # mostly positive curvature
+        y[0] = -s[0]  # negative curvature: update skipped
+        y[1] = 0.0    # zero curvature: update skipped
+        out[f"H{n}"], out[f"s{n}"], out[f"y{n}"] = H, s, y
+        out[f"Hout{n}"] = rh.reference_bfgs_update(torch.tensor(H), torch.tensor(s), torch.tensor(y))
+        out[f"scale{n}"] = rh.reference_initial_scale(torch.tensor(s), torch.tensor(y))
+        out[f"Hout{n}_f32"] = rh.reference_bfgs_update(*[torch.tensor(a, dtype=torch.float32) for a in (H, s, y)])
+    # the literal known-answer vectors of tests/autograd_solvers/test_bfgs_solver.py:307-332
+    s = np.array([[-1.26262069, -0.78272035, 0.98543104]])
+    y = np.array([[0.15339519, -0.28944666, 0.54194925]])
+    H = np.array([[[2.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 3.0]]])
+    out["kat_s"], out["kat_y"], out["kat_H"] = s, y, H
+    out["kat_Hout"] = rh.reference_bfgs_update(torch.tensor(H), torch.tensor(s), torch.tensor(y))
+    _save("bfgs_update", **out)
+
+
+def gen_line_search():
+    rng = np.random.default_rng(13)
+    out = {}
+    # (a) the reference tests' |x - target| cases, tests/autograd_solvers/line_search/test_wolffe_conditions.py:214-305
+    targets = np.array([[1.0, 1.0], [10.0, 10.0], [0.25, 0.25], [-9.7, 2.2]])
+    dirs = np.array([[10.0, 0.0], [0.2, 0.1], [1.0, 1.0], [1.0, 0.0]])
+    for dt in ("float32", "float64"):
+        tdt = getattr(torch, dt)
+        tg = torch.tensor(targets, dtype=tdt)
+
+        def dist(x, mask, tg=tg):
+            return torch.linalg.vector_norm(x - tg[mask.reshape(-1)], dim=-1)
+
+        for strong in (False, True):
+            a, p, f0, g = rh.reference_line_search(dist, torch.zeros(4, 2, dtype=tdt), torch.tensor(dirs, dtype=tdt),
+                                                   strong=strong)
+            out[f"dist_alpha_{dt}_{int(strong)}"], out[f"dist_probes_{dt}_{int(strong)}"] = a, p
+    out["dist_targets"], out["dist_dirs"] = targets, dirs
+    # (b) analytic objectives from random points along random (mostly descent) directions, c1=.1, c2=.6 as in :152-211
+    for name, n in (("sphere", 4), ("log_sphere", 3), ("rosenbrock", 2), ("cosine", 4), ("x2_sine", 2)):
+        x = rng.normal(0.0, 2.0, size=(24, n))
+        f0, g = rh.reference_cost_grad(rh.ANALYTIC[name], torch.tensor(x))
+        d = -g * rng.uniform(0.01, 3.0, size=(24, 1)) + 0.05 * rng.standard_normal((24, n))
+        out[f"{name}_x"], out[f"{name}_d"] = x, d
+        for strong in (False, True):
+            a, p, _, _ = rh.reference_line_search(rh.ANALYTIC[name], torch.tensor(x), torch.tensor(d),
+                                                  sufficient_decrease=0.1, curvature=0.6, strong=strong)
+            out[f"{name}_alpha_{int(strong)}"], out[f"{name}_probes_{int(strong)}"] = a, p
+    # (c) the calibration objective, default c1/c2, steepest descent and a scaled-up direction
+    b = syn.make_distort10(32, 64, seed=31, dtype=np.float64)
+    obj = rh.make_objective(b)
+    x = torch.tensor(b.x0)
+    f0, g = rh.reference_cost_grad(obj, x)
+    d = -g * rng.choice([1e-3, 1e-2, 1.0], size=(32, 1))
+    a, p, _, _ = rh.reference_line_search(obj, x, torch.tensor(d), strong=True)
+    out.update(d10_points=b.points_3d, d10_obs=b.obs, d10_pose=b.pose, d10_x=b.x0, d10_d=d, d10_alpha=a, d10_probes=p)
+    _save("line_search", **out)
+
+
+def gen_analytic_solves():
+    rng = np.random.default_rng(14)
+    out = {}
+    cases = {
+        # starts follow tests/autograd_solvers/test_bfgs_solver.py:49-97,203-230
+        "sphere": np.concatenate([[[1.1, 2.3, 0.0, 0.0]], rng.normal(0, 1, (15, 4))]),
+        "sphere_offset": np.concatenate([[[1.1, 2.3]], rng.normal(0, 1, (7, 2))]),
+        "log_sphere": np.concatenate([[[-0.3, 0.8]], [[-1700.3, 24942.8]], rng.normal(0, 3, (6, 2))]),
+        "rosenbrock": np.concatenate([[[-1.2, 1.0]], rng.uniform(-2, 2, (15, 2))]),
+        "cosine": np.concatenate([[[0.03, -18.8, 23.8, 19.0]], rng.normal(0, 5, (7, 4))]),
+        "x2_sine": np.array([[17.8885, 35.7771], [-7.641, -7.641], [10.288, -10.288], [9.232, 9.232], [-18.025, 6.0083]]),
+    }
+    for name, x0 in cases.items():
+        for dt in ("float64", "float32"):
+            r = rh.reference_solve(rh.ANALYTIC[name], torch.tensor(x0, dtype=getattr(torch, dt)),
+                                   error_threshold=1e-6, iterations=1000)
+            for k in ("x", "cost", "iters", "fevals", "reason"):
+                out[f"{name}_{dt}_{k}"] = r[k]
+        out[f"{name}_x0"] = x0
+    _save("analytic_solves", **out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", nargs="*", default=None)
+    args = ap.parse_args()
+    small = {"camera_model": gen_camera_model, "bfgs_update": gen_bfgs_update, "line_search": gen_line_search,
+             "analytic_solves": gen_analytic_solves}
+    names = args.only or (list(small) + list(SOLVE_CASES))
+    for name in names:
+        print(name, flush=True)
+        if name in small:
+            small[name]()
+        else:
+            gen_solve(name)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,370 @@
+"""GPU: the CUDA path, called through the Python surface -> C-ABI, against the C oracle on the same
+seeded inputs and against the golden fixtures written from the reference."""
+import numpy as np
+import pytest
+import torch
+
+import davo_b200
+from conftest import golden_batch, load_golden
+from oracle import c_oracle
+from parity import compare_solves, summary
+
+pytestmark = pytest.mark.gpu
+
+TDT = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+
+
+def gpu_solve(batch, weights=None, **kw):
+    """Solve a synthetic batch on the GPU; returns the same dict layout as the oracle."""
+    dt = TDT[batch.x0.dtype]
+    if batch.model == "distort10":
+        obj = davo_b200.DistortionObjective(torch.from_numpy(batch.points_3d), torch.from_numpy(batch.obs),
+                                            None if batch.pose is None else torch.from_numpy(batch.pose),
+                                            weights=weights, dtype=dt)
+    else:
+        obj = davo_b200.JointPoseObjective(torch.from_numpy(batch.points_3d), torch.from_numpy(batch.obs),
+                                           weights=weights, dtype=dt)
+    solver = davo_b200.BFGSSolver(**kw).eval()
+    info = solver(torch.from_numpy(batch.x0), obj, return_info=True)
+    return dict(x=info.parameters.numpy(), cost=info.cost.numpy(), converged=info.converged.numpy(),
+                iters=info.iterations.numpy(), fevals=info.evaluations.numpy(), reason=info.reason.numpy())
+
+
+# ---- objective evaluation ---------------------------------------------------------------------------
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_stage_matches_oracle(dt):
+    b = davo_b200.synthetic.make_distort10(37, 50, seed=3, dtype=dt, random_pose=True)
+    obj = davo_b200.DistortionObjective(torch.from_numpy(b.points_3d), torch.from_numpy(b.obs), torch.from_numpy(b.pose))
+    ref = c_oracle.stage(b.points_3d, b.obs, b.pose)
+    got = obj.data0.cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.allclose(got, ref, rtol=3e-6 if dt == np.float32 else 1e-13, atol=1e-6 if dt == np.float32 else 1e-14)
+    assert np.array_equal(got[..., 2:], ref[..., 2:])  # observations are copied bit for bit
+
+
+@pytest.mark.parametrize("dt,rtol", [(np.float32, 2e-4), (np.float64, 1e-11)])
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 256, 700])
+def test_cost_gradient_matches_oracle(dt, rtol, N):
+    b = davo_b200.synthetic.make_distort10(19, N, seed=N, dtype=dt)
+    rng = np.random.default_rng(N)
+    x = (b.x0 + 0.02 * rng.standard_normal(b.x0.shape)).astype(dt)
+    obj = davo_b200.DistortionObjective(torch.from_numpy(b.points_3d), torch.from_numpy(b.obs), torch.from_numpy(b.pose))
+    cost, grad = obj.evaluate(torch.from_numpy(x))
+    fo, go = c_oracle.eval_cost_grad("distort10", x, c_oracle.stage(b.points_3d, b.obs, b.pose), N=N)
+    assert np.allclose(cost.cpu().numpy(), fo, rtol=rtol)
+    scale = np.abs(go).max(axis=1, keepdims=True)
+    assert np.all(np.abs(grad.cpu().numpy() - go) <= rtol * scale + 1e-30)
+
+
+def test_cost_gradient_matches_reference_autograd_golden():
+    g = load_golden("camera_model")
+    obj = davo_b200.DistortionObjective(torch.from_numpy(g["d10_points"]), torch.from_numpy(g["d10_obs"]),
+                                        torch.from_numpy(g["d10_pose"]))
+    cost, grad = obj.evaluate(torch.from_numpy(g["d10_x"]))
+    assert np.allclose(cost.cpu().numpy(), g["d10_cost"], rtol=1e-11)
+    assert np.allclose(grad.cpu().numpy(), g["d10_grad"], rtol=1e-9, atol=1e-12)
+
+
+def test_weighted_cost_gradient_matches_oracle():
+    b = davo_b200.synthetic.make_distort10(11, 70, seed=5, dtype=np.float64)
+    rng = np.random.default_rng(5)
+    w = rng.uniform(0.0, 2.0, size=(11, 70))
+    w[:, ::7] = 0.0  # a visibility mask (networks/calibration_network.py:66)
+    x = b.x0 + 0.02 * rng.standard_normal(b.x0.shape)
+    obj = davo_b200.DistortionObjective(torch.from_numpy(b.points_3d), torch.from_numpy(b.obs), weights=torch.from_numpy(w))
+    cost, grad = obj.evaluate(torch.from_numpy(x))
+    fo, go = c_oracle.eval_cost_grad("distort10", x, c_oracle.stage(b.points_3d, b.obs, b.pose), weights=w, N=70)
+    assert np.allclose(cost.cpu().numpy(), fo, rtol=1e-11)
+    assert np.allclose(grad.cpu().numpy(), go, rtol=1e-9, atol=1e-12)
+
+
+def test_descriptor_is_callable_with_reference_convention():
+    """(params[k,n], mask[B]) -> err[k] with autograd, so the reference's own solver could drive it."""
+    b = davo_b200.synthetic.make_distort10(9, 40, seed=8, dtype=np.float64)
+    obj = davo_b200.DistortionObjective(torch.from_numpy(b.points_3d), torch.from_numpy(b.obs))
+    mask = torch.tensor([True, False, True, True, False, False, True, False, True])
+    x = torch.from_numpy(b.x0)[mask].clone().requires_grad_(True)
+    err = obj(x, mask)
+    (g,) = torch.autograd.grad(err.sum(), x)
+    fo, go = c_oracle.eval_cost_grad("distort10", b.x0, c_oracle.stage(b.points_3d, b.obs, b.pose), N=40)
+    assert np.allclose(err.detach().numpy(), fo[mask.numpy()], rtol=1e-11)
+    assert np.allclose(g.numpy(), go[mask.numpy()], rtol=1e-9, atol=1e-12)
+
+
+# ---- camera model, least squares, BFGS helpers ---------------------------------------------------------
+
+def test_forward_model_and_jacobian_match_reference_golden():
+    g = load_golden("camera_model")
+    pts, th = torch.from_numpy(g["points_3d"]), torch.from_numpy(g["params16"])
+    u, v = davo_b200.compute_distorted_camera_model(pts, th)
+    assert np.allclose(u.numpy(), g["u"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(v.numpy(), g["v"], rtol=1e-12, atol=1e-12)
+    J, u2, v2 = davo_b200.compute_distorted_camera_model_and_jacobian(pts[1:], th[1:])
+    assert J.shape == (5, 24, 16)
+    assert np.allclose(J.numpy(), g["J_autograd"], rtol=1e-9, atol=1e-11)
+    assert np.array_equal(u2.numpy(), u.numpy()[1:]) and np.array_equal(v2.numpy(), v.numpy()[1:])
+    u32, v32 = davo_b200.compute_distorted_camera_model(pts[1:].float(), th[1:].float())
+    assert np.allclose(u32.numpy(), g["u32"][1:], rtol=2e-5, atol=2e-6)
+    assert np.allclose(v32.numpy(), g["v32"][1:], rtol=2e-5, atol=2e-6)
+    with pytest.raises(ValueError):
+        davo_b200.compute_distorted_camera_model(pts, th[:, :10])
+
+
+@pytest.mark.parametrize("P", [3, 16, 45, 300])
+def test_least_squares_matches_oracle(P):
+    rng = np.random.default_rng(P)
+    B, F, N = 5, 2, 37
+    res = rng.standard_normal((B, F, N, 2))
+    jac = rng.standard_normal((B, F, N, 2, P))
+    w = rng.uniform(0, 1, size=(B, F, N, 1))
+    for weights in (None, w):
+        e, g = c_oracle.least_squares(res, jac, weights)
+        tw = None if weights is None else torch.from_numpy(weights)
+        eg = davo_b200.find_error(torch.from_numpy(res), tw)
+        gg = davo_b200.find_error_gradient(torch.from_numpy(res), torch.from_numpy(jac), tw)
+        assert np.allclose(eg.numpy(), e, rtol=1e-12)
+        assert np.allclose(gg.numpy(), g, rtol=1e-10, atol=1e-12)
+        # and against the reference's formula written with torch ops (solvers/least_squares_utils.py:16-48)
+        sq = torch.from_numpy(res).square() if tw is None else tw * torch.from_numpy(res).square()
+        assert np.allclose(eg.numpy(), sq.sum((1, 2, 3)).numpy(), rtol=1e-12)
+    assert torch.equal(davo_b200.find_residuals(torch.ones(2, 3), torch.full((2, 3), 0.25)), torch.full((2, 3), 0.75))
+
+
+@pytest.mark.parametrize("n", [3, 10, 34])
+def test_bfgs_update_matches_reference_golden(n):
+    g = load_golden("bfgs_update")
+    H, s, y = (torch.from_numpy(g[k + str(n)]) for k in ("H", "s", "y"))
+    out = davo_b200.BFGSSolver.update_inverse_hessian(H, s, y)
+    assert np.allclose(out.numpy(), g[f"Hout{n}"], rtol=1e-12, atol=1e-13)
+    assert torch.equal(out[:2], H[:2])  # curvature <= 0: unchanged bit for bit (test_bfgs_solver.py:335-361)
+    assert np.array_equal(out.numpy(), c_oracle.bfgs_update(g[f"H{n}"], g[f"s{n}"], g[f"y{n}"]))  # same op order
+    sc = davo_b200.BFGSSolver.scale_initial_inverse_hessian(s, y)
+    assert sc.shape == (s.shape[0], 1)
+    assert np.allclose(sc.squeeze(-1).numpy(), g[f"scale{n}"], rtol=1e-13)
+    out32 = davo_b200.BFGSSolver.update_inverse_hessian(H.float(), s.float(), y.float())
+    assert np.allclose(out32.numpy()[2:], g[f"Hout{n}_f32"][2:], rtol=2e-3, atol=2e-3)
+
+
+def test_bfgs_update_known_answer():
+    """tests/autograd_solvers/test_bfgs_solver.py:307-332 with its literal numbers."""
+    step = torch.tensor([-1.26262069, -0.78272035, 0.98543104], dtype=torch.float64)
+    dg = torch.tensor([0.15339519, -0.28944666, 0.54194925], dtype=torch.float64)
+    H = torch.tensor([[2.0, 1.0, 0.0], [1.0, 1.0, 0.0], [0.0, 0.0, 3.0]], dtype=torch.float64)
+    c = (step * dg).sum()
+    left = torch.eye(3) - (step[:, None] * dg[None, :]) / c
+    right = torch.eye(3) - (dg[:, None] * step[None, :]) / c
+    expected = left @ H @ right + step[:, None] * step[None, :] / c
+    result = davo_b200.BFGSSolver.update_inverse_hessian(H, step, dg)
+    assert result.shape == (3, 3)
+    assert torch.isclose(expected, result).all()
+
+
+# ---- line search ------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+@pytest.mark.parametrize("strong", [False, True])
+def test_line_search_reference_cases(dt, strong):
+    """test_wolffe_conditions.py:214-305: alpha < 1, alpha > 1, alpha == 0.25 exactly, alpha ~ 0."""
+    g = load_golden("line_search")
+    name = "float32" if dt == torch.float32 else "float64"
+    tg = torch.tensor(g["dist_targets"], dtype=dt)
+    d = torch.tensor(g["dist_dirs"], dtype=dt)
+    x = torch.zeros(4, 2, dtype=dt)
+    obj = davo_b200.AnalyticObjective("distance", (4,), 2, dtype=dt, target=tg)
+    f0, gr = obj.evaluate(x)
+    alpha, probes = davo_b200.line_search_wolfe_conditions(x, d, f0, gr, obj, strong=strong, return_probes=True)
+    assert alpha.shape == (4,)
+    assert np.array_equal(alpha.numpy(), g[f"dist_alpha_{name}_{int(strong)}"])
+    assert np.array_equal(probes.numpy(), g[f"dist_probes_{name}_{int(strong)}"])
+    assert alpha[0] < 1.0 and alpha[1] > 1.0 and alpha[2] == 0.25
+    assert torch.isclose(alpha[3], torch.tensor(0.0, dtype=dt))
+
+
+@pytest.mark.parametrize("name", ["sphere", "log_sphere", "rosenbrock", "cosine", "x2_sine"])
+@pytest.mark.parametrize("strong", [False, True])
+def test_line_search_analytic_matches_reference_golden(name, strong):
+    g = load_golden("line_search")
+    x, d = torch.from_numpy(g[f"{name}_x"]), torch.from_numpy(g[f"{name}_d"])
+    obj = davo_b200.AnalyticObjective(name, (x.shape[0],), x.shape[1], dtype=torch.float64)
+    f0, gr = obj.evaluate(x)
+    alpha, probes = davo_b200.line_search_wolfe_conditions(x, d, f0, gr, obj, sufficient_decrease=0.1, curvature=0.6,
+                                                           strong=strong, return_probes=True)
+    assert np.array_equal(probes.numpy(), g[f"{name}_probes_{int(strong)}"])
+    assert np.allclose(alpha.numpy(), g[f"{name}_alpha_{int(strong)}"], rtol=1e-13)
+    # the returned alpha satisfies both Wolfe inequalities (test_wolffe_conditions.py:152-211)
+    f1, g1 = obj.evaluate(x + alpha[:, None] * d)
+    g0 = (d * gr.cpu()).sum(-1)
+    ok = alpha > 0
+    assert torch.all((f1.cpu() <= f0.cpu() + 0.1 * alpha * g0 + 1e-12)[ok])
+    dphi = (d * g1.cpu()).sum(-1)
+    if strong:
+        assert torch.all((dphi.abs() <= -0.6 * g0 + 1e-9)[ok & (probes < 1000)])
+
+
+def test_line_search_calibration_matches_reference_golden():
+    g = load_golden("line_search")
+    obj = davo_b200.DistortionObjective(torch.from_numpy(g["d10_points"]), torch.from_numpy(g["d10_obs"]),
+                                        torch.from_numpy(g["d10_pose"]))
+    x, d = torch.from_numpy(g["d10_x"]), torch.from_numpy(g["d10_d"])
+    f0, gr = obj.evaluate(x)
+    alpha, probes = davo_b200.line_search_wolfe_conditions(x, d, f0, gr, obj, strong=True, return_probes=True)
+    assert np.array_equal(probes.numpy(), g["d10_probes"])
+    assert np.allclose(alpha.numpy(), g["d10_alpha"], rtol=1e-12)
+
+
+def test_line_search_warns_on_bad_constants():
+    obj = davo_b200.AnalyticObjective("sphere", (2,), 3, dtype=torch.float64)
+    x = torch.ones(2, 3, dtype=torch.float64)
+    f0, gr = obj.evaluate(x)
+    with pytest.warns(UserWarning):  # wolfe_conditions.py:65-69
+        davo_b200.line_search_wolfe_conditions(x, -gr.cpu(), f0, gr, obj, sufficient_decrease=0.9, curvature=0.1)
+
+
+# ---- analytic solves: the reference's solver tests, mirrored ------------------------------------------
+
+@pytest.mark.parametrize("name", ["sphere", "sphere_offset", "log_sphere", "rosenbrock", "cosine", "x2_sine"])
+def test_analytic_solves_match_reference_golden(name):
+    g = load_golden("analytic_solves")
+    x0 = torch.from_numpy(g[f"{name}_x0"])
+    obj = davo_b200.AnalyticObjective(name, (x0.shape[0],), x0.shape[1], dtype=torch.float64)
+    info = davo_b200.BFGSSolver(error_threshold=1e-6).eval()(x0, obj, return_info=True)
+    same = info.iterations.numpy() == g[f"{name}_float64_iters"]
+    assert same.mean() >= 0.9
+    assert np.array_equal(info.evaluations.numpy()[same], g[f"{name}_float64_fevals"][same])
+    assert np.array_equal(info.reason.numpy(), g[f"{name}_float64_reason"])
+    assert np.allclose(info.parameters.numpy()[same], g[f"{name}_float64_x"][same], rtol=1e-6, atol=1e-8)
+    oracle = c_oracle.solve(name, g[f"{name}_x0"], error_threshold=1e-6)
+    assert np.array_equal(info.iterations.numpy(), oracle["iters"])
+    assert np.allclose(info.parameters.numpy(), oracle["x"], rtol=1e-9, atol=1e-11)
+
+
+def test_solver_reference_behaviours():
+    """Batch dimensions (test_bfgs_solver.py:150-160), iteration cap (:134-147), monotone in budget (:190-200)."""
+    rng = np.random.default_rng(0)
+    x0 = torch.tensor(rng.normal(0.0, 1.0, size=(3, 8, 4)))
+    obj = davo_b200.AnalyticObjective("sphere", (3, 8), 4, dtype=torch.float64)
+    out = davo_b200.BFGSSolver(error_threshold=1e-6).eval()(x0, obj)
+    assert out.shape == (3, 8, 4) and out.dtype == torch.float64 and out.device == x0.device
+    assert torch.isclose(out, torch.zeros_like(out), atol=1e-3).all()
+    start = torch.tensor([[-1.2, 1.0]], dtype=torch.float64)
+    ros = davo_b200.AnalyticObjective("rosenbrock", (1,), 2, dtype=torch.float64)
+    errs = []
+    for iters in (1, 2, 4, 8, 16, 64):
+        info = davo_b200.BFGSSolver(error_threshold=1e-9, iterations=iters).eval()(start, ros, return_info=True)
+        assert int(info.iterations[0]) <= iters
+        errs.append(float(info.cost[0]))
+    assert all(b <= a + 1e-12 for a, b in zip(errs, errs[1:]))
+    assert errs[-1] < 1e-6
+
+
+def test_solver_refuses_unimplemented_modes():
+    obj = davo_b200.AnalyticObjective("sphere", (2,), 3, dtype=torch.float32)
+    x0 = torch.ones(2, 3)
+    with pytest.raises(NotImplementedError):
+        davo_b200.BFGSSolver()(x0, obj)  # training mode with drop-path 0.1 (the reference default)
+    with pytest.raises(NotImplementedError):
+        davo_b200.BFGSSolver().eval()(x0.clone().requires_grad_(True), obj)
+    with pytest.raises(ValueError):
+        davo_b200.BFGSSolver().eval()(torch.ones(2, 4), obj)
+    out = davo_b200.BFGSSolver(drop_path_p=0.0, training_error_threshold=1e-2)(x0, obj)  # training thresholds
+    assert out.shape == (2, 3)
+
+
+# ---- calibration solves: gates G64 / G32 ---------------------------------------------------------------
+
+F64_CASES = [("solve_cfg2_f64", 0.99, 1e-4, 1e-5), ("solve_cfg2_pose_f64", 0.99, 1e-4, 1e-5),
+             ("solve_cfg4_f64", 0.97, 1e-4, 1e-3)]
+
+
+@pytest.mark.parametrize("name,min_steps,max_dth,max_dc", F64_CASES)
+def test_solve_float64_gate(name, min_steps, max_dth, max_dc):
+    """north_star tolerances: parameters rel <= 1e-4, cost rel <= 1e-5, identical step counts >= 99 %,
+    against the float64 reference (golden) and against the oracle."""
+    g = load_golden(name)
+    batch = golden_batch(g["meta"])
+    kw = g["meta"]["solver_kwargs"]
+    got = gpu_solve(batch, **kw)
+    for label, ref in (("reference", g), ("oracle", c_oracle.solve_batch(batch, **kw))):
+        m = compare_solves(got, ref, kw["error_threshold"])
+        print(name, label, summary(m))
+        assert m["steps_equal"] >= min_steps
+        assert m["reason_equal"] >= min_steps
+        assert m["dtheta_p99"] <= max_dth
+        assert m["dcost_p99"] <= max_dc
+
+
+def test_solve_noisy_float64_cost_tolerance():
+    g = load_golden("solve_cfg2_noisy_f64")
+    batch = golden_batch(g["meta"])
+    kw = g["meta"]["solver_kwargs"]
+    got = gpu_solve(batch, **kw)
+    m = compare_solves(got, g, kw["error_threshold"])
+    print(summary(m))
+    assert m["dcost_p99"] <= 1e-5 and m["dtheta_p99"] <= 1e-4
+
+
+@pytest.mark.parametrize("name,floor,max_dth", [("solve_cfg2_f32", 0.97, 5e-3), ("solve_cfg4_f32", 0.80, 5e-2)])
+def test_solve_float32_gate(name, floor, max_dth):
+    """Gate G32: float32 kernel vs the float32 reference, judged against the reference's own float32
+    self-consistency band (98.7-99.8 % identical steps, dtheta p99 1e-4..1e-3)."""
+    g = load_golden(name)
+    batch = golden_batch(g["meta"])
+    kw = g["meta"]["solver_kwargs"]
+    got = gpu_solve(batch, **kw)
+    m = compare_solves(got, g, kw["error_threshold"])
+    print(name, "reference", summary(m))
+    assert m["steps_equal"] >= floor
+    assert m["dtheta_p99"] <= max_dth
+    mo = compare_solves(got, c_oracle.solve_batch(batch, **kw), kw["error_threshold"])
+    print(name, "oracle", summary(mo))
+    assert mo["steps_equal"] >= floor
+
+
+@pytest.mark.parametrize("N", [1, 7, 33, 100])
+def test_solve_ragged_match_counts(N):
+    """N not a multiple of the warp width, down to a single match (under-determined: must not hang)."""
+    batch = davo_b200.synthetic.make_distort10(40, N, seed=100 + N, dtype=np.float64)
+    kw = dict(error_threshold=1e-12, iterations=60)
+    got = gpu_solve(batch, **kw)
+    ref = c_oracle.solve_batch(batch, **kw)
+    m = compare_solves(got, ref, 1e-12)
+    print(N, summary(m))
+    assert m["steps_equal"] >= 0.9
+    assert m["reason_equal"] >= 0.9
+
+
+def test_solve_weighted_matches_oracle():
+    batch = davo_b200.synthetic.make_distort10(64, 96, seed=77, dtype=np.float64)
+    rng = np.random.default_rng(77)
+    w = (rng.uniform(size=(64, 96)) > 0.2).astype(np.float64)
+    kw = dict(error_threshold=1e-12, iterations=200)
+    got = gpu_solve(batch, weights=torch.from_numpy(w), **kw)
+    staged = c_oracle.stage(batch.points_3d, batch.obs, batch.pose)
+    ref = c_oracle.solve("distort10", batch.x0, staged, weights=w, N=96, **kw)
+    m = compare_solves(got, ref, 1e-12)
+    print(summary(m))
+    assert m["steps_equal"] >= 0.98 and m["dtheta_p99"] <= 1e-6
+
+
+def test_solve_full_size_properties():
+    """BASELINE config 2 at full size (64K x 256, float32): size-independent properties.
+    (1) solving is idempotent: a converged solution re-submitted retires at once with 0 steps;
+    (2) permuting the problems permutes the outputs; (3) every output row is written."""
+    B = 65536
+    batch = davo_b200.synthetic.make_distort10(B, 256, seed=0xB200, dtype=np.float32)
+    obj = davo_b200.DistortionObjective(torch.from_numpy(batch.points_3d), torch.from_numpy(batch.obs))
+    solver = davo_b200.BFGSSolver(error_threshold=1e-5).eval()
+    info = solver(torch.from_numpy(batch.x0), obj, return_info=True)
+    assert info.converged.float().mean() > 0.99
+    assert int(info.iterations.min()) >= 1 and int(info.iterations.max()) <= 1000
+    again = solver(info.parameters, obj, return_info=True)
+    conv = info.converged
+    assert torch.equal(again.parameters[conv], info.parameters[conv])
+    assert int(again.iterations[conv].max()) == 0
+    assert torch.equal(again.cost[conv], info.cost[conv])
+    perm = torch.randperm(4096, generator=torch.Generator().manual_seed(1))
+    sub = davo_b200.DistortionObjective.from_staged(obj.data0[:4096][perm.to(obj.device)])
+    pinfo = solver(torch.from_numpy(batch.x0)[:4096][perm], sub, return_info=True)
+    assert torch.equal(pinfo.parameters, info.parameters[:4096][perm])
+    assert torch.equal(pinfo.iterations, info.iterations[:4096][perm])
