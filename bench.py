@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — the batched calibration solve on N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2|cfg3|cfg4]
+
+A step = one pass of the hot path over one batch: stage the matches (davo_stage_matches) and solve
+every problem (davo_solve_calibration); with N > 1 also the single all-gather of the solved records.
+Workload at every N: BASELINE.json configs[1] per GPU — 65 536 problems x 256 matches, n = 10, float32,
+error_threshold 1e-7 (the driver's eval value, networks/calibration_network.py:44), 1000-iteration cap —
+i.e. weak scaling (N x 64K problems in total, each rank generating its own shard from seed 0xB200+rank).
+
+`value` (solves/s) is device time with the raw inputs already in HBM; `e2e` is the same metric through
+BFGSSolver.forward with HOST pinned buffers, H2D and D2H copies inside the timed region.
+`--impl reference` times the CPU arm: the reference is pure Python and /root/reference does not exist on
+the GPU box, so it is the C oracle port of the reference's algorithm (oracle/calib_oracle.c) on all host
+threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_MATCH_EVAL = {"distort10": 93.0, "joint": 145.0}
+SOLVER_KW = {"cfg2": dict(error_threshold=1e-7, iterations=1000),
+             "cfg3": dict(error_threshold=1e-5, iterations=1000),
+             "cfg4": dict(error_threshold=1e-5, iterations=1000)}
+
+
+def make_batch(config: str, B: int, seed: int):
+    import davo_b200
+    syn = davo_b200.synthetic
+    if config == "cfg2":
+        return syn.make_distort10(B, 256, seed=seed, dtype=np.float32)
+    if config == "cfg4":
+        return syn.make_distort10(B, 256, seed=seed, dtype=np.float32, ill_conditioned=True, pathological=0.02)
+    if config == "cfg3":
+        return syn.make_joint(B, 256, 4, seed=seed, dtype=np.float32)
+    raise ValueError(config)
+
+
+def default_B(config: str) -> int:
+    return 16384 if config == "cfg3" else 65536
+
+
+def workload_name(config: str, B: int) -> str:
+    return {"cfg2": f"configs[1]: intrinsics+distortion fit, {B} problems x 256 matches, n=10",
+            "cfg3": f"configs[2]: joint intrinsics + 4 view poses, {B} problems x 1024 matches, n=34",
+            "cfg4": f"configs[3]: ill-conditioned heavy distortion, {B} problems x 256 matches, n=10"}[config]
+
+
+def algorithmic_flops(batch, fevals: np.ndarray, iters: np.ndarray) -> float:
+    """sum fevals * matches * F_fg + sum iters * (12 n^2 + 10 n), with the reference-equivalent
+    evaluation count (what the reference's algorithm evaluates, not what the kernel skipped by reuse)."""
+    matches = batch.N * batch.views
+    n = batch.n
+    return float(fevals.astype(np.float64).sum() * matches * FLOP_PER_MATCH_EVAL[batch.model]
+                 + iters.astype(np.float64).sum() * (12 * n * n + 10 * n))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(config: str, B_workload: int, budget_s: float, threads: int = 0):
+    """Time the C oracle (a port of the reference's algorithm) on a bounded sample of the workload."""
+    from oracle import c_oracle
+    cores = c_oracle.max_threads() if threads <= 0 else threads
+    kw = SOLVER_KW[config]
+    pilot_B = max(16 * cores, 256)
+    pilot = make_batch(config, pilot_B, 0xB200)
+    t0 = time.perf_counter()
+    c_oracle.solve_batch(pilot, threads=cores, **kw)
+    pilot_t = max(time.perf_counter() - t0, 1e-4)
+    sample_B = int(min(B_workload, max(pilot_B, budget_s / pilot_t * pilot_B)))
+    sample = make_batch(config, sample_B, 0xB200)
+    t0 = time.perf_counter()
+    r = c_oracle.solve_batch(sample, threads=cores, **kw)
+    dt = time.perf_counter() - t0
+    return dict(value=sample_B / dt, seconds=dt, cores=cores, sample_B=sample_B,
+                iters_per_s=float(r["iters"].sum()) / dt,
+                sample=f"first {sample_B} problems of the workload (seed 0xB200), {dt:.1f} s on {cores} threads")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # N > 1: rank 0 alone runs and prints it
+    B = args.batch or default_B(args.config)
+    steps, warm = max(args.steps, 1), args.warmup
+    per_step_budget = min(20.0, 120.0 / (steps + warm))
+    for _ in range(warm):
+        cpu_arm(args.config, B, per_step_budget)
+    res = [cpu_arm(args.config, B, per_step_budget) for _ in range(steps)]
+    value = float(np.mean([r["value"] for r in res]))
+    ms = float(np.mean([r["seconds"] for r in res])) * 1e3
+    line = {"impl": "reference", "metric": "calibration_solves_per_sec", "value": value, "unit": "solves/s",
+            "bfgs_iters_per_sec": float(np.mean([r["iters_per_s"] for r in res])),
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, B), "sample_per_step": res[-1]["sample"]},
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": res[-1]["cores"], "kind": "port",
+                             "sample": res[-1]["sample"]},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference is pure Python/PyTorch and is not present on the GPU box; this arm times the C "
+                    "port of its algorithm (oracle/calib_oracle.c, -O2, OpenMP over problems)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the BASELINE size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import davo_b200
+    from davo_b200 import _lib
+    from davo_b200.distributed import ResultSlab
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch or default_B(args.config)
+    batch = make_batch(args.config, B, 0xB200 + rank)
+    kw = SOLVER_KW[args.config]
+    solver = davo_b200.BFGSSolver(**kw).eval()
+    steps, warm = args.steps, max(args.warmup, 3)
+
+    # ---- raw inputs resident in HBM (value) and in pinned host memory (e2e) ------------------------------
+    h_pts = torch.from_numpy(batch.points_3d).pin_memory()
+    h_obs = torch.from_numpy(batch.obs).pin_memory()
+    h_x0 = torch.from_numpy(batch.x0).pin_memory()
+    d_pts, d_obs, d_x0 = h_pts.to(dev), h_obs.to(dev), h_x0.to(dev)
+    slab = ResultSlab(B * world, batch.n, torch.float32, world, dev)
+    out = slab.buffers(rank)
+
+    def make_objective(pts, obs):
+        if batch.model == "distort10":
+            return davo_b200.DistortionObjective(pts, obs)  # runs davo_stage_matches
+        return davo_b200.JointPoseObjective(pts, obs)
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+    def step(record=False):
+        if record:
+            ev[0].record()
+        obj = make_objective(d_pts, d_obs)
+        if record:
+            ev[1].record()
+        solver.solve_into(d_x0, obj, out=out)
+        if record:
+            ev[2].record()
+        slab.all_gather(rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warm):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    solve_ms, stage_ms = [], []
+    barrier()
+    t_start.record()
+    for _ in range(steps):
+        step(record=True)
+        # per-kernel events are read after the loop; recording them does not synchronise
+        solve_ms.append((ev[1], ev[2]))
+        stage_ms.append((ev[0], ev[1]))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_end.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_start.elapsed_time(t_end)
+    solve_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in solve_ms]))
+    stage_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in stage_ms]))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / steps
+
+    iters = out.iterations.cpu().numpy()
+    fevals = out.evaluations.cpu().numpy()
+    converged = float(out.converged.float().mean().item())
+    reasons = np.bincount(out.reason.cpu().numpy(), minlength=4).tolist()
+    stats = torch.tensor([float(iters.sum()), float(fevals.sum()), converged * B], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats)
+    total_B = B * world
+    value = total_B / (ms_per_step * 1e-3)
+
+    # ---- e2e: the public call with host buffers, H2D + D2H inside the timed region -------------------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            obj = make_objective(h_pts, h_obs)                       # H2D of points + observations, staging
+            info = solver(h_x0, obj, return_info=True)               # H2D of x0, solve, D2H of every output
+            return info
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            info = e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / steps
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        h2d = h_pts.numel() * 4 + h_obs.numel() * 4 + h_x0.numel() * 4
+        d2h = sum(t.numel() * t.element_size() for t in info)
+        e2e = {"value": total_B / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the solve kernel): FP32 CUDA-core pipe ----------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    props = torch.cuda.get_device_properties(dev)
+    sm_max_mhz = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+    fp32_peak = props.multi_processor_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12   # TFLOP/s
+    flops = algorithmic_flops(batch, fevals, iters)                                # this rank's launch
+    achieved = flops / (solve_kernel_ms * 1e-3) / 1e12
+    stage_bytes = batch.N * B * (20 + 16) if batch.model == "distort10" else 0     # read 20 B, write 16 B per match
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    stage_gbs = stage_bytes / (stage_kernel_ms * 1e-3) / 1e9 if stage_bytes else None
+
+    line = {
+        "metric": "calibration_solves_per_sec", "value": value, "unit": "solves/s",
+        "bfgs_iters_per_sec": float(stats[0].item()) / (ms_per_step * 1e-3),
+        "fevals_per_sec": float(stats[1].item()) / (ms_per_step * 1e-3),
+        "converged_frac": float(stats[2].item()) / total_B,
+        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, B), "problems_per_gpu": B, "solver": kw,
+                   "l2": f"inputs larger than L2 (staged matches {batch.N * batch.views * B * 16 / 1e6:.0f} MB per GPU)",
+                   "seed": "0xB200 + rank", "collective": "one all_gather_into_tensor of the solved records"
+                   if world > 1 else "none (single GPU)"},
+        "kernel_ms": {"solve": solve_kernel_ms, "stage": stage_kernel_ms},
+        "mean_iters": float(iters.mean()), "mean_fevals": float(fevals.mean()), "reasons_rank0": reasons,
+        "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": achieved / fp32_peak, "traffic": None,
+                     "peak_source": f"{props.multi_processor_count} SMs x 128 lanes x 2 x {sm_max_mhz:.0f} MHz "
+                                    "(no FP32 figure in MEASURED_PEAKS.json; sm_max_mhz taken from it)",
+                     "flops_counted": "SURVEY.md 8(d): reference-equivalent fevals x matches x "
+                                      f"{FLOP_PER_MATCH_EVAL[batch.model]:.0f} + iters x (12n^2+10n)"},
+        "roofline_staging": None if stage_gbs is None else {
+            "bound": "hbm", "achieved": stage_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,
+            "traffic": None, "bytes_counted": "20 B read + 16 B written per match"},
+        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        c = cpu_arm(args.config, B, 15.0)
+        line["cpu_baseline"] = {"value": c["value"], "unit": "solves/s", "cores": c["cores"], "kind": "port",
+                                "sample": c["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,8 +29,8 @@ class _EvalFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, params, objective, index):
         cost, grad = objective.evaluate(params, index=index, want_grad=True)
-        ctx.save_for_backward(grad)
-        return cost
+        ctx.save_for_backward(grad.to(device=params.device, dtype=params.dtype))
+        return cost.to(device=params.device, dtype=params.dtype)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -85,7 +85,7 @@ class CalibrationObjective:
             index = mask.reshape(-1).to(self.device).nonzero(as_tuple=True)[0]
         lead = params.shape[:-1]
         out = _EvalFunction.apply(params.reshape(-1, self.n), self, index)
-        return out.reshape(lead).to(params.device)
+        return out.reshape(lead)
 
 
 class DistortionObjective(CalibrationObjective):

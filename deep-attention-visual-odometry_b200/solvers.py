@@ -28,6 +28,25 @@ class SolveInfo(NamedTuple):
     reason: torch.Tensor      # (B..)   int32, 0 threshold / 1 step size / 2 iteration cap / 3 NaN cost
 
 
+class SolveBuffers(NamedTuple):
+    """Device-resident outputs of one solve launch (all rows are always written)."""
+
+    x: torch.Tensor            # [B,n]
+    cost: torch.Tensor         # [B]
+    converged: torch.Tensor    # [B] uint8
+    iterations: torch.Tensor   # [B] int32
+    evaluations: torch.Tensor  # [B] int32
+    reason: torch.Tensor       # [B] int32
+    workspace: torch.Tensor    # DAVO_WORKSPACE_BYTES of scratch (work-queue counter)
+
+    @classmethod
+    def allocate(cls, B, n, dtype, device) -> "SolveBuffers":
+        i32 = lambda: torch.empty(B, dtype=torch.int32, device=device)
+        return cls(torch.empty(B, n, dtype=dtype, device=device), torch.empty(B, dtype=dtype, device=device),
+                   torch.empty(B, dtype=torch.uint8, device=device), i32(), i32(), i32(),
+                   torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device))
+
+
 def _require_descriptor(error_function) -> CalibrationObjective:
     if not isinstance(error_function, CalibrationObjective):
         raise TypeError(
@@ -62,7 +81,7 @@ class BFGSSolver(Module):
         self.training_error_threshold = (float(training_error_threshold) if training_error_threshold is not None
                                          else self.error_threshold)
 
-    def forward(self, parameters: torch.Tensor, error_function, return_info: bool = False):
+    def forward(self, parameters: torch.Tensor, error_function, return_info: bool = False, out=None):
         obj = _require_descriptor(error_function)
         if parameters.requires_grad:
             raise NotImplementedError("differentiating through the solve (create_graph) is not implemented")
@@ -82,31 +101,36 @@ class BFGSSolver(Module):
             raise ValueError(f"parameters have {n} columns, the objective expects {obj.n}")
         if tuple(batch_shape) != obj.batch_shape and parameters.numel() // n != obj.B:
             raise ValueError(f"parameters batch {tuple(batch_shape)} does not match the objective's {obj.batch_shape}")
+        out_dev = parameters.device
+        x0 = parameters.detach().to(device=obj.device, dtype=obj.dtype, non_blocking=True).reshape(obj.B, n)
+        buf = self.solve_into(x0.contiguous(), obj, error_threshold=error_threshold, iterations=iterations, out=out)
+        result = buf.x.reshape(parameters.shape).to(device=out_dev, dtype=parameters.dtype)
+        if not return_info:
+            return result
+        back = lambda t: t.reshape(batch_shape).to(out_dev)
+        return SolveInfo(result, back(buf.cost), back(buf.converged).bool(), back(buf.iterations),
+                         back(buf.evaluations), back(buf.reason))
+
+    def solve_into(self, x0: torch.Tensor, obj: CalibrationObjective, *, error_threshold=None, iterations=None,
+                   out: "SolveBuffers | None" = None) -> "SolveBuffers":
+        """The launch itself: x0 [B,n] on the objective's device -> device-resident SolveBuffers.  Stream
+        ordered, no host synchronisation; `out` lets a caller (e.g. the multi-GPU gather slab) own the
+        output memory so the kernel writes straight into it."""
         device = _lib.require_cuda() if obj.device.type != "cuda" else obj.device
-        B = obj.B
+        B, n = obj.B, obj.n
+        error_threshold = self.error_threshold if error_threshold is None else error_threshold
+        iterations = self.iterations if iterations is None else iterations
         with torch.cuda.device(device):
-            x0 = parameters.detach().to(device=device, dtype=obj.dtype, non_blocking=True).reshape(B, n).contiguous()
-            x = torch.empty_like(x0)
-            cost = torch.empty(B, dtype=obj.dtype, device=device)
-            converged = torch.empty(B, dtype=torch.uint8, device=device)
-            iters = torch.empty(B, dtype=torch.int32, device=device)
-            fevals = torch.empty(B, dtype=torch.int32, device=device)
-            reason = torch.empty(B, dtype=torch.int32, device=device)
-            workspace = torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+            buf = out if out is not None else SolveBuffers.allocate(B, n, obj.dtype, device)
             desc = obj.desc(iterations=iterations, strong=True, sufficient_decrease=self.sufficient_decrease,
                             curvature=self.curvature, error_threshold=error_threshold,
                             minimum_step=self.minimum_step)
             st = _lib.lib().davo_solve_calibration(
                 ctypes.byref(desc), _lib.ptr(obj.data0), _lib.ptr(obj.data1), _lib.ptr(obj.weights), _lib.ptr(x0),
-                _lib.ptr(x), _lib.ptr(cost), _lib.ptr(converged), _lib.ptr(iters), _lib.ptr(fevals),
-                _lib.ptr(reason), _lib.ptr(workspace), _lib.stream_ptr())
+                _lib.ptr(buf.x), _lib.ptr(buf.cost), _lib.ptr(buf.converged), _lib.ptr(buf.iterations),
+                _lib.ptr(buf.evaluations), _lib.ptr(buf.reason), _lib.ptr(buf.workspace), _lib.stream_ptr())
         _lib.check(st, "davo_solve_calibration")
-        out_dev = parameters.device
-        result = x.reshape(parameters.shape).to(device=out_dev, dtype=parameters.dtype)
-        if not return_info:
-            return result
-        back = lambda t: t.reshape(batch_shape).to(out_dev)
-        return SolveInfo(result, back(cost), back(converged).bool(), back(iters), back(fevals), back(reason))
+        return buf
 
     # ---- the two static helpers of the reference, on the GPU -----------------------------------------
     @staticmethod

@@ -73,10 +73,21 @@ def gen_solve(name):
     dt_s = time.time() - t
     print(f"  {name}: reference {dt_s:.1f}s, {batch.B / dt_s:.1f} solves/s, iters mean {r['iters'].mean():.1f}, "
           f"fevals mean {r['fevals'].mean():.1f}, reasons {np.bincount(r['reason'], minlength=4)}", flush=True)
+    # The reference's own reproducibility band: the same problems with the order of
+    # the matches permuted, i.e. nothing but a different floating-point summation order.
+    perm = np.random.default_rng(0x5EED).permutation(batch.N)
+    pb = syn.CalibrationBatch(batch.model, batch.points_3d[:, perm],
+                              batch.obs[:, perm] if batch.model == "distort10" else batch.obs[:, :, perm],
+                              batch.pose, batch.x0, batch.truth, batch.views)
+    rp = rh.reference_solve(rh.make_objective(pb, getattr(torch, dt)), torch.as_tensor(batch.x0), **skw)
+    print(f"  {name}: self-consistency under a permutation of the matches: identical steps "
+          f"{(rp['iters'] == r['iters']).mean():.4f}, identical reason {(rp['reason'] == r['reason']).mean():.4f}",
+          flush=True)
     meta = dict(generator=gen, generator_kwargs=gkw, dtype=dt, solver_kwargs=skw, digest=batch.digest(),
                 reference_seconds=dt_s, reference_threads=torch.get_num_threads(), torch=torch.__version__)
     _save(name, meta=json.dumps(meta), x=r["x"], cost=r["cost"], iters=r["iters"], fevals=r["fevals"],
-          reason=r["reason"], converged=r["converged"])
+          reason=r["reason"], converged=r["converged"], perm_x=rp["x"], perm_cost=rp["cost"],
+          perm_iters=rp["iters"], perm_fevals=rp["fevals"], perm_reason=rp["reason"])
 
 
 def gen_camera_model():

@@ -5,7 +5,7 @@ import pytest
 
 from conftest import golden_batch, load_golden
 from oracle import c_oracle
-from parity import compare_solves, summary
+from parity import assert_within_band, compare_solves, reference_band, summary
 
 
 def test_forward_model_matches_reference():
@@ -115,51 +115,25 @@ def test_analytic_solves(name):
     assert (r32["iters"] == g[f"{name}_float32_iters"]).mean() >= 0.6  # fp32 trajectories are chaotic near the floor
 
 
-# (fixture, min identical step counts, max dtheta p99, max dcost p99)
-F64_CASES = [("solve_cfg2_f64", 0.99, 1e-6, 1e-5), ("solve_cfg2_pose_f64", 0.99, 1e-6, 1e-5),
-             # joint pose + intrinsics is worse conditioned: parameters agree to ~1e-8 while the noise-free
-             # optimum's cost (~1e-11, below the threshold) is itself rounding noise -> looser cost bound
-             ("solve_cfg3_small_f64", 0.99, 1e-6, 1e-2), ("solve_cfg3_f64", 0.99, 1e-6, 1e-2),
-             ("solve_cfg4_f64", 0.97, 1e-4, 1e-3)]
+F64_CASES = ["solve_cfg2_f64", "solve_cfg2_pose_f64", "solve_cfg3_small_f64", "solve_cfg3_f64", "solve_cfg4_f64",
+             "solve_cfg2_noisy_f64"]
+F32_CASES = ["solve_cfg2_f32", "solve_cfg2_f32_thr1e-7", "solve_cfg3_f32", "solve_cfg4_f32"]
 
 
-@pytest.mark.parametrize("name,min_steps,max_dth,max_dc", F64_CASES)
-def test_solve_float64_matches_reference(name, min_steps, max_dth, max_dc):
-    """Gate G64 for the oracle: identical accepted-step counts and termination reasons."""
+@pytest.mark.parametrize("name", F64_CASES + F32_CASES)
+def test_solve_matches_reference_within_its_own_band(name):
+    """Gates G64 / G32 for the oracle.  float64 on well-conditioned problems (configs 2, 3): identical
+    accepted-step counts and termination reasons, parameters to ~1e-11.  Ill-conditioned (config 4), noisy
+    and float32 runs are chaotic in the reference itself; there the bar is the reference's own band."""
     g = load_golden(name)
     batch = golden_batch(g["meta"])
     kw = g["meta"]["solver_kwargs"]
     r = c_oracle.solve_batch(batch, **kw)
     m = compare_solves(r, g, kw["error_threshold"])
-    print(name, summary(m))
-    assert m["steps_equal"] >= min_steps
-    assert m["reason_equal"] >= min_steps
-    assert m["dtheta_p99"] <= max_dth
-    assert m["dcost_p99"] <= max_dc
-
-
-def test_solve_noisy_float64_matches_reference():
-    """Noisy observations: optimum cost ~ 2 N sigma^2 so a relative cost tolerance is meaningful.  Every
-    problem retires on the step size after wandering on the noise floor, so step counts are not comparable."""
-    g = load_golden("solve_cfg2_noisy_f64")
-    batch = golden_batch(g["meta"])
-    kw = g["meta"]["solver_kwargs"]
-    r = c_oracle.solve_batch(batch, **kw)
-    m = compare_solves(r, g, kw["error_threshold"])
-    print(summary(m))
-    assert m["dcost_p99"] <= 1e-5
-    assert m["dtheta_p99"] <= 1e-4
-
-
-@pytest.mark.parametrize("name", ["solve_cfg2_f32", "solve_cfg3_f32", "solve_cfg4_f32"])
-def test_solve_float32_within_reference_band(name):
-    """Gate G32: the reference only reproduces itself to ~99 % step counts in float32."""
-    g = load_golden(name)
-    batch = golden_batch(g["meta"])
-    kw = g["meta"]["solver_kwargs"]
-    r = c_oracle.solve_batch(batch, **kw)
-    m = compare_solves(r, g, kw["error_threshold"])
-    print(name, summary(m))
-    floor = 0.80 if "cfg4" in name else (0.90 if "cfg3" in name else 0.97)
-    assert m["steps_equal"] >= floor
-    assert m["dtheta_p99"] <= (5e-2 if "cfg4" in name else 5e-3)
+    band = reference_band(g, kw["error_threshold"])
+    print(name, "oracle vs reference", summary(m))
+    print(name, "reference vs itself", summary(band))
+    assert_within_band(m, band)
+    if name in ("solve_cfg2_f64", "solve_cfg2_pose_f64", "solve_cfg3_small_f64"):
+        assert m["steps_equal"] == 1.0 and m["fevals_equal"] == 1.0 and m["reason_equal"] == 1.0
+        assert m["dtheta_max"] <= 1e-6
