@@ -1,0 +1,211 @@
+// solver_wide.cuh — one warp solves one problem with up to 64 parameters (the JOINT model: 10
+// intrinsics + 6 pose parameters per view).  Same state machine as solver_warp.cuh, restated from
+//   autograd_solvers/bfgs_solver.py:80-303, utils/func_inverse_curvature.py:8-11,
+//   autograd_solvers/line_search/wolfe_conditions.py:23-253,
+// but with the n-vectors and the n x n inverse Hessian in this warp's SHARED memory (n = 34 needs
+// 4.6 KB for H; registers could not hold two rows per lane next to the match arithmetic).  Lane L
+// works on components L and L + 32.  H rows are padded to n + 1 words, so a lane walking its row and
+// 32 lanes reading one column are both bank-conflict free.  Scalars are replicated and bitwise
+// identical across lanes; reductions over components are per-lane partial sums + a 5-step butterfly.
+#pragma once
+#include "davo_common.cuh"
+#include "solver_warp.cuh"  // same_bits
+
+namespace davo {
+
+constexpr int kWideMax = 64;
+
+template <typename T>
+__device__ __forceinline__ T warp_allreduce(T v) {
+    v += shfl_xor(v, 1);
+    v += shfl_xor(v, 2);
+    v += shfl_xor(v, 4);
+    v += shfl_xor(v, 8);
+    v += shfl_xor(v, 16);
+    return v;
+}
+
+// Per-warp shared-memory workspace of the wide solver.
+template <typename T>
+struct WideWorkspace {
+    T *x, *g, *gprev, *d, *s, *y, *yH, *Hy, *xt, *gt, *H;
+    int ld;  // row stride of H
+    __host__ __device__ static size_t bytes(int n) {
+        return sizeof(T) * (10 * (size_t)kWideMax + (size_t)n * (n + 1));
+    }
+    __device__ void carve(unsigned char* base, int n) {
+        T* p = reinterpret_cast<T*>(base);
+        x = p; g = x + kWideMax; gprev = g + kWideMax; d = gprev + kWideMax; s = d + kWideMax;
+        y = s + kWideMax; yH = y + kWideMax; Hy = yH + kWideMax; xt = Hy + kWideMax; gt = xt + kWideMax;
+        H = gt + kWideMax;
+        ld = n + 1;
+    }
+};
+
+template <typename T>
+__device__ __forceinline__ T wide_dot(const T* a, const T* b, int n, int lane) {
+    T acc = T(0);
+    for (int c = lane; c < n; c += 32) acc = add_rn(acc, mul_rn(a[c], b[c]));
+    return warp_allreduce(acc);
+}
+
+// wolfe_conditions.py:23-239.  x, d, g live in shared memory; probes are evaluated at ws.xt with the
+// gradient written to ws.gt.
+template <typename T, typename Obj>
+__device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const SolveParams<T>& p, const T* x,
+                                                                const T* d, T f0, const T* g, T* xt, T* gt,
+                                                                int lane) {
+    const int n = p.n;
+    const T g0 = wide_dot(d, g, n, lane);       // :77
+    bool widening = true, zooming = false;      // :80-82
+    T lo = T(0), hi = T(0), cand = T(1);        // :97-108
+    T lo_f = f0, hi_f = f0, cand_f = f0;        // :109-111
+    int probes = 0;
+    const T neg_c2_g0 = mul_rn(T(-1) * p.c2, g0);
+    for (int i = 0; i < p.max_ls; ++i) {        // :116
+        if (!(widening || zooming)) break;      // :119-121
+        if (i > 0) {
+            if (widening) { hi = cand; hi_f = cand_f; cand = mul_rn(T(2), cand); }  // :125-127
+            if (zooming) cand = mul_rn(T(0.5), add_rn(lo, hi));                      // :128-131
+        }
+        __syncwarp();
+        for (int c = lane; c < n; c += 32) xt[c] = add_rn(x[c], mul_rn(cand, d[c]));  // :139
+        __syncwarp();
+        cand_f = obj.eval(xt, gt);
+        const T dphi = wide_dot(d, gt, n, lane);                                    // :141
+        ++probes;
+        bool D = cand_f > add_rn(f0, mul_rn(mul_rn(p.c1, cand), g0));               // :146-150
+        if (zooming) D = D || (cand_f >= lo_f);                                     // :151-153
+        if (widening && i > 0) D = D || (cand_f >= hi_f);                           // :154-157
+        const bool C = p.strong ? (fabs(dphi) <= neg_c2_g0) : (mul_rn(T(-1), dphi) <= neg_c2_g0);  // :160-169
+        const bool G = widening ? (dphi >= T(0)) : (mul_rn(dphi, sub_rn(hi, lo)) >= T(0));         // :174-180
+        if (zooming) {                                                              // :187-207
+            if (D) { hi = cand; hi_f = cand_f; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; zooming = false; }
+            else { if (G) { hi = lo; hi_f = lo_f; } lo = cand; lo_f = cand_f; }
+        } else {                                                                    // :216-237
+            if (D) { lo = hi; lo_f = hi_f; hi = cand; hi_f = cand_f; widening = false; zooming = true; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; widening = false; }
+            else if (G) { lo = cand; lo_f = cand_f; widening = false; zooming = true; }
+        }
+        if (zooming && !(lo != hi)) zooming = false;                                // :236
+    }
+    LineSearchResult<T> r;
+    r.alpha = hi; r.last_cand = cand; r.last_f = cand_f; r.last_g = T(0); r.probes = probes;
+    return r;
+}
+
+// bfgs_solver.py:80-215 for one problem.
+template <typename T, typename Obj>
+__device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p, int b, WideWorkspace<T>& ws,
+                                               int lane) {
+    const int n = p.n, ld = ws.ld;
+    T *x = ws.x, *g = ws.g, *gprev = ws.gprev, *gt = ws.gt;
+    T *d = ws.d, *s = ws.s, *y = ws.y, *yH = ws.yH, *Hy = ws.Hy, *H = ws.H;
+    __syncwarp();
+    for (int c = lane; c < n; c += 32) {
+        x[c] = p.x0[(size_t)b * n + c];
+        s[c] = T(0);
+        g[c] = T(0);
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = lane; j < n; j += 32) H[i * ld + j] = (i == j) ? T(1) : T(0);  // :112-117
+    __syncwarp();
+    T f = T(0);
+    int iters = 0, fevals = 0, reason = DAVO_REASON_CAP;
+    bool have_fg = false, have_f = false;
+
+    for (int k = 0; k < p.max_iters; ++k) {  // :118
+        if (!have_fg) f = obj.eval(x, g);    // :128-135
+        ++fevals;
+        have_f = true;
+        if (!(f > p.thr)) {                  // :143
+            reason = (f <= p.thr) ? DAVO_REASON_THRESHOLD : DAVO_REASON_NAN;
+            break;
+        }
+        __syncwarp();
+        if (k == 0) {
+            for (int c = lane; c < n; c += 32) d[c] = mul_rn(T(-1), g[c]);  // :152-155
+        } else {
+            for (int c = lane; c < n; c += 32) y[c] = sub_rn(g[c], gprev[c]);  // :157
+            __syncwarp();
+            const T sy = wide_dot(s, y, n, lane);
+            if (k == 1) {                                                      // :159-167, :217-233
+                T den = wide_dot(y, y, n, lane);
+                den = (den < T(1e-5)) ? T(1e-5) : den;
+                T sc = div_rn(sy, den);
+                sc = (sc < T(1e-4)) ? T(1e-4) : sc;
+                for (int i = 0; i < n; ++i)
+                    for (int j = lane; j < n; j += 32) H[i * ld + j] = mul_rn(sc, H[i * ld + j]);
+                __syncwarp();
+            }
+            T rho = div_rn(T(1), sy);                                          // func_inverse_curvature.py:8-11
+            if (sy <= T(0)) rho = T(0);
+            for (int c = lane; c < n; c += 32) {
+                T a = T(0), bsum = T(0);
+                for (int i = 0; i < n; ++i) {
+                    a = add_rn(a, mul_rn(y[i], H[i * ld + c]));                // (y^T H)_c, :268-270
+                    bsum = add_rn(bsum, mul_rn(H[c * ld + i], y[i]));          // (H y)_c,   :293-295
+                }
+                yH[c] = a;
+                Hy[c] = bsum;
+            }
+            __syncwarp();
+            T qp = T(0);                                                       // :271-274
+            for (int c = lane; c < n; c += 32) qp = add_rn(qp, mul_rn(yH[c], mul_rn(y[c], rho)));
+            const T onepq = add_rn(T(1), warp_allreduce(qp));
+            for (int i = 0; i < n; ++i) {                                      // :278-303
+                const T sri = mul_rn(s[i], rho), Hyi = Hy[i];
+                for (int j = lane; j < n; j += 32) {
+                    const T sop = mul_rn(mul_rn(sri, s[j]), onepq);
+                    const T sgp = mul_rn(sri, yH[j]);
+                    const T gsp = mul_rn(Hyi, mul_rn(s[j], rho));
+                    H[i * ld + j] = sub_rn(sub_rn(add_rn(H[i * ld + j], sop), sgp), gsp);
+                }
+            }
+            __syncwarp();
+            for (int c = lane; c < n; c += 32) {                               // :173-176
+                T a = T(0);
+                for (int j = 0; j < n; ++j) a = fma_t(H[c * ld + j], g[j], a);
+                d[c] = mul_rn(T(-1), a);
+            }
+        }
+        __syncwarp();
+        const LineSearchResult<T> ls = line_search_wide(obj, p, x, d, f, g, ws.xt, gt, lane);  // :181-190
+        fevals += ls.probes;
+        ++iters;
+        T nrm2 = T(0);
+        for (int c = lane; c < n; c += 32) {                                   // :191-199
+            const T sc = mul_rn(ls.alpha, d[c]);
+            s[c] = sc;
+            x[c] = add_rn(x[c], sc);
+            nrm2 = add_rn(nrm2, mul_rn(sc, sc));
+        }
+        const T nrm = sqrt_rn(warp_allreduce(nrm2));
+        have_fg = same_bits(ls.alpha, ls.last_cand);
+        have_f = have_fg;
+        {   // rotate gradient buffers: gprev <- g, and g <- gt when the accepted point is the last probe
+            T* old = gprev;
+            gprev = g;
+            if (have_fg) { g = gt; gt = old; f = ls.last_f; }
+            else { g = old; }
+        }
+        __syncwarp();
+        if (!(nrm > p.min_step)) {                                             // :203-207
+            reason = DAVO_REASON_STEP;
+            break;
+        }
+    }
+    if (!have_f) f = obj.eval(x, gt);  // cost at the returned parameters (networks/calibration_network.py:71)
+    __syncwarp();
+    for (int c = lane; c < n; c += 32) p.x_out[(size_t)b * n + c] = x[c];
+    if (lane == 0) {
+        if (p.cost_out) p.cost_out[b] = f;
+        if (p.converged_out) p.converged_out[b] = (f <= p.thr) ? 1 : 0;
+        if (p.iters_out) p.iters_out[b] = iters;
+        if (p.fevals_out) p.fevals_out[b] = fevals;
+        if (p.reason_out) p.reason_out[b] = reason;
+    }
+}
+
+}  // namespace davo

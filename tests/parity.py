@@ -39,7 +39,13 @@ def assert_within_band(m, band, steps_slack=0.04, reason_slack=0.03, tol_factor=
                        cost_floor=1e-5):
     """north_star tolerances (identical steps >= 99 %, dtheta <= 1e-4, dcost <= 1e-5) wherever the reference
     itself meets them; otherwise at least as tight as the reference's own band (with statistical slack)."""
-    assert m["steps_equal"] >= min(0.99, band["steps_equal"] - steps_slack), (summary(m), summary(band))
-    assert m["reason_equal"] >= min(0.99, band["reason_equal"] - reason_slack), (summary(m), summary(band))
-    assert m["dtheta_p99"] <= max(theta_floor, tol_factor * band["dtheta_p99"]), (summary(m), summary(band))
-    assert m["dcost_p99"] <= max(cost_floor, tol_factor * band["dcost_p99"]), (summary(m), summary(band))
+    B = len(m["dtheta"])
+    for key, slack in (("steps_equal", steps_slack), ("reason_equal", reason_slack)):
+        p = band[key]
+        slack = max(slack, 3.0 * np.sqrt(max(p * (1.0 - p), 1e-4) / B))  # 3 sigma of a binomial estimate over B problems
+        assert m[key] >= min(0.99, p - slack), (key, summary(m), summary(band))
+    # Where the reference's own tail is already of order one the trajectories are chaotic (float32 at its
+    # noise floor, ill-conditioned config 4): a p99 of a heavy tail is not a stable statistic, compare medians.
+    for key, floor in (("dtheta", theta_floor), ("dcost", cost_floor)):
+        stat = "_p99" if band[key + "_p99"] <= 1e-2 else "_median"
+        assert m[key + stat] <= max(floor, tol_factor * band[key + stat]), (key + stat, summary(m), summary(band))
