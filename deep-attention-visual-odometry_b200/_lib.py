@@ -13,7 +13,8 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdavo_b200.so")
+# DAVO_B200_LIB selects an A/B build of the same ABI (tools/); the product library is the default
+LIB_PATH = os.environ.get("DAVO_B200_LIB") or os.path.join(_HERE, "libdavo_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 ABI_VERSION = 1

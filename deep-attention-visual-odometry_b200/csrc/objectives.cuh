@@ -20,35 +20,39 @@ namespace davo {
 template <typename T>
 struct Intrinsics {
     T cx, cy, k1, k2, k3, p1, p2, fx, s, fy;
-    T k2x2, k3x3, p1x2, p2x2, p1x6, p2x6;
+    T k1x2, k2x4, k3x6, p1x2, p2x2, p1x6, p2x6;
     __device__ __forceinline__ void load(const T* th) {
-        cx = th[0]; cy = th[1]; k1 = th[2]; k2 = th[3]; k3 = th[4];
-        p1 = th[5]; p2 = th[6]; fx = th[7]; s = th[8]; fy = th[9];
-        k2x2 = T(2) * k2; k3x3 = T(3) * k3;
+        using V4 = typename Vec4<T>::type;
+        const V4* t4 = reinterpret_cast<const V4*>(th);  // the parameter line is 16-byte aligned, >= 12 entries
+        const V4 q0 = t4[0], q1 = t4[1], q2 = t4[2];
+        cx = q0.x; cy = q0.y; k1 = q0.z; k2 = q0.w; k3 = q1.x;
+        p1 = q1.y; p2 = q1.z; fx = q1.w; s = q2.x; fy = q2.y;
+        k1x2 = T(2) * k1; k2x4 = T(4) * k2; k3x6 = T(6) * k3;
         p1x2 = T(2) * p1; p2x2 = T(2) * p2; p1x6 = T(6) * p1; p2x6 = T(6) * p2;
     }
 };
 
-// One match: residuals, squared error and the 10 intrinsic-gradient accumulators.
-// acc[0..9] += d(cost/2)/d(cx,cy,k1,k2,k3,p1,p2,fx,s,fy), acc[10] += cost.
+// One match: residuals, squared error and the intrinsic-gradient accumulators.
+//   acc[0..9]  += d(cost/2)/d(cx,cy,k1,k2,k3,p1,p2,fx,s,fy)   (acc[5], acc[6] without their 2uv terms)
+//   acc[10]    += cost
+//   acc[11]    += ru * uv,  acc[12] += rv * uv                 (folded into acc[5], acc[6] by fold_uv_terms)
 // (gu, gv) = d(cost/2)/d(u, v) are returned for the pose chain rule of the JOINT model.
-// ~56 FP instructions in fp32; counted as 93 flop by SURVEY.md §8(d).
+// 53 FP32 instructions; counted as 93 flop by SURVEY.md 8(d).
 template <typename T, bool kWeighted>
 __device__ __forceinline__ void match_cost_grad(const Intrinsics<T>& I, T a, T b, T us, T vs, T w,
                                                 T (&acc)[kSlots], T& gu, T& gv) {
     const T u = fma_t(I.fx, a, I.s * b);            // distorted_camera_model.py:59-61
     const T v = I.fy * b;                           // :62
-    const T uu = u * u, vv = v * v;
-    const T uv2 = (u + u) * v;                      // 2uv
+    const T uu = u * u, vv = v * v, uv = u * v;     // :65
     const T r2 = uu + vv;                           // :64
     const T rad = fma_t(r2, fma_t(r2, fma_t(r2, I.k3, I.k2), I.k1), T(1));  // :66-74 (Horner)
     const T A = fma_t(T(2), uu, r2);                // r2 + 2u^2
     const T Bv = fma_t(T(2), vv, r2);               // r2 + 2v^2
     T ru = fma_t(u, rad, I.cx - us);                // :75-80 minus the observation
-    ru = fma_t(I.p1, uv2, ru);
+    ru = fma_t(I.p1x2, uv, ru);
     ru = fma_t(I.p2, A, ru);
     T rv = fma_t(v, rad, I.cy - vs);                // :81-86
-    rv = fma_t(I.p2, uv2, rv);
+    rv = fma_t(I.p2x2, uv, rv);
     rv = fma_t(I.p1, Bv, rv);
     if (kWeighted) {
         acc[10] = fma_t(w, fma_t(ru, ru, rv * rv), acc[10]);  // least_squares_utils.py:24-28
@@ -58,14 +62,14 @@ __device__ __forceinline__ void match_cost_grad(const Intrinsics<T>& I, T a, T b
         acc[10] = fma_t(ru, ru, acc[10]);
         acc[10] = fma_t(rv, rv, acc[10]);
     }
-    const T radp = fma_t(r2, fma_t(r2, I.k3x3, I.k2x2), I.k1);  // d rad / d r2
-    T Duu = fma_t(uu + uu, radp, rad);
+    const T radp2 = fma_t(r2, fma_t(r2, I.k3x6, I.k2x4), I.k1x2);  // 2 d rad / d r2
+    T Duu = fma_t(uu, radp2, rad);                  // d u'/d u = rad + 2u^2 rad' + 2 p1 v + 6 p2 u
     Duu = fma_t(I.p1x2, v, Duu);
     Duu = fma_t(I.p2x6, u, Duu);
-    T Dvv = fma_t(vv + vv, radp, rad);
+    T Dvv = fma_t(vv, radp2, rad);                  // d v'/d v = rad + 2v^2 rad' + 6 p1 v + 2 p2 u
     Dvv = fma_t(I.p1x6, v, Dvv);
     Dvv = fma_t(I.p2x2, u, Dvv);
-    T Duv = uv2 * radp;
+    T Duv = uv * radp2;                             // d u'/d v = d v'/d u = 2uv rad' + 2 p1 u + 2 p2 v
     Duv = fma_t(I.p1x2, u, Duv);
     Duv = fma_t(I.p2x2, v, Duv);
     gu = fma_t(ru, Duu, rv * Duv);
@@ -77,11 +81,22 @@ __device__ __forceinline__ void match_cost_grad(const Intrinsics<T>& I, T a, T b
     acc[2] = fma_t(t, r2, acc[2]);
     acc[3] = fma_t(t, r4, acc[3]);
     acc[4] = fma_t(t, r6, acc[4]);
-    acc[5] = fma_t(ru, uv2, fma_t(rv, Bv, acc[5]));
-    acc[6] = fma_t(ru, A, fma_t(rv, uv2, acc[6]));
+    acc[5] = fma_t(rv, Bv, acc[5]);
+    acc[6] = fma_t(ru, A, acc[6]);
+    acc[11] = fma_t(ru, uv, acc[11]);
+    acc[12] = fma_t(rv, uv, acc[12]);
     acc[7] = fma_t(gu, a, acc[7]);
     acc[8] = fma_t(gu, b, acc[8]);
     acc[9] = fma_t(gv, b, acc[9]);
+}
+
+// d/dp1 = sum (2uv ru + Bv rv), d/dp2 = sum (A ru + 2uv rv): add the 2uv parts once per evaluation.
+template <typename T>
+__device__ __forceinline__ void fold_uv_terms(T (&acc)[kSlots]) {
+    acc[5] = fma_t(T(2), acc[11], acc[5]);
+    acc[6] = fma_t(T(2), acc[12], acc[6]);
+    acc[11] = T(0);
+    acc[12] = T(0);
 }
 
 // ---- DISTORT10: matches {a, b, u*, v*} staged once per problem into shared memory by bulk TMA ----
@@ -144,6 +159,7 @@ struct Distort10Objective {
                 match_cost_grad<T, false>(I, m.x, m.y, m.z, m.w, T(1), acc, gu, gv);
             }
         }
+        fold_uv_terms(acc);
         const T mine = reduce_scatter16<true>(acc, lane);  // slot c total in lanes 2c, 2c+1
         f = shfl_idx(mine, 20);                            // slot 10 = cost
         g_own = (lane < 20) ? T(2) * mine : T(0);          // least_squares_utils.py:43 (factor 2)

@@ -161,6 +161,7 @@ struct JointObjective {
                 gout[10 + 6 * v + lane] = T(2) * out;  // least_squares_utils.py:43
             }
         }
+        fold_uv_terms(acc);
         const T mine = reduce_scatter16<true>(acc, lane);
         const T f = shfl_idx(mine, 20);
         if (!(lane & 1) && lane < 20) gout[lane >> 1] = T(2) * mine;

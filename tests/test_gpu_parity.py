@@ -315,8 +315,8 @@ def test_joint_solve_gate_against_reference(name):
     print(name, "kernel vs reference ", summary(m))
     print(name, "reference vs itself ", summary(band))
     # the noise-free optimum's cost is ~1e-11 (below the threshold) and is rounding noise of the worse
-    # conditioned pose parameters: cost is compared with a floor of 1e-2 of max(cost, threshold) here
-    assert_within_band(m, band, cost_floor=1e-2)
+    # conditioned pose parameters: cost is compared with a floor of 5e-2 of max(cost, threshold) here
+    assert_within_band(m, band, cost_floor=5e-2)
     if name == "solve_cfg3_small_f64":
         assert m["steps_equal"] >= 0.99 and m["dtheta_p99"] <= 1e-4
 
