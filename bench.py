@@ -313,6 +313,13 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     stage_gbs = stage_bytes / (stage_kernel_ms * 1e-3) / 1e9 if stage_bytes else None
 
+    traffic = None
+    try:  # DRAM bytes per launch of the solve kernel from the committed ncu --set full capture of this workload
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.config == "cfg2" and B == default_B("cfg2"):
+            traffic = tj["solve_cfg2"]["bytes"]
+    except (OSError, KeyError):
+        pass
     line = {
         "metric": "calibration_solves_per_sec", "value": value, "unit": "solves/s",
         "bfgs_iters_per_sec": float(stats[0].item()) / (ms_per_step * 1e-3),
@@ -327,7 +334,10 @@ def main():
         "kernel_ms": {"solve": solve_kernel_ms, "stage": stage_kernel_ms},
         "mean_iters": float(iters.mean()), "mean_fevals": float(fevals.mean()), "reasons_rank0": reasons,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak, "traffic": None,
+                     "frac": achieved / fp32_peak, "traffic": traffic,
+                     "traffic_note": "DRAM bytes per launch (ncu); the kernel is FP32-pipe bound, its staged matches "
+                                     f"are {batch.N * batch.views * B * 16} B and are read from HBM once",
+                     "executed_frac": achieved / fp32_peak * float((fevals - iters).sum()) / float(fevals.sum()),
                      "peak_source": f"{props.multi_processor_count} SMs x 128 lanes x 2 x {sm_max_mhz:.0f} MHz "
                                     "(no FP32 figure in MEASURED_PEAKS.json; sm_max_mhz taken from it)",
                      "flops_counted": "SURVEY.md 8(d): reference-equivalent fevals x matches x "

@@ -79,11 +79,58 @@ __global__ void __launch_bounds__(256) stage_kernel(int B, int N, const T* __res
     }
 }
 
+// Identity pose (BASELINE configs 2, 4, 5): no per-problem constants, so the [B*N] matches are one flat
+// array.  Each thread stages kStageUnroll matches a grid-stride apart and issues all of their loads
+// before the first use (20 B x 4 in flight per thread) — the kernel is pure HBM streaming:
+// 20 B read + 16 B written per match in float32.
+constexpr int kStageUnroll = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256) stage_identity_kernel(long long total, const T* __restrict__ pts,
+                                                             const T* __restrict__ obs, T* __restrict__ staged) {
+    using V4 = typename Vec4<T>::type;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = (long long)blockIdx.x * blockDim.x + threadIdx.x; base < total;
+         base += stride * kStageUnroll) {
+        T X[kStageUnroll], Y[kStageUnroll], Z[kStageUnroll], U[kStageUnroll], Vv[kStageUnroll];
+#pragma unroll
+        for (int k = 0; k < kStageUnroll; ++k) {
+            const long long i = base + k * stride;
+            if (i < total) {
+                X[k] = __ldg(pts + 3 * i); Y[k] = __ldg(pts + 3 * i + 1); Z[k] = __ldg(pts + 3 * i + 2);
+                U[k] = __ldg(obs + 2 * i); Vv[k] = __ldg(obs + 2 * i + 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kStageUnroll; ++k) {
+            const long long i = base + k * stride;
+            if (i < total) {
+                // R = I, t = 0 evaluated with the reference's sums (x*1 + y*0 + z*0 + 0 is exact); z' == 0 -> 1e-8
+                T zp = Z[k];
+                if (zp == T(0)) zp += T(1e-8);
+                V4 out;
+                out.x = div_rn(X[k], zp);
+                out.y = div_rn(Y[k], zp);
+                out.z = U[k];
+                out.w = Vv[k];
+                reinterpret_cast<V4*>(staged)[i] = out;
+            }
+        }
+    }
+}
+
 template <typename T>
 int launch_stage(int B, int N, const T* pts, const T* obs, const T* pose, T* staged, cudaStream_t s) {
     if (B == 0 || N == 0) return DAVO_OK;
-    const int grid = B < 148 * 64 ? B : 148 * 64;
-    stage_kernel<T><<<grid, 256, 0, s>>>(B, N, pts, obs, pose, staged);
+    if (!pose) {
+        const long long total = (long long)B * N;
+        long long blocks = (total + 256LL * kStageUnroll - 1) / (256LL * kStageUnroll);
+        if (blocks > 148LL * 64) blocks = 148LL * 64;
+        stage_identity_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(total, pts, obs, staged);
+    } else {
+        const int grid = B < 148 * 64 ? B : 148 * 64;
+        stage_kernel<T><<<grid, 256, 0, s>>>(B, N, pts, obs, pose, staged);
+    }
     count_launch();
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
 }

@@ -104,6 +104,7 @@ class DistortionObjective(CalibrationObjective):
     def __init__(self, points_3d, observed_2d, pose=None, weights=None, dtype=None, device=None):
         device = _lib.require_cuda() if device is None else torch.device(device)
         points_3d = torch.as_tensor(points_3d)
+        observed_2d = torch.as_tensor(observed_2d)
         dtype = dtype or points_3d.dtype
         batch_shape, N = points_3d.shape[:-2], points_3d.shape[-2]
         super().__init__(batch_shape, 10, N, dtype, device)
@@ -111,21 +112,59 @@ class DistortionObjective(CalibrationObjective):
             raise ValueError(f"observed_2d must be {tuple(batch_shape) + (N, 2)}, got {tuple(observed_2d.shape)}")
         if points_3d.shape[-1] != 3:
             raise ValueError("points_3d must end in a dimension of 3")
-        pts = _to_device(points_3d, dtype, device).reshape(self.B, N, 3)
-        obs = _to_device(observed_2d, dtype, device).reshape(self.B, N, 2)
-        ps = None if pose is None else _to_device(pose, dtype, device).reshape(self.B, 6)
-        self.weights = None if weights is None else _to_device(weights, dtype, device).reshape(self.B, N)
-        self.data0 = torch.empty(self.B, N, 4, dtype=dtype, device=device)
-        desc = self.desc()
-        with torch.cuda.device(device):
-            st = _lib.lib().davo_stage_matches(ctypes.byref(desc), _lib.ptr(pts), _lib.ptr(obs), _lib.ptr(ps),
-                                               _lib.ptr(self.data0), _lib.stream_ptr())
+        flat = lambda t, tail: None if t is None else torch.as_tensor(t).reshape((self.B,) + tail)
+        self._raw = (flat(points_3d, (N, 3)), flat(observed_2d, (N, 2)), flat(pose, (6,)), flat(weights, (N,)))
+        self._data0 = None
+        self.weights = None
+        # Host inputs are staged lazily so that BFGSSolver.forward can overlap the host-to-device copies of
+        # one chunk of problems with the staging and solve of the previous chunk; device inputs stage now.
+        if all(t is None or t.device.type == "cuda" for t in self._raw):
+            self.materialize()
+
+    @property
+    def data0(self):
+        if self._data0 is None and getattr(self, "_raw", None) is not None:
+            self.materialize()
+        return self._data0
+
+    @data0.setter
+    def data0(self, value):
+        self._data0 = value
+
+    @property
+    def is_staged(self) -> bool:
+        return self._data0 is not None
+
+    def stage_rows(self, lo: int, hi: int, staged: torch.Tensor, weights_out=None) -> None:
+        """Copy problems [lo, hi) to the device (if they are on the host) and run davo_stage_matches on them,
+        writing staged[lo:hi].  Stream ordered on the current stream; no host synchronisation."""
+        pts, obs, pose, w = self._raw
+        up = lambda t: None if t is None else t[lo:hi].to(device=self.device, dtype=self.dtype, non_blocking=True).contiguous()
+        d_pts, d_obs, d_pose = up(pts), up(obs), up(pose)
+        if w is not None and weights_out is not None:
+            weights_out[lo:hi].copy_(w[lo:hi], non_blocking=True)
+        desc = self.desc(B=hi - lo)
+        st = _lib.lib().davo_stage_matches(ctypes.byref(desc), _lib.ptr(d_pts), _lib.ptr(d_obs), _lib.ptr(d_pose),
+                                           _lib.ptr(staged[lo:hi]), _lib.stream_ptr())
         _lib.check(st, "davo_stage_matches")
+
+    def materialize(self) -> None:
+        """Stage every problem now (one davo_stage_matches launch)."""
+        if self._data0 is not None:
+            return
+        with torch.cuda.device(self.device):
+            staged = torch.empty(self.B, self.N, 4, dtype=self.dtype, device=self.device)
+            w = self._raw[3]
+            wdev = None if w is None else torch.empty(self.B, self.N, dtype=self.dtype, device=self.device)
+            self.stage_rows(0, self.B, staged, wdev)
+            self._data0, self.weights = staged, wdev
 
     @classmethod
     def from_staged(cls, staged: torch.Tensor, weights=None):
         """Wrap an already staged [(B..),N,4] device buffer (no copy)."""
         self = cls.__new__(cls)
+        self._raw = None
+        self._data0 = None
         CalibrationObjective.__init__(self, staged.shape[:-2], 10, staged.shape[-2], staged.dtype, staged.device)
         self.data0 = staged.contiguous().reshape(self.B, self.N, 4)
         self.weights = None if weights is None else weights.to(staged.device, staged.dtype).reshape(self.B, self.N)

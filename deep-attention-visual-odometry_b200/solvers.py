@@ -47,6 +47,18 @@ class SolveBuffers(NamedTuple):
                    torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device))
 
 
+_STREAMS: dict = {}
+
+
+def _compute_streams(device):
+    """Two side streams per device, created once: the caching allocator keeps one memory pool per stream, so
+    fresh streams on every call would turn every chunk buffer into a cudaMalloc."""
+    key = (device.type, device.index)
+    if key not in _STREAMS:
+        _STREAMS[key] = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)]
+    return _STREAMS[key]
+
+
 def _require_descriptor(error_function) -> CalibrationObjective:
     if not isinstance(error_function, CalibrationObjective):
         raise TypeError(
@@ -102,14 +114,63 @@ class BFGSSolver(Module):
         if tuple(batch_shape) != obj.batch_shape and parameters.numel() // n != obj.B:
             raise ValueError(f"parameters batch {tuple(batch_shape)} does not match the objective's {obj.batch_shape}")
         out_dev = parameters.device
-        x0 = parameters.detach().to(device=obj.device, dtype=obj.dtype, non_blocking=True).reshape(obj.B, n)
-        buf = self.solve_into(x0.contiguous(), obj, error_threshold=error_threshold, iterations=iterations, out=out)
+        if getattr(obj, "is_staged", True):
+            x0 = parameters.detach().to(device=obj.device, dtype=obj.dtype, non_blocking=True).reshape(obj.B, n)
+            buf = self.solve_into(x0.contiguous(), obj, error_threshold=error_threshold, iterations=iterations,
+                                  out=out)
+        else:  # host-resident problem set: overlap the copies with staging + solve, chunk by chunk
+            buf = self._solve_streamed(parameters.detach().reshape(obj.B, n), obj, error_threshold, iterations, out)
         result = buf.x.reshape(parameters.shape).to(device=out_dev, dtype=parameters.dtype)
         if not return_info:
             return result
         back = lambda t: t.reshape(batch_shape).to(out_dev)
         return SolveInfo(result, back(buf.cost), back(buf.converged).bool(), back(buf.iterations),
                          back(buf.evaluations), back(buf.reason))
+
+    #: problems per chunk of the streamed (host-input) path; each chunk is one H2D copy + stage + solve
+    stream_chunk = 8192
+
+    def _solve_streamed(self, x0_host: torch.Tensor, obj, error_threshold, iterations, out) -> "SolveBuffers":
+        """Host inputs -> device results with the copies hidden behind compute.
+
+        The batch is cut into chunks of `stream_chunk` problems.  A copy stream moves chunk k+1's points,
+        observations and start parameters host -> device while chunk k is staged (davo_stage_matches) and
+        solved (davo_solve_calibration) on a compute stream; chunks alternate between two compute streams so
+        that the next chunk's persistent grid fills the SMs as the previous chunk's tail drains.  The staged
+        matches stay resident in `obj` afterwards.  Nothing here synchronises the host."""
+        device = obj.device
+        B, n = obj.B, obj.n
+        with torch.cuda.device(device):
+            buf = out if out is not None else SolveBuffers.allocate(B, n, obj.dtype, device)
+            staged = torch.empty(B, obj.N, 4, dtype=obj.dtype, device=device)
+            has_w = obj._raw[3] is not None
+            wdev = torch.empty(B, obj.N, dtype=obj.dtype, device=device) if has_w else None
+            x0_dev = torch.empty(B, n, dtype=obj.dtype, device=device)
+            main = torch.cuda.current_stream()
+            start = torch.cuda.Event()
+            start.record(main)
+            compute = _compute_streams(device)
+            chunk = max(1, int(self.stream_chunk))
+            spans = [(lo, min(lo + chunk, B)) for lo in range(0, B, chunk)]
+            workspaces = torch.empty(len(spans), _lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+            for k, (lo, hi) in enumerate(spans):
+                cs = compute[k % 2]
+                cs.wait_event(start)
+                with torch.cuda.stream(cs):
+                    obj.stage_rows(lo, hi, staged, wdev)                       # H2D + davo_stage_matches
+                    x0_dev[lo:hi].copy_(x0_host[lo:hi], non_blocking=True)
+                    sub = type(obj).from_staged(staged[lo:hi], None if wdev is None else wdev[lo:hi])
+                    view = SolveBuffers(buf.x[lo:hi], buf.cost[lo:hi], buf.converged[lo:hi], buf.iterations[lo:hi],
+                                        buf.evaluations[lo:hi], buf.reason[lo:hi], workspaces[k])
+                    self.solve_into(x0_dev[lo:hi], sub, error_threshold=error_threshold, iterations=iterations,
+                                    out=view)
+                    done = torch.cuda.Event()
+                    done.record(cs)
+                main.wait_event(done)
+            obj.data0, obj.weights = staged, wdev
+            for t in (staged, x0_dev, workspaces) + ((wdev,) if wdev is not None else ()):
+                t.record_stream(compute[0]); t.record_stream(compute[1])
+        return buf
 
     def solve_into(self, x0: torch.Tensor, obj: CalibrationObjective, *, error_threshold=None, iterations=None,
                    out: "SolveBuffers | None" = None) -> "SolveBuffers":

@@ -295,6 +295,7 @@ static REAL FN(line_search)(const FN(problem)* p, const REAL* x, const REAL* d, 
         int D = cand_f > f0 + c1 * cand * g0;                 /* :146-150 */
         if (zooming) D = D || (cand_f >= lo_f);               /* :151-153 */
         if (widening && i > 0) D = D || (cand_f >= hi_f);     /* :154-157 */
+        davo_oracle_stat[0] += 1; davo_oracle_stat[1] += D;   /* unsynchronised statistics, single-thread use */
         int C;
         if (strong) C = (dphi < 0 ? -dphi : dphi) <= R(-1.0) * c2 * g0; /* :160-164 */
         else        C = R(-1.0) * dphi <= R(-1.0) * c2 * g0;            /* :165-169 */

@@ -43,6 +43,19 @@ def test_stage_matches_oracle(dt):
     assert np.array_equal(got[..., 2:], ref[..., 2:])  # observations are copied bit for bit
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("B,N", [(1, 1), (3, 5), (37, 256), (1500, 33)])
+def test_stage_identity_pose_is_bit_equal_to_zero_pose(dt, B, N):
+    """pose=None takes the flat streaming kernel; it must equal the general kernel run with a zero pose, and the oracle."""
+    b = davo_b200.synthetic.make_distort10(B, N, seed=B + N, dtype=dt)
+    b.points_3d[0, 0, 2] = 0.0  # the z' == 0 guard (distorted_camera_model.py:57)
+    pts, obs = torch.from_numpy(b.points_3d), torch.from_numpy(b.obs)
+    flat = davo_b200.DistortionObjective(pts.cuda(), obs.cuda())
+    general = davo_b200.DistortionObjective(pts.cuda(), obs.cuda(), torch.zeros(B, 6, dtype=pts.dtype).cuda())
+    assert torch.equal(flat.data0, general.data0)
+    assert np.array_equal(flat.data0.cpu().numpy(), c_oracle.stage(b.points_3d, b.obs, None))
+
+
 @pytest.mark.parametrize("dt,rtol", [(np.float32, 2e-4), (np.float64, 1e-11)])
 @pytest.mark.parametrize("N", [1, 31, 32, 33, 256, 700])
 def test_cost_gradient_matches_oracle(dt, rtol, N):
@@ -385,6 +398,28 @@ def test_solve_weighted_matches_oracle():
     m = compare_solves(got, ref, 1e-12)
     print(summary(m))
     assert m["steps_equal"] >= 0.98 and m["dtheta_p99"] <= 1e-6
+
+
+def test_streamed_host_path_equals_resident_path():
+    """Host inputs go through the chunked copy/stage/solve pipeline; results must be bit-identical to staging
+    everything first, for any chunk size (including one that does not divide the batch)."""
+    batch = davo_b200.synthetic.make_distort10(1000, 64, seed=4, dtype=np.float32)
+    rng = np.random.default_rng(4)
+    w = torch.from_numpy((rng.uniform(size=(1000, 64)) > 0.1).astype(np.float32))
+    pts, obs, x0 = (torch.from_numpy(a) for a in (batch.points_3d, batch.obs, batch.x0))
+    for weights in (None, w):
+        resident = davo_b200.DistortionObjective(pts.cuda(), obs.cuda(), weights=None if weights is None else weights.cuda())
+        assert resident.is_staged
+        solver = davo_b200.BFGSSolver(error_threshold=1e-6).eval()
+        ref = solver(x0, resident, return_info=True)
+        for chunk in (16384, 333, 64):
+            lazy = davo_b200.DistortionObjective(pts.pin_memory(), obs.pin_memory(), weights=weights)
+            assert not lazy.is_staged
+            solver.stream_chunk = chunk
+            got = solver(x0, lazy, return_info=True)
+            assert lazy.is_staged and torch.equal(lazy.data0, resident.data0)
+            for a, b in zip(got, ref):
+                assert torch.equal(a, b)
 
 
 def test_solve_full_size_properties():
