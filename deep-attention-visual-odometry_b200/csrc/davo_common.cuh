@@ -18,6 +18,9 @@ constexpr unsigned kFull = 0xffffffffu;
 template <typename T> struct Vec4;
 template <> struct Vec4<float> { using type = float4; };
 template <> struct Vec4<double> { using type = double4; };
+template <typename T> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
 
 // ---- non-contracted arithmetic ----------------------------------------------------------------
 // The control arithmetic of the solver (trial points, Wolfe tests, the H update) mirrors the

@@ -6,6 +6,7 @@
 #include "davo_common.cuh"
 #include "objectives_joint.cuh"
 #include "solver_wide.cuh"
+#include "solver_cta.cuh"
 #include "launch.h"
 
 namespace davo {
@@ -98,8 +99,78 @@ static int launch_joint(const SolveParams<T>& p, cudaStream_t stream) {
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
 }
 
+// ---- CTA-per-problem solve (W warps cooperate on one problem) -------------------------------------------
+template <typename T, int W>
+__host__ __device__ inline size_t joint_cta_smem(int N, int V, int n, bool has_w) {
+    return JointCtaObjective<T, W, false>::data_bytes(N, V, has_w) + CtaWorkspace<T>::bytes(n, W) + 32;
+}
+
+#ifndef DAVO_JOINT_MIN_BLOCKS
+#define DAVO_JOINT_MIN_BLOCKS 4
+#endif
+
+template <typename T, int W, bool kWeighted>
+__global__ void __launch_bounds__(32 * W, (W == 4 && sizeof(T) == 4) ? DAVO_JOINT_MIN_BLOCKS : 1) joint_cta_kernel(const SolveParams<T> p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using Obj = JointCtaObjective<T, W, kWeighted>;
+    const size_t data = Obj::data_bytes(p.N, p.V, p.has_w != 0);
+    CtaWorkspace<T> ws;
+    ws.carve(smem + data, p.n, W);
+    unsigned char* tail = smem + data + CtaWorkspace<T>::bytes(p.n, W);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+    volatile unsigned* slot = reinterpret_cast<volatile unsigned*>(tail + 16);
+    Obj obj(p, smem, ws.red, bar);
+    obj.init();
+    for (;;) {
+        if (threadIdx.x == 0) *slot = atomicAdd(p.queue, 1u);
+        __syncthreads();
+        const unsigned b = *slot;
+        if (b >= (unsigned)p.B) break;
+        obj.bind((int)b);  // starts with a barrier: every thread has read the slot before it is rewritten
+        solve_one_cta<T, W>(obj, p, (int)b, ws);
+    }
+}
+
+template <typename T, int W>
+static int launch_joint_cta(const SolveParams<T>& p, cudaStream_t stream) {
+    auto kernel = p.has_w ? joint_cta_kernel<T, W, true> : joint_cta_kernel<T, W, false>;
+    const size_t smem = joint_cta_smem<T, W>(p.N, p.V, p.n, p.has_w != 0);
+    int dev = 0, sms = 0, max_optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DAVO_ERR_CUDA;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * W, smem) != cudaSuccess || per_sm < 1)
+        return DAVO_ERR_CUDA;
+    long long grid = (long long)per_sm * sms;
+    if (grid > p.B) grid = p.B;
+    if (grid < 1) grid = 1;
+    if (cudaMemsetAsync(p.queue, 0, sizeof(unsigned), stream) != cudaSuccess) return DAVO_ERR_CUDA;
+    kernel<<<(unsigned)grid, 32 * W, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+}
+
+// W = the largest power of two <= min(V, 4): warp w evaluates views w, w+W, ...
+template <typename T>
+static int launch_joint_solve(const SolveParams<T>& p, cudaStream_t s) {
+    if (p.V < 1 || p.V > kMaxViews || p.n > kWideMax) return DAVO_ERR_UNSUPPORTED;
+    if (p.V >= 4) return launch_joint_cta<T, 4>(p, s);
+    if (p.V >= 2) return launch_joint_cta<T, 2>(p, s);
+    return launch_joint_cta<T, 1>(p, s);
+}
+
+#if DAVO_JOINT_WARP_SOLVE  // A/B: the warp-per-problem wide solver
 int launch_solve_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint<float, JMode::kSolve>(p, s); }
 int launch_solve_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint<double, JMode::kSolve>(p, s); }
+#else
+int launch_solve_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint_solve<float>(p, s); }
+int launch_solve_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint_solve<double>(p, s); }
+#endif
 int launch_eval_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint<float, JMode::kEval>(p, s); }
 int launch_eval_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint<double, JMode::kEval>(p, s); }
 int launch_line_search_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint<float, JMode::kLineSearch>(p, s); }

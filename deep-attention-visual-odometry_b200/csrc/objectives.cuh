@@ -100,7 +100,9 @@ __device__ __forceinline__ void fold_uv_terms(T (&acc)[kSlots]) {
 }
 
 // ---- DISTORT10: matches {a, b, u*, v*} staged once per problem into shared memory by bulk TMA ----
-template <typename T>
+// kWeighted is a compile-time switch (the launcher picks the instantiation) so that only one copy of the
+// match loop is compiled into a kernel: the solve kernel has to stay inside the instruction cache.
+template <typename T, bool kWeighted = false>
 struct Distort10Objective {
     using V4 = typename Vec4<T>::type;
     static constexpr bool kUsesSmemMatches = true;
@@ -131,7 +133,7 @@ struct Distort10Objective {
             mbar_expect_tx(bar, bytes_m);
             tma_load_1d(matches, p.data0 + (size_t)b * p.N * 4, bytes_m, bar);
         }
-        if (p.has_w) {  // [B,N] rows are not 16-byte aligned for every N: plain coalesced loads
+        if (kWeighted) {  // [B,N] rows are not 16-byte aligned for every N: plain coalesced loads
             for (int i = lane; i < p.N; i += 32) weights[i] = p.w[(size_t)b * p.N + i];
         }
         mbar_wait(bar, parity);
@@ -139,6 +141,8 @@ struct Distort10Objective {
         __syncwarp();
     }
 
+    // One evaluation.  Inlined at its three call sites (outer iteration, line-search probe, final cost): a
+    // __noinline__ version shrank the kernel from 57 KB to 27 KB of SASS but ran 12 % slower (call + stack).
     __device__ __forceinline__ void eval(const T* th, T& f, T& g_own) {
         Intrinsics<T> I;
         I.load(th);
@@ -146,18 +150,11 @@ struct Distort10Objective {
 #pragma unroll
         for (int k = 0; k < kSlots; ++k) acc[k] = T(0);
         T gu, gv;
-        if (p.has_w) {
-#pragma unroll 2
-            for (int i = lane; i < p.N; i += 32) {
-                const V4 m = matches[i];
-                match_cost_grad<T, true>(I, m.x, m.y, m.z, m.w, weights[i], acc, gu, gv);
-            }
-        } else {
+        const int N = p.N;
 #pragma unroll 4
-            for (int i = lane; i < p.N; i += 32) {
-                const V4 m = matches[i];
-                match_cost_grad<T, false>(I, m.x, m.y, m.z, m.w, T(1), acc, gu, gv);
-            }
+        for (int i = lane; i < N; i += 32) {
+            const V4 m = matches[i];
+            match_cost_grad<T, kWeighted>(I, m.x, m.y, m.z, m.w, kWeighted ? weights[i] : T(1), acc, gu, gv);
         }
         fold_uv_terms(acc);
         const T mine = reduce_scatter16<true>(acc, lane);  // slot c total in lanes 2c, 2c+1

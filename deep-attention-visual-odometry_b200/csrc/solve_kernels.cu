@@ -114,7 +114,9 @@ static int launch_warp_kernel(const SolveParams<T>& p, cudaStream_t stream) {
 
 template <typename T, Mode kMode>
 static int dispatch_model(const SolveParams<T>& p, cudaStream_t stream) {
-    if (p.model == DAVO_MODEL_DISTORT10) return launch_warp_kernel<T, 10, Distort10Objective<T>, kMode>(p, stream);
+    if (p.model == DAVO_MODEL_DISTORT10)
+        return p.has_w ? launch_warp_kernel<T, 10, Distort10Objective<T, true>, kMode>(p, stream)
+                       : launch_warp_kernel<T, 10, Distort10Objective<T, false>, kMode>(p, stream);
     if (p.model >= DAVO_MODEL_SPHERE && p.model <= DAVO_MODEL_DISTANCE) {
         if (p.n > kSlots) return DAVO_ERR_UNSUPPORTED;
         return launch_warp_kernel<T, kSlots, AnalyticObjective<T>, kMode>(p, stream);

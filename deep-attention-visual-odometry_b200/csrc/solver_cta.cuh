@@ -1,0 +1,361 @@
+// solver_cta.cuh — one CTA (W warps) solves one JOINT problem (intrinsics + 6 pose parameters per
+// view, n = 10 + 6V <= 64).  Same state machine as solver_warp.cuh / solver_wide.cuh, restated from
+//   autograd_solvers/bfgs_solver.py:80-303, utils/func_inverse_curvature.py:8-11,
+//   autograd_solvers/line_search/wolfe_conditions.py:23-253.
+//
+// Why a CTA here: one JOINT evaluation is V x N matches (1024 at config 3) and a 16K-problem batch
+// gives a warp-per-problem grid only ~9 problems per resident warp, so a quarter of the launch was tail.
+// With W = 4 warps per problem the per-problem latency drops ~4x, the CTA's staged points / observations /
+// H / vectors are shared by the 4 warps (more CTAs fit per SM), and there are ~22 problems per CTA to
+// balance.  Warp w evaluates views w, w+W, ...: a view's pose gradient never leaves its warp; only the
+// 11 intrinsic sums cross warps (shared memory + one barrier).
+//
+// Every thread carries the same scalar state (f, alpha, lo, hi, counters ...): dot products over the
+// n-vectors are recomputed per warp in the same order from shared memory, so the scalars are bitwise
+// identical across the CTA and all control flow is CTA-uniform (barriers are safe).
+#pragma once
+#include "davo_common.cuh"
+#include "objectives.cuh"
+#include "solver_warp.cuh"  // LineSearchResult, same_bits
+#include "solver_wide.cuh"  // warp_allreduce, wide_dot, kWideMax
+
+namespace davo {
+
+template <typename T>
+struct CtaWorkspace {
+    T *x, *g, *gprev, *d, *s, *y, *yH, *Hy, *xt, *gt, *H;
+    T* red;  // [W][16] per-warp intrinsic sums
+    int ld;
+    __host__ __device__ static size_t bytes(int n, int W) {
+        return sizeof(T) * (10 * (size_t)kWideMax + (size_t)n * (n + 1) + (size_t)W * kSlots);
+    }
+    __device__ void carve(unsigned char* base, int n, int W) {
+        T* p = reinterpret_cast<T*>(base);
+        x = p; g = x + kWideMax; gprev = g + kWideMax; d = gprev + kWideMax; s = d + kWideMax;
+        y = s + kWideMax; yH = y + kWideMax; Hy = yH + kWideMax; xt = Hy + kWideMax; gt = xt + kWideMax;
+        red = gt + kWideMax;
+        H = red + (size_t)W * kSlots;
+        ld = n + 1;
+    }
+};
+
+// The JOINT objective evaluated by a whole CTA.  th and gout are shared-memory vectors; the caller has
+// made th visible to the CTA (barrier) before the call; on return gout is visible to the CTA.
+template <typename T, int W, bool kWeighted>
+struct JointCtaObjective {
+    const SolveParams<T>& p;
+    T* world;  // [N,3]
+    T* obs;    // [V,N,2]
+    T* wts;    // [V,N] (only if p.has_w)
+    T* red;    // [W][16]
+    uint64_t* bar;
+    unsigned parity;
+    int lane, warp, tid;
+
+    // world points are padded to a multiple of 4 elements so that the observations start 16-byte aligned
+    // (bulk-TMA destination, float2 / double2 reads) for every N
+    __host__ __device__ static size_t world_elems(int N) { return ((size_t)N * 3 + 3) & ~size_t(3); }
+    __host__ __device__ static size_t obs_elems(int N, int V) { return ((size_t)V * N * 2 + 3) & ~size_t(3); }
+    __host__ __device__ static size_t data_bytes(int N, int V, bool has_w) {
+        size_t b = sizeof(T) * (world_elems(N) + obs_elems(N, V) + (has_w ? (size_t)V * N : 0));
+        return (b + 127) & ~size_t(127);
+    }
+
+    __device__ JointCtaObjective(const SolveParams<T>& p_, unsigned char* slab, T* red_, uint64_t* bar_)
+        : p(p_), red(red_), bar(bar_), parity(0) {
+        tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
+        world = reinterpret_cast<T*>(slab);
+        obs = world + world_elems(p.N);
+        wts = obs + obs_elems(p.N, p.V);
+    }
+
+    __device__ __forceinline__ void init() {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+
+    // Stage problem b: two bulk TMA copies (world points, observations) completing on one mbarrier.
+    __device__ __forceinline__ void bind(int b) {
+        __syncthreads();  // every warp is done with the previous problem's slab
+        const size_t wb = sizeof(T) * (size_t)p.N * 3, ob = sizeof(T) * (size_t)p.V * p.N * 2;
+        const T* gw = p.data0 + (size_t)b * p.N * 3;
+        const T* go = p.data1 + (size_t)b * p.V * p.N * 2;
+        const bool bulk = (wb % 16 == 0) && (ob % 16 == 0);
+        if (bulk) {
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(bar, (unsigned)(wb + ob));
+                tma_load_1d(world, gw, (unsigned)wb, bar);
+                tma_load_1d(obs, go, (unsigned)ob, bar);
+            }
+        } else {
+            for (int i = tid; i < p.N * 3; i += 32 * W) world[i] = gw[i];
+            for (int i = tid; i < p.V * p.N * 2; i += 32 * W) obs[i] = go[i];
+        }
+        if (kWeighted)
+            for (int i = tid; i < p.V * p.N; i += 32 * W) wts[i] = p.w[(size_t)b * p.V * p.N + i];
+        if (bulk) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        }
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ T eval(const T* th, T* gout) {
+        using V2 = typename Vec2<T>::type;
+        const int N = p.N, V = p.V;
+        Intrinsics<T> I;
+        I.load(th);
+        T acc[kSlots];
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k) acc[k] = T(0);
+        for (int v = warp; v < V; v += W) {
+            const T* pose = th + 10 + 6 * v;
+            // sin/cos of this view's three Euler angles: lanes 0..2 compute, everyone receives
+            T sn = T(0), cs = T(0);
+            if (lane < 3) {
+                const T ang = pose[lane];
+                sn = sin(ang);
+                cs = cos(ang);
+            }
+            const T sx = shfl_idx(sn, 0), cx = shfl_idx(cs, 0), sy = shfl_idx(sn, 1), cy = shfl_idx(cs, 1),
+                    sz = shfl_idx(sn, 2), cz = shfl_idx(cs, 2);
+            const T t0 = pose[3], t1 = pose[4], t2 = pose[5];
+            // R = Rz Ry Rx, distorted_camera_model.py:38-55
+            const T r00 = cy * cz, r01 = sx * sy * cz - cx * sz, r02 = cx * sy * cz + sx * sz;
+            const T r10 = cy * sz, r11 = sx * sy * sz + cx * cz, r12 = cx * sy * sz - sx * cz;
+            const T r20 = -sy, r21 = sx * cy, r22 = cx * cy;
+            T part[kSlots];  // 0..8: M = sum gX' (x) X (row major), 9..11: g_t = sum gX'
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k) part[k] = T(0);
+            const V2* ob = reinterpret_cast<const V2*>(obs) + (size_t)v * N;
+            const T* wv = wts + (size_t)v * N;
+#pragma unroll 2
+            for (int i = lane; i < N; i += 32) {
+                const T X = world[3 * i], Y = world[3 * i + 1], Z = world[3 * i + 2];
+                const V2 o = ob[i];
+                const T xp = fma_t(X, r00, fma_t(Y, r01, fma_t(Z, r02, t0)));
+                const T yp = fma_t(X, r10, fma_t(Y, r11, fma_t(Z, r12, t1)));
+                T zp = fma_t(X, r20, fma_t(Y, r21, fma_t(Z, r22, t2)));
+                if (zp == T(0)) zp += T(1e-8);  // :57
+                const T iz = div_rn(T(1), zp);
+                const T a = xp * iz, b = yp * iz;
+                T gu, gv;
+                match_cost_grad<T, kWeighted>(I, a, b, o.x, o.y, kWeighted ? wv[i] : T(1), acc, gu, gv);
+                const T gA = gu * I.fx;
+                const T gB = fma_t(gu, I.s, gv * I.fy);
+                const T gx = gA * iz, gy = gB * iz;
+                const T gz = -fma_t(gA, a, gB * b) * iz;
+                part[0] = fma_t(gx, X, part[0]); part[1] = fma_t(gx, Y, part[1]); part[2] = fma_t(gx, Z, part[2]);
+                part[3] = fma_t(gy, X, part[3]); part[4] = fma_t(gy, Y, part[4]); part[5] = fma_t(gy, Z, part[5]);
+                part[6] = fma_t(gz, X, part[6]); part[7] = fma_t(gz, Y, part[7]); part[8] = fma_t(gz, Z, part[8]);
+                part[9] += gx; part[10] += gy; part[11] += gz;
+            }
+            const T mine = reduce_scatter16<true>(part, lane);  // total of slot lane >> 1
+            // every lane needs all of M for <dR/dr_k, M>_F: 12 broadcasts from the owning lanes
+            const T m0 = shfl_idx(mine, 0), m1 = shfl_idx(mine, 2), m2 = shfl_idx(mine, 4), m3 = shfl_idx(mine, 6),
+                    m4 = shfl_idx(mine, 8), m5 = shfl_idx(mine, 10), m6 = shfl_idx(mine, 12),
+                    m7 = shfl_idx(mine, 14), m8 = shfl_idx(mine, 16);
+            if (lane < 3) {
+                T d0, d1, d2, d3, d4, d5, d6, d7, d8;  // dR/dr_k of R = Rz Ry Rx
+                if (lane == 0) {
+                    d0 = T(0); d1 = cx * sy * cz + sx * sz;  d2 = -sx * sy * cz + cx * sz;
+                    d3 = T(0); d4 = cx * sy * sz - sx * cz;  d5 = -sx * sy * sz - cx * cz;
+                    d6 = T(0); d7 = cx * cy;                 d8 = -sx * cy;
+                } else if (lane == 1) {
+                    d0 = -sy * cz; d1 = sx * cy * cz; d2 = cx * cy * cz;
+                    d3 = -sy * sz; d4 = sx * cy * sz; d5 = cx * cy * sz;
+                    d6 = -cy;      d7 = -sx * sy;     d8 = -cx * sy;
+                } else {
+                    d0 = -cy * sz; d1 = -sx * sy * sz - cx * cz; d2 = -cx * sy * sz + sx * cz;
+                    d3 = cy * cz;  d4 = sx * sy * cz - cx * sz;  d5 = cx * sy * cz + sx * sz;
+                    d6 = T(0); d7 = T(0); d8 = T(0);
+                }
+                const T out = d0 * m0 + d1 * m1 + d2 * m2 + d3 * m3 + d4 * m4 + d5 * m5 + d6 * m6 + d7 * m7 + d8 * m8;
+                gout[10 + 6 * v + lane] = T(2) * out;  // least_squares_utils.py:43
+            }
+            if (lane >= 18 && lane < 24 && !(lane & 1)) gout[10 + 6 * v + 3 + ((lane - 18) >> 1)] = T(2) * mine;  // d/dt
+        }
+        fold_uv_terms(acc);
+        const T mine = reduce_scatter16<true>(acc, lane);
+        if (!(lane & 1)) red[warp * kSlots + (lane >> 1)] = mine;
+        __syncthreads();
+        T f = T(0);
+#pragma unroll
+        for (int w = 0; w < W; ++w) f += red[w * kSlots + 10];
+        if (tid < 10) {
+            T gsum = T(0);
+#pragma unroll
+            for (int w = 0; w < W; ++w) gsum += red[w * kSlots + tid];
+            gout[tid] = T(2) * gsum;
+        }
+        __syncthreads();
+        return f;
+    }
+};
+
+// out[c] = scale * sum_j H[c][j] v[j].  n is small (34 at config 3), so a whole warp per row would idle
+// most lanes and pay a 5-step butterfly per row; instead FOUR threads share a row (j = q, q+4, ...) and
+// combine with two shuffles, i.e. 8 rows per warp and 32 rows per pass of a 4-warp CTA.
+template <typename T, int W>
+__device__ __forceinline__ void cta_matvec(const T* H, int ld, const T* v, T* out, int n, T scale) {
+    const int tid = threadIdx.x, q = tid & 3;
+    constexpr int kRowsPerPass = 32 * W / 4;
+    for (int c0 = 0; c0 < n; c0 += kRowsPerPass) {   // CTA-uniform trip count: the shuffles below are safe
+        const int c = c0 + (tid >> 2);
+        T a = T(0);
+        if (c < n)
+            for (int j = q; j < n; j += 4) a = fma_t(H[c * ld + j], v[j], a);
+        a += shfl_xor(a, 1);
+        a += shfl_xor(a, 2);
+        if (c < n && q == 0) out[c] = scale * a;
+    }
+}
+
+template <typename T, int W, typename Obj>
+__device__ __forceinline__ LineSearchResult<T> line_search_cta(Obj& obj, const SolveParams<T>& p, const T* x,
+                                                               const T* d, T f0, const T* g, T* xt, T* gt) {
+    const int n = p.n, tid = threadIdx.x, lane = tid & 31;
+    const T g0 = wide_dot(d, g, n, lane);       // :77 (each warp, same order: identical in every thread)
+    bool widening = true, zooming = false;      // :80-82
+    T lo = T(0), hi = T(0), cand = T(1);        // :97-108
+    T lo_f = f0, hi_f = f0, cand_f = f0;        // :109-111
+    int probes = 0;
+    const T neg_c2_g0 = mul_rn(T(-1) * p.c2, g0);
+    for (int i = 0; i < p.max_ls; ++i) {        // :116
+        if (!(widening || zooming)) break;      // :119-121
+        if (i > 0) {
+            if (widening) { hi = cand; hi_f = cand_f; cand = mul_rn(T(2), cand); }  // :125-127
+            if (zooming) cand = mul_rn(T(0.5), add_rn(lo, hi));                      // :128-131
+        }
+        if (tid < n) xt[tid] = add_rn(x[tid], mul_rn(cand, d[tid]));                 // :139
+        __syncthreads();
+        cand_f = obj.eval(xt, gt);
+        const T dphi = wide_dot(d, gt, n, lane);                                    // :141
+        ++probes;
+        bool D = cand_f > add_rn(f0, mul_rn(mul_rn(p.c1, cand), g0));               // :146-150
+        if (zooming) D = D || (cand_f >= lo_f);                                     // :151-153
+        if (widening && i > 0) D = D || (cand_f >= hi_f);                           // :154-157
+        const bool C = p.strong ? (fabs(dphi) <= neg_c2_g0) : (mul_rn(T(-1), dphi) <= neg_c2_g0);  // :160-169
+        const bool G = widening ? (dphi >= T(0)) : (mul_rn(dphi, sub_rn(hi, lo)) >= T(0));         // :174-180
+        if (zooming) {                                                              // :187-207
+            if (D) { hi = cand; hi_f = cand_f; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; zooming = false; }
+            else { if (G) { hi = lo; hi_f = lo_f; } lo = cand; lo_f = cand_f; }
+        } else {                                                                    // :216-237
+            if (D) { lo = hi; lo_f = hi_f; hi = cand; hi_f = cand_f; widening = false; zooming = true; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; widening = false; }
+            else if (G) { lo = cand; lo_f = cand_f; widening = false; zooming = true; }
+        }
+        if (zooming && !(lo != hi)) zooming = false;                                // :236
+    }
+    LineSearchResult<T> r;
+    r.alpha = hi; r.last_cand = cand; r.last_f = cand_f; r.last_g = T(0); r.probes = probes;
+    return r;
+}
+
+// bfgs_solver.py:80-215 for one problem, executed by the whole CTA.
+template <typename T, int W, typename Obj>
+__device__ __forceinline__ void solve_one_cta(Obj& obj, const SolveParams<T>& p, int b, CtaWorkspace<T>& ws) {
+    const int n = p.n, ld = ws.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kThreads = 32 * W;
+    T *x = ws.x, *g = ws.g, *gprev = ws.gprev, *gt = ws.gt;
+    T *d = ws.d, *s = ws.s, *y = ws.y, *yH = ws.yH, *Hy = ws.Hy, *H = ws.H;
+    if (tid < n) {
+        x[tid] = p.x0[(size_t)b * n + tid];
+        s[tid] = T(0);
+        g[tid] = T(0);
+    }
+    for (int i = warp; i < n; i += W)
+        for (int j = lane; j < n; j += 32) H[i * ld + j] = (i == j) ? T(1) : T(0);  // :112-117
+    __syncthreads();
+    T f = T(0);
+    int iters = 0, fevals = 0, reason = DAVO_REASON_CAP;
+    bool have_fg = false, have_f = false;
+
+    for (int k = 0; k < p.max_iters; ++k) {  // :118
+        if (!have_fg) f = obj.eval(x, g);    // :128-135
+        ++fevals;
+        have_f = true;
+        if (!(f > p.thr)) {                  // :143
+            reason = (f <= p.thr) ? DAVO_REASON_THRESHOLD : DAVO_REASON_NAN;
+            break;
+        }
+        if (k == 0) {
+            if (tid < n) d[tid] = mul_rn(T(-1), g[tid]);  // :152-155
+        } else {
+            if (tid < n) y[tid] = sub_rn(g[tid], gprev[tid]);  // :157
+            __syncthreads();
+            const T sy = wide_dot(s, y, n, lane);
+            if (k == 1) {                                      // :159-167, :217-233
+                T den = wide_dot(y, y, n, lane);
+                den = (den < T(1e-5)) ? T(1e-5) : den;
+                T sc = div_rn(sy, den);
+                sc = (sc < T(1e-4)) ? T(1e-4) : sc;
+                for (int i = warp; i < n; i += W)
+                    for (int j = lane; j < n; j += 32) H[i * ld + j] = mul_rn(sc, H[i * ld + j]);
+                __syncthreads();
+            }
+            T rho = div_rn(T(1), sy);                          // func_inverse_curvature.py:8-11
+            if (sy <= T(0)) rho = T(0);
+            // H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the right (:263-303),
+            // using y^T H = (H y)^T (H stays symmetric to rounding under this update; see solver_warp.cuh).
+            cta_matvec<T, W>(H, ld, y, Hy, n, T(1));           // (H y)_c, :293-295: one warp per row
+            __syncthreads();
+            const T q = mul_rn(wide_dot(y, Hy, n, lane), rho); // y^T H y / (y^T s), :271-274
+            const T onepq = add_rn(T(1), q);
+            {   // all W*32 threads walk the n x n elements; (i, j) advance without a division
+                const int step_i = kThreads / n, step_j = kThreads % n;
+                int i = tid / n, j = tid % n;
+                for (int e = tid; e < n * n; e += kThreads) {
+                    const T sri = mul_rn(s[i], rho);
+                    const T inner = fma_t(s[j], onepq, -Hy[j]);            // s_j (1+q) - (y^T H)_j
+                    H[i * ld + j] = fma_t(-mul_rn(Hy[i], rho), s[j], fma_t(sri, inner, H[i * ld + j]));
+                    i += step_i;
+                    j += step_j;
+                    if (j >= n) { j -= n; ++i; }
+                }
+            }
+            __syncthreads();
+            cta_matvec<T, W>(H, ld, g, d, n, T(-1));           // d = -H g, :173-176
+        }
+        __syncthreads();
+        const LineSearchResult<T> ls = line_search_cta<T, W>(obj, p, x, d, f, g, ws.xt, gt);  // :181-190
+        fevals += ls.probes;
+        ++iters;
+        if (tid < n) {                                         // :191-199
+            const T sc = mul_rn(ls.alpha, d[tid]);
+            s[tid] = sc;
+            x[tid] = add_rn(x[tid], sc);
+        }
+        __syncthreads();
+        const T nrm = sqrt_rn(wide_dot(s, s, n, lane));        // :203-205
+        have_fg = same_bits(ls.alpha, ls.last_cand);
+        have_f = have_fg;
+        {   // rotate gradient buffers: gprev <- g, and g <- gt when the accepted point is the last probe
+            T* old = gprev;
+            gprev = g;
+            if (have_fg) { g = gt; gt = old; f = ls.last_f; }
+            else { g = old; }
+        }
+        if (!(nrm > p.min_step)) {                             // :203-207
+            reason = DAVO_REASON_STEP;
+            break;
+        }
+    }
+    if (!have_f) f = obj.eval(x, gt);  // cost at the returned parameters (networks/calibration_network.py:71)
+    __syncthreads();
+    if (tid < n) p.x_out[(size_t)b * n + tid] = x[tid];
+    if (tid == 0) {
+        if (p.cost_out) p.cost_out[b] = f;
+        if (p.converged_out) p.converged_out[b] = (f <= p.thr) ? 1 : 0;
+        if (p.iters_out) p.iters_out[b] = iters;
+        if (p.fevals_out) p.fevals_out[b] = fevals;
+        if (p.reason_out) p.reason_out[b] = reason;
+    }
+}
+
+}  // namespace davo
