@@ -313,11 +313,12 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     stage_gbs = stage_bytes / (stage_kernel_ms * 1e-3) / 1e9 if stage_bytes else None
 
-    traffic = None
+    traffic = stage_traffic = None
     try:  # DRAM bytes per launch of the solve kernel from the committed ncu --set full capture of this workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if args.config == "cfg2" and B == default_B("cfg2"):
-            traffic = tj["solve_cfg2"]["bytes"]
+        if B == default_B(args.config) and args.config in ("cfg2", "cfg3"):
+            traffic = tj["solve_" + args.config]["bytes"]
+        stage_traffic = tj["stage_cfg2"]["bytes"] if (args.config == "cfg2" and B == default_B("cfg2")) else None
     except (OSError, KeyError):
         pass
     line = {
@@ -344,7 +345,7 @@ def main():
                                       f"{FLOP_PER_MATCH_EVAL[batch.model]:.0f} + iters x (12n^2+10n)"},
         "roofline_staging": None if stage_gbs is None else {
             "bound": "hbm", "achieved": stage_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,
-            "traffic": None, "bytes_counted": "20 B read + 16 B written per match"},
+            "traffic": stage_traffic, "bytes_counted": "20 B read + 16 B written per match"},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
     }
     if not args.no_cpu_baseline and world == 1:

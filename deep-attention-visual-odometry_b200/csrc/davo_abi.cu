@@ -17,7 +17,7 @@ static int check_desc(const davo_problem_desc* d) {
     if (!d) return DAVO_ERR_NULL_POINTER;
     if (d->B < 0 || d->N < 0 || d->n < 1 || d->V < 1) return DAVO_ERR_BAD_SHAPE;
     if (d->dtype != DAVO_F32 && d->dtype != DAVO_F64) return DAVO_ERR_UNSUPPORTED;
-    if (d->max_iters < 0 || d->max_ls_iters < 0) return DAVO_ERR_BAD_ARGUMENT;
+    if (d->max_iters < 0 || d->max_ls_iters < 1) return DAVO_ERR_BAD_ARGUMENT;
     if (d->model == DAVO_MODEL_DISTORT10) {
         if (d->n != 10 || d->V != 1) return DAVO_ERR_BAD_SHAPE;
     } else if (d->model == DAVO_MODEL_JOINT) {

@@ -153,10 +153,20 @@ __device__ __forceinline__ bool same_bits<double>(double a, double b) {
     return __double_as_longlong(a) == __double_as_longlong(b);
 }
 
-// bfgs_solver.py:80-215 for one problem.  NP = compile-time bound on n (row length held in registers).
+// bfgs_solver.py:80-215 driving wolfe_conditions.py:23-239 for one problem.  NP = compile-time bound on n
+// (row length of H held in registers).
+//
+// The outer loop and the line search are written as ONE loop around ONE objective evaluation: the
+// evaluator is the bulk of the kernel's code, and with a separate call site in the outer iteration, the line
+// search and the final cost it was inlined three times (57 KB of SASS, beyond the instruction cache).
+// `mode` says what the evaluation that is about to run is for:
+//   kEvalOuter  (f, grad) at x for the top of an outer iteration          bfgs_solver.py:128-135
+//   kEvalProbe  a line-search probe at x + cand * d                       wolfe_conditions.py:134-143
+//   kEvalFinal  the cost at the returned parameters                       networks/calibration_network.py:71
 template <typename T, int NP, typename Obj>
 __device__ __forceinline__ void solve_one_warp(Obj& obj, const SolveParams<T>& p, int b, T* xt_line, T* bc_line,
                                                int lane) {
+    enum { kEvalOuter, kEvalProbe, kEvalFinal };
     const int n = p.n;
     const int c = lane >> 1;
     const bool own = c < n;
@@ -165,112 +175,185 @@ __device__ __forceinline__ void solve_one_warp(Obj& obj, const SolveParams<T>& p
     T H[NP];
 #pragma unroll
     for (int j = 0; j < NP; ++j) H[j] = (j == c) ? T(1) : T(0);  // :112-117
-    int iters = 0, fevals = 0, reason = DAVO_REASON_CAP;
-    bool have_fg = false, have_f = false;
+    int iters = 0, fevals = 0, reason = DAVO_REASON_CAP, k = 0;
+    // line-search state (wolfe_conditions.py:77-114)
+    bool widening = false, zooming = false;
+    T lo = T(0), hi = T(0), cand = T(1), lo_f = T(0), hi_f = T(0), cand_f = T(0), f0 = T(0), g0 = T(0),
+      neg_c2_g0 = T(0), gt = T(0);
+    int ls_i = 0;
+    int mode = (p.max_iters > 0) ? kEvalOuter : kEvalFinal;
 
-    for (int k = 0; k < p.max_iters; ++k) {  // :118
-        if (!have_fg) eval_at(obj, x, xt_line, lane, f, g);  // :128-135
-        ++fevals;
-        have_f = true;
-        if (!(f > p.thr)) {  // :143 (strict >; NaN retires)
-            reason = (f <= p.thr) ? DAVO_REASON_THRESHOLD : DAVO_REASON_NAN;
+    for (;;) {
+        const T pt = (mode == kEvalProbe) ? add_rn(x, mul_rn(cand, d)) : x;  // wolfe_conditions.py:139
+        T fe, ge;
+        eval_at(obj, pt, xt_line, lane, fe, ge);
+        if (mode == kEvalFinal) {
+            f = fe;
             break;
         }
-        if (k == 0) {
-            d = mul_rn(T(-1), g);  // :152-155
+        bool start_iteration = false;
+        if (mode == kEvalOuter) {
+            f = fe;
+            g = ge;
+            start_iteration = true;
         } else {
-            const T y = sub_rn(g, gprev);                    // :157
-            const T sy = slot_allreduce(mul_rn(s, y));       // y^T s
-            if (k == 1) {                                    // :159-167, :217-233 (eq. 6.20)
-                T den = slot_allreduce(mul_rn(y, y));
-                den = (den < T(1e-5)) ? T(1e-5) : den;
-                T sc = div_rn(sy, den);
-                sc = (sc < T(1e-4)) ? T(1e-4) : sc;
-#pragma unroll
-                for (int j = 0; j < NP; ++j) H[j] = mul_rn(sc, H[j]);
+            // ---- one line-search probe has been evaluated: wolfe_conditions.py:143-237 ----
+            cand_f = fe;
+            gt = ge;
+            ++fevals;
+            const T dphi = slot_allreduce(mul_rn(d, gt));                  // d/d alpha f(x + alpha d), :141
+            bool D = cand_f > add_rn(f0, mul_rn(mul_rn(p.c1, cand), g0)); // :146-150
+            if (zooming) D = D || (cand_f >= lo_f);                       // :151-153
+            if (widening && ls_i > 0) D = D || (cand_f >= hi_f);          // :154-157
+            const bool C = p.strong ? (fabs(dphi) <= neg_c2_g0)           // :160-164
+                                    : (mul_rn(T(-1), dphi) <= neg_c2_g0); // :165-169
+            const bool G = widening ? (dphi >= T(0)) : (mul_rn(dphi, sub_rn(hi, lo)) >= T(0));  // :174-180
+            if (zooming) {                                                // :187-207
+                if (D) {
+                    hi = cand; hi_f = cand_f;
+                } else if (C) {
+                    hi = lo = cand; hi_f = lo_f = cand_f; zooming = false;
+                } else {
+                    if (G) { hi = lo; hi_f = lo_f; }
+                    lo = cand; lo_f = cand_f;
+                }
+            } else {                                                      // widening, :216-237
+                if (D) {
+                    lo = hi; lo_f = hi_f; hi = cand; hi_f = cand_f; widening = false; zooming = true;
+                } else if (C) {
+                    hi = lo = cand; hi_f = lo_f = cand_f; widening = false;
+                } else if (G) {
+                    lo = cand; lo_f = cand_f; widening = false; zooming = true;
+                }
             }
-            T rho = div_rn(T(1), sy);                        // func_inverse_curvature.py:8-11
-            if (sy <= T(0)) rho = T(0);
+            if (zooming && !(lo != hi)) zooming = false;                  // :236
+            ++ls_i;
+            if ((widening || zooming) && ls_i < p.max_ls) {               // :116-121: another probe
+                if (widening) {                                           // :125-127
+                    hi = cand; hi_f = cand_f; cand = mul_rn(T(2), cand);
+                }
+                if (zooming) cand = mul_rn(T(0.5), add_rn(lo, hi));       // :128-131, :242-253
+                continue;
+            }
+            // ---- line search finished, alpha = upper_alpha (:239): take the step, bfgs_solver.py:191-207 ----
+            ++iters;
+            s = mul_rn(hi, d);                                            // :191
+            x = add_rn(x, s);                                             // :192
+            const T nrm = sqrt_rn(slot_allreduce(mul_rn(s, s)));          // :203-205
+            gprev = g;
+            // The accepted point is bitwise x + alpha d: when the search returns the probe it has just made,
+            // that probe's (f, grad) ARE the next outer iteration's evaluation.
+            const bool reuse = same_bits(hi, cand);
+            ++k;
+            const bool stop_step = !(nrm > p.min_step);                   // :203-207 (strict >)
+            if (stop_step || k >= p.max_iters) {                          // :118
+                reason = stop_step ? DAVO_REASON_STEP : DAVO_REASON_CAP;
+                if (reuse) {
+                    f = cand_f;
+                    break;
+                }
+                mode = kEvalFinal;
+                continue;
+            }
+            if (!reuse) {
+                mode = kEvalOuter;
+                continue;
+            }
+            f = cand_f;
+            g = gt;
+            start_iteration = true;
+        }
+        if (start_iteration) {
+            // ---- top of an outer iteration with (f, g) at x: bfgs_solver.py:136-190 ----
+            ++fevals;  // the reference evaluates here even when we could reuse the probe
+            if (!(f > p.thr)) {                                           // :143 (strict >; NaN retires)
+                reason = (f <= p.thr) ? DAVO_REASON_THRESHOLD : DAVO_REASON_NAN;
+                break;
+            }
+            if (k == 0) {
+                d = mul_rn(T(-1), g);                                     // :152-155
+            } else {
+                const T y = sub_rn(g, gprev);                             // :157
+                const T sy = slot_allreduce(mul_rn(s, y));                // y^T s
+                if (k == 1) {                                             // :159-167, :217-233 (eq. 6.20)
+                    T den = slot_allreduce(mul_rn(y, y));
+                    den = (den < T(1e-5)) ? T(1e-5) : den;
+                    T sc = div_rn(sy, den);
+                    sc = (sc < T(1e-4)) ? T(1e-4) : sc;
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) H[j] = mul_rn(sc, H[j]);
+                }
+                T rho = div_rn(T(1), sy);                                 // func_inverse_curvature.py:8-11
+                if (sy <= T(0)) rho = T(0);
+                T gvv[NP];
 #if DAVO_FAITHFUL_BFGS
-            // Literal restatement: y^T H and H y are formed separately (H is symmetric only up to rounding)
-            // and every product is rounded before the next operation, as ATen does.
-            T yv[NP], sv[NP], yHv[NP];
-            slot_gather<T, NP>(y, bc_line, lane, yv);
-            slot_gather<T, NP>(s, bc_line, lane, sv);
-            T Hy = T(0);                                     // (H y)_c, :293-295
-            T part[kSlots];
+                // Literal restatement: y^T H and H y are formed separately (H is symmetric only up to
+                // rounding) and every product is rounded before the next operation, as ATen does.
+                T yv[NP], sv[NP], yHv[NP];
+                slot_gather<T, NP>(y, bc_line, lane, yv);
+                slot_gather<T, NP>(s, bc_line, lane, sv);
+                T Hy = T(0);                                              // (H y)_c, :293-295
+                T part[kSlots];
 #pragma unroll
-            for (int j = 0; j < kSlots; ++j) part[j] = T(0);
+                for (int j = 0; j < kSlots; ++j) part[j] = T(0);
 #pragma unroll
-            for (int j = 0; j < NP; ++j) {
-                Hy = fma_t(H[j], yv[j], Hy);
-                part[j] = mul_rn(y, H[j]);                   // y_c H[c][j]
-            }
-            const T yH = reduce_scatter16<false>(part, lane);  // (y^T H)_c, :268-270
-            slot_gather<T, NP>(yH, bc_line, lane, yHv);
-            T q = T(0);                                      // :271-274
+                for (int j = 0; j < NP; ++j) {
+                    Hy = fma_t(H[j], yv[j], Hy);
+                    part[j] = mul_rn(y, H[j]);                            // y_c H[c][j]
+                }
+                const T yH = reduce_scatter16<false>(part, lane);         // (y^T H)_c, :268-270
+                slot_gather<T, NP>(yH, bc_line, lane, yHv);
+                T q = T(0);                                               // :271-274
 #pragma unroll
-            for (int j = 0; j < NP; ++j) q = fma_t(yHv[j], mul_rn(yv[j], rho), q);
-            const T sr = mul_rn(s, rho);                     // :277
-            const T onepq = add_rn(T(1), q);
+                for (int j = 0; j < NP; ++j) q = fma_t(yHv[j], mul_rn(yv[j], rho), q);
+                const T sr = mul_rn(s, rho);                              // :277
+                const T onepq = add_rn(T(1), q);
 #pragma unroll
-            for (int j = 0; j < NP; ++j) {                   // :278-303, old H on the right-hand side
-                const T srj = mul_rn(sv[j], rho);
-                const T sop = mul_rn(mul_rn(sr, sv[j]), onepq);
-                const T sgp = mul_rn(sr, yHv[j]);
-                const T gsp = mul_rn(Hy, srj);
-                H[j] = sub_rn(sub_rn(add_rn(H[j], sop), sgp), gsp);
-            }
-            T gvv[NP];
-            slot_gather<T, NP>(g, bc_line, lane, gvv);
+                for (int j = 0; j < NP; ++j) {                            // :278-303, old H on the right
+                    const T srj = mul_rn(sv[j], rho);
+                    const T sop = mul_rn(mul_rn(sr, sv[j]), onepq);
+                    const T sgp = mul_rn(sr, yHv[j]);
+                    const T gsp = mul_rn(Hy, srj);
+                    H[j] = sub_rn(sub_rn(add_rn(H[j], sop), sgp), gsp);
+                }
+                slot_gather<T, NP>(g, bc_line, lane, gvv);
 #else
-            // Same update, H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the
-            // right (:263-303), using y^T H = (H y)^T: H stays symmetric to rounding under this update, so the
-            // two differ in the last bits only (the float64 gate still matches the reference's step counts
-            // on 100 % of problems).  Saves the reduce-scatter over rows and lets the products fuse.
-            T yv[NP], sv[NP];
-            slot_gather2<T, NP>(y, s, bc_line, xt_line, lane, yv, sv);
-            T Hy = T(0);                                     // (H y)_c, :293-295
+                // Same update, H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the
+                // right (:263-303), using y^T H = (H y)^T: H stays symmetric to rounding under this update, so
+                // the two differ in the last bits only (the float64 gate still matches the reference's step
+                // counts on 100 % of problems).  Saves the reduce-scatter over rows and lets the products fuse.
+                T yv[NP], sv[NP];
+                slot_gather2<T, NP>(y, s, bc_line, xt_line, lane, yv, sv);
+                T Hy = T(0);                                              // (H y)_c, :293-295
 #pragma unroll
-            for (int j = 0; j < NP; ++j) Hy = fma_t(H[j], yv[j], Hy);
-            const T q = mul_rn(slot_allreduce(mul_rn(y, Hy)), rho);  // y^T H y / (y^T s), :271-274
-            const T onepq = add_rn(T(1), q);
-            const T sr = mul_rn(s, rho);                     // :277
-            const T nHyrho = -mul_rn(Hy, rho);
-            T Hyv[NP], gvv[NP];
-            slot_gather2<T, NP>(Hy, g, bc_line, xt_line, lane, Hyv, gvv);
+                for (int j = 0; j < NP; ++j) Hy = fma_t(H[j], yv[j], Hy);
+                const T q = mul_rn(slot_allreduce(mul_rn(y, Hy)), rho);   // y^T H y / (y^T s), :271-274
+                const T onepq = add_rn(T(1), q);
+                const T sr = mul_rn(s, rho);                              // :277
+                const T nHyrho = -mul_rn(Hy, rho);
+                T Hyv[NP];
+                slot_gather2<T, NP>(Hy, g, bc_line, xt_line, lane, Hyv, gvv);
 #pragma unroll
-            for (int j = 0; j < NP; ++j) {
-                const T inner = fma_t(sv[j], onepq, -Hyv[j]);   // s_j (1+q) - (y^T H)_j
-                H[j] = fma_t(nHyrho, sv[j], fma_t(sr, inner, H[j]));
-            }
+                for (int j = 0; j < NP; ++j) {
+                    const T inner = fma_t(sv[j], onepq, -Hyv[j]);         // s_j (1+q) - (y^T H)_j
+                    H[j] = fma_t(nHyrho, sv[j], fma_t(sr, inner, H[j]));
+                }
 #endif
-            T Hg = T(0);
+                T Hg = T(0);
 #pragma unroll
-            for (int j = 0; j < NP; ++j) Hg = fma_t(H[j], gvv[j], Hg);
-            d = own ? mul_rn(T(-1), Hg) : T(0);              // :173-176
+                for (int j = 0; j < NP; ++j) Hg = fma_t(H[j], gvv[j], Hg);
+                d = own ? mul_rn(T(-1), Hg) : T(0);                       // :173-176
+            }
+            // ---- line-search set-up, wolfe_conditions.py:77-114 ----
+            f0 = f;
+            g0 = slot_allreduce(mul_rn(d, g));                            // :77
+            neg_c2_g0 = mul_rn(T(-1) * p.c2, g0);                         // -1.0 * curvature * base_gradient
+            widening = true; zooming = false;                             // :80-82
+            lo = T(0); hi = T(0); cand = T(1);                            // :97-108
+            lo_f = f0; hi_f = f0; cand_f = f0;                            // :109-111
+            ls_i = 0;
+            mode = kEvalProbe;
         }
-        const LineSearchResult<T> ls = line_search_warp(obj, p, x, d, f, g, xt_line, lane);  // :181-190
-        fevals += ls.probes;
-        ++iters;
-        s = mul_rn(ls.alpha, d);                             // :191
-        x = add_rn(x, s);                                    // :192
-        const T nrm = sqrt_rn(slot_allreduce(mul_rn(s, s))); // :203-205
-        gprev = g;
-        have_fg = same_bits(ls.alpha, ls.last_cand);
-        have_f = have_fg;
-        if (have_fg) {
-            f = ls.last_f;
-            g = ls.last_g;
-        }
-        if (!(nrm > p.min_step)) {                           // :203-207
-            reason = DAVO_REASON_STEP;
-            break;
-        }
-    }
-    if (!have_f) {  // cost at the returned parameters (networks/calibration_network.py:71)
-        T gtmp;
-        eval_at(obj, x, xt_line, lane, f, gtmp);
     }
     if (own && !(lane & 1)) p.x_out[(size_t)b * n + c] = x;
     if (lane == 0) {
