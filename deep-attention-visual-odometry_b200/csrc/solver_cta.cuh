@@ -116,11 +116,7 @@ struct JointCtaObjective {
             const T* pose = th + 10 + 6 * v;
             // sin/cos of this view's three Euler angles: lanes 0..2 compute, everyone receives
             T sn = T(0), cs = T(0);
-            if (lane < 3) {
-                const T ang = pose[lane];
-                sn = sin(ang);
-                cs = cos(ang);
-            }
+            if (lane < 3) sincos(pose[lane], &sn, &cs);  // one shared range reduction
             const T sx = shfl_idx(sn, 0), cx = shfl_idx(cs, 0), sy = shfl_idx(sn, 1), cy = shfl_idx(cs, 1),
                     sz = shfl_idx(sn, 2), cz = shfl_idx(cs, 2);
             const T t0 = pose[3], t1 = pose[4], t2 = pose[5];
@@ -215,6 +211,29 @@ __device__ __forceinline__ void cta_matvec(const T* H, int ld, const T* v, T* ou
     }
 }
 
+// Two products in one pass over H: out_a = H a, out_b = H b.
+template <typename T, int W>
+__device__ __forceinline__ void cta_matvec2(const T* H, int ld, const T* a, const T* b, T* out_a, T* out_b, int n) {
+    const int tid = threadIdx.x, q = tid & 3;
+    constexpr int kRowsPerPass = 32 * W / 4;
+    for (int c0 = 0; c0 < n; c0 += kRowsPerPass) {
+        const int c = c0 + (tid >> 2);
+        T sa = T(0), sb = T(0);
+        if (c < n)
+            for (int j = q; j < n; j += 4) {
+                const T h = H[c * ld + j];
+                sa = fma_t(h, a[j], sa);
+                sb = fma_t(h, b[j], sb);
+            }
+        sa += shfl_xor(sa, 1); sb += shfl_xor(sb, 1);
+        sa += shfl_xor(sa, 2); sb += shfl_xor(sb, 2);
+        if (c < n && q == 0) {
+            out_a[c] = sa;
+            out_b[c] = sb;
+        }
+    }
+}
+
 template <typename T, int W, typename Obj>
 __device__ __forceinline__ LineSearchResult<T> line_search_cta(Obj& obj, const SolveParams<T>& p, const T* x,
                                                                const T* d, T f0, const T* g, T* xt, T* gt) {
@@ -301,26 +320,42 @@ __device__ __forceinline__ void solve_one_cta(Obj& obj, const SolveParams<T>& p,
             }
             T rho = div_rn(T(1), sy);                          // func_inverse_curvature.py:8-11
             if (sy <= T(0)) rho = T(0);
-            // H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the right (:263-303),
-            // using y^T H = (H y)^T (H stays symmetric to rounding under this update; see solver_warp.cuh).
-            cta_matvec<T, W>(H, ld, y, Hy, n, T(1));           // (H y)_c, :293-295: one warp per row
+            // H' = H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the right
+            // (:263-303), using y^T H = (H y)^T (H stays symmetric to rounding; see solver_warp.cuh).
+            // One pass over H forms H y AND H g; the new direction -H' g (:173-176) then follows from
+            //   H' g = H g + (s rho) [ (1+q) s.g - (H y).g ] - (H y) rho s.g
+            // without waiting for H' to be written, so the update of H and of d share one barrier.
+            cta_matvec2<T, W>(H, ld, y, g, Hy, yH /* scratch: H g */, n);
             __syncthreads();
-            const T q = mul_rn(wide_dot(y, Hy, n, lane), rho); // y^T H y / (y^T s), :271-274
+            const T* Hg = yH;
+            T a0 = T(0), a1 = T(0), a2 = T(0);
+            for (int c = lane; c < n; c += 32) {
+                a0 = fma_t(y[c], Hy[c], a0);
+                a1 = fma_t(s[c], g[c], a1);
+                a2 = fma_t(Hy[c], g[c], a2);
+            }
+            const T q = mul_rn(warp_allreduce(a0), rho);       // y^T H y / (y^T s), :271-274
+            const T sg = warp_allreduce(a1), hyg = warp_allreduce(a2);
             const T onepq = add_rn(T(1), q);
-            {   // all W*32 threads walk the n x n elements; (i, j) advance without a division
-                const int step_i = kThreads / n, step_j = kThreads % n;
-                int i = tid / n, j = tid % n;
-                for (int e = tid; e < n * n; e += kThreads) {
-                    const T sri = mul_rn(s[i], rho);
-                    const T inner = fma_t(s[j], onepq, -Hy[j]);            // s_j (1+q) - (y^T H)_j
-                    H[i * ld + j] = fma_t(-mul_rn(Hy[i], rho), s[j], fma_t(sri, inner, H[i * ld + j]));
-                    i += step_i;
-                    j += step_j;
-                    if (j >= n) { j -= n; ++i; }
+            if (tid < n) {
+                const T sr = mul_rn(s[tid], rho);
+                const T hpg = fma_t(-Hy[tid] * rho, sg, fma_t(sr, fma_t(onepq, sg, -hyg), Hg[tid]));
+                d[tid] = mul_rn(T(-1), hpg);
+            }
+            {   // four threads share a row (as in cta_matvec2): the row's constants are loaded once
+                const int qd = tid & 3;
+                constexpr int kRowsPerPass = kThreads / 4;
+                for (int i0 = 0; i0 < n; i0 += kRowsPerPass) {
+                    const int i = i0 + (tid >> 2);
+                    if (i < n) {
+                        const T sri = mul_rn(s[i], rho), nHyrho = -mul_rn(Hy[i], rho);
+                        for (int j = qd; j < n; j += 4) {
+                            const T inner = fma_t(s[j], onepq, -Hy[j]);   // s_j (1+q) - (y^T H)_j
+                            H[i * ld + j] = fma_t(nHyrho, s[j], fma_t(sri, inner, H[i * ld + j]));
+                        }
+                    }
                 }
             }
-            __syncthreads();
-            cta_matvec<T, W>(H, ld, g, d, n, T(-1));           // d = -H g, :173-176
         }
         __syncthreads();
         const LineSearchResult<T> ls = line_search_cta<T, W>(obj, p, x, d, f, g, ws.xt, gt);  // :181-190
