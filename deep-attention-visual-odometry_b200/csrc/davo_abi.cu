@@ -10,6 +10,11 @@ namespace davo {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+#if DAVO_TRACE
+static void* g_trace = nullptr;
+static int g_trace_problem = -1, g_trace_capacity = 0;
+#endif
+
 static bool is_analytic(int model) { return model >= DAVO_MODEL_SPHERE && model <= DAVO_MODEL_DISTANCE; }
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -59,6 +64,9 @@ static SolveParams<T> make_params(const davo_problem_desc* d, const void* data0,
     p.data0 = static_cast<const T*>(data0);
     p.data1 = static_cast<const T*>(data1);
     p.w = d->has_weights ? static_cast<const T*>(w) : nullptr;
+#if DAVO_TRACE
+    p.trace = static_cast<T*>(g_trace); p.trace_problem = g_trace_problem; p.trace_capacity = g_trace_capacity;
+#endif
     return p;
 }
 }  // namespace davo
@@ -66,6 +74,13 @@ static SolveParams<T> make_params(const davo_problem_desc* d, const void* data0,
 using namespace davo;
 
 extern "C" {
+
+#if DAVO_TRACE
+// debug builds only (not part of the ABI): record 8 values per accepted step of one problem
+void davo_debug_trace(void* buffer, int problem, int capacity) {
+    g_trace = buffer; g_trace_problem = problem; g_trace_capacity = capacity;
+}
+#endif
 
 int davo_abi_version(void) { return DAVO_ABI_VERSION; }
 

@@ -9,6 +9,10 @@
 
 #include "../../include/davo_b200.h"
 
+#ifndef DAVO_TRACE
+#define DAVO_TRACE 0
+#endif
+
 namespace davo {
 
 constexpr int kSlots = 16;  // distributed-vector width of the warp-per-problem solver (n <= 16)
@@ -162,6 +166,11 @@ struct SolveParams {
     const T* base_cost;
     const T* base_grad;
     T* alpha_out;
+#if DAVO_TRACE
+    T* trace;           // debug builds only: 8 values per accepted step of problem `trace_problem`
+    int trace_problem;
+    int trace_capacity;
+#endif
 };
 
 }  // namespace davo

@@ -14,6 +14,10 @@
 #pragma once
 #include "davo_common.cuh"
 
+#ifndef DAVO_ORACLE_ARITH
+#define DAVO_ORACLE_ARITH 0
+#endif
+
 namespace davo {
 
 // Per-evaluation constants derived from the 10 intrinsics, hoisted out of the match loop.
@@ -41,6 +45,44 @@ struct Intrinsics {
 template <typename T, bool kWeighted>
 __device__ __forceinline__ void match_cost_grad(const Intrinsics<T>& I, T a, T b, T us, T vs, T w,
                                                 T (&acc)[kSlots], T& gu, T& gv) {
+#if DAVO_ORACLE_ARITH
+    // Debug variant: the oracle's expressions, operation by operation, without FMA (oracle/calib_oracle_impl.h
+    // match_intrinsics).  Used to separate effects of the evaluator's rounding from effects of the solver.
+    const T u = add_rn(mul_rn(I.fx, a), mul_rn(I.s, b));
+    const T v = mul_rn(I.fy, b);
+    const T r2 = add_rn(mul_rn(u, u), mul_rn(v, v));
+    const T uv = mul_rn(u, v);
+    const T rad = add_rn(add_rn(add_rn(T(1), mul_rn(I.k1, r2)), mul_rn(mul_rn(I.k2, r2), r2)),
+                         mul_rn(mul_rn(mul_rn(I.k3, r2), r2), r2));
+    const T A = add_rn(r2, mul_rn(mul_rn(T(2), u), u)), Bv = add_rn(r2, mul_rn(mul_rn(T(2), v), v));
+    const T up = add_rn(add_rn(add_rn(mul_rn(u, rad), mul_rn(mul_rn(T(2), I.p1), uv)), mul_rn(I.p2, A)), I.cx);
+    const T vp = add_rn(add_rn(add_rn(mul_rn(v, rad), mul_rn(mul_rn(T(2), I.p2), uv)), mul_rn(I.p1, Bv)), I.cy);
+    T ru = sub_rn(up, us), rv = sub_rn(vp, vs);
+    T cost = add_rn(mul_rn(ru, ru), mul_rn(rv, rv));
+    if (kWeighted) { cost = mul_rn(w, cost); ru = mul_rn(w, ru); rv = mul_rn(w, rv); }
+    acc[10] = add_rn(acc[10], cost);
+    const T r4 = mul_rn(r2, r2), r6 = mul_rn(r4, r2);
+    const T radp = add_rn(add_rn(I.k1, mul_rn(mul_rn(T(2), I.k2), r2)), mul_rn(mul_rn(T(3), I.k3), r4));
+    const T uv2 = mul_rn(T(2), uv);
+    const T Duu = add_rn(add_rn(add_rn(rad, mul_rn(mul_rn(mul_rn(T(2), u), u), radp)), mul_rn(mul_rn(T(2), I.p1), v)),
+                         mul_rn(mul_rn(T(6), I.p2), u));
+    const T Dvv = add_rn(add_rn(add_rn(rad, mul_rn(mul_rn(mul_rn(T(2), v), v), radp)), mul_rn(mul_rn(T(6), I.p1), v)),
+                         mul_rn(mul_rn(T(2), I.p2), u));
+    const T Duv = add_rn(add_rn(mul_rn(uv2, radp), mul_rn(mul_rn(T(2), I.p1), u)), mul_rn(mul_rn(T(2), I.p2), v));
+    gu = add_rn(mul_rn(ru, Duu), mul_rn(rv, Duv));
+    gv = add_rn(mul_rn(ru, Duv), mul_rn(rv, Dvv));
+    const T t = add_rn(mul_rn(ru, u), mul_rn(rv, v));
+    acc[0] = add_rn(acc[0], ru);
+    acc[1] = add_rn(acc[1], rv);
+    acc[2] = add_rn(acc[2], mul_rn(t, r2));
+    acc[3] = add_rn(acc[3], mul_rn(t, r4));
+    acc[4] = add_rn(acc[4], mul_rn(t, r6));
+    acc[5] = add_rn(acc[5], add_rn(mul_rn(ru, uv2), mul_rn(rv, Bv)));
+    acc[6] = add_rn(acc[6], add_rn(mul_rn(ru, A), mul_rn(rv, uv2)));
+    acc[7] = add_rn(acc[7], mul_rn(gu, a));
+    acc[8] = add_rn(acc[8], mul_rn(gu, b));
+    acc[9] = add_rn(acc[9], mul_rn(gv, b));
+#else
     const T u = fma_t(I.fx, a, I.s * b);            // distorted_camera_model.py:59-61
     const T v = I.fy * b;                           // :62
     const T uu = u * u, vv = v * v, uv = u * v;     // :65
@@ -88,6 +130,90 @@ __device__ __forceinline__ void match_cost_grad(const Intrinsics<T>& I, T a, T b
     acc[7] = fma_t(gu, a, acc[7]);
     acc[8] = fma_t(gu, b, acc[8]);
     acc[9] = fma_t(gv, b, acc[9]);
+#endif
+}
+
+// ---- packed pairs: two matches per instruction ---------------------------------------------------------
+// sm_100 has fma/mul/add.rn.f32x2 (SASS FFMA2 / FMUL2 / FADD2): both components are rounded exactly like the
+// scalar instruction, the FMA pipe spends the same cycles as for two scalar instructions, but the pair takes ONE
+// issue slot, and a per-evaluation constant can be read as a broadcast 32-bit operand (no duplicated registers).
+// The solve kernel is issue bound (tools/ffma2_probe.cu: 16 FFMA + 12 integer instructions per round run 1.39x
+// faster with the FFMAs paired), so the match loop works on PAIRS of matches.  The float64 instantiation uses the
+// same code with component-wise arithmetic.
+__device__ __forceinline__ float2 pk(float s) { return make_float2(s, s); }
+__device__ __forceinline__ double2 pk(double s) { return make_double2(s, s); }
+__device__ __forceinline__ float2 pfma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 pmul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ double2 pfma(double2 a, double2 b, double2 c) {
+    return make_double2(fma(a.x, b.x, c.x), fma(a.y, b.y, c.y));
+}
+__device__ __forceinline__ double2 pmul(double2 a, double2 b) { return make_double2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ double2 padd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+
+constexpr int kPairAcc = 13;  // acc[0..9] gradient sums, acc[10] cost, acc[11], acc[12] the uv terms of p1, p2
+
+// match_cost_grad for two matches at once.  nus, nvs are the NEGATED observations (negated once, when the problem
+// is staged into shared memory), second_valid = false zeroes the residuals of the pair's second match (ragged N):
+// every accumulated quantity is linear in (ru, rv), so that removes it from all sums.
+template <typename T, bool kWeighted>
+__device__ __forceinline__ void match_pair_cost_grad(const Intrinsics<T>& I, typename Vec2<T>::type a,
+                                                     typename Vec2<T>::type b, typename Vec2<T>::type nus,
+                                                     typename Vec2<T>::type nvs, typename Vec2<T>::type w,
+                                                     bool second_valid, typename Vec2<T>::type (&acc)[kPairAcc],
+                                                     typename Vec2<T>::type& gu, typename Vec2<T>::type& gv) {
+    using P = typename Vec2<T>::type;
+    const P u = pfma(pk(I.fx), a, pmul(pk(I.s), b));                // distorted_camera_model.py:59-61
+    const P v = pmul(pk(I.fy), b);                                  // :62
+    const P uu = pmul(u, u), vv = pmul(v, v), uv = pmul(u, v);      // :65
+    const P r2 = padd(uu, vv);                                      // :64
+    const P rad = pfma(r2, pfma(r2, pfma(r2, pk(I.k3), pk(I.k2)), pk(I.k1)), pk(T(1)));  // :66-74 (Horner)
+    const P A = pfma(pk(T(2)), uu, r2);                             // r2 + 2u^2
+    const P Bv = pfma(pk(T(2)), vv, r2);                            // r2 + 2v^2
+    P ru = pfma(u, rad, padd(pk(I.cx), nus));                       // :75-80 minus the observation
+    ru = pfma(pk(I.p1x2), uv, ru);
+    ru = pfma(pk(I.p2), A, ru);
+    P rv = pfma(v, rad, padd(pk(I.cy), nvs));                       // :81-86
+    rv = pfma(pk(I.p2x2), uv, rv);
+    rv = pfma(pk(I.p1), Bv, rv);
+    if (!second_valid) {
+        ru.y = T(0);
+        rv.y = T(0);
+    }
+    if (kWeighted) {
+        acc[10] = pfma(w, pfma(ru, ru, pmul(rv, rv)), acc[10]);     // least_squares_utils.py:24-28
+        ru = pmul(ru, w);                                           // :43-45
+        rv = pmul(rv, w);
+    } else {
+        acc[10] = pfma(ru, ru, acc[10]);
+        acc[10] = pfma(rv, rv, acc[10]);
+    }
+    const P radp2 = pfma(r2, pfma(r2, pk(I.k3x6), pk(I.k2x4)), pk(I.k1x2));  // 2 d rad / d r2
+    P Duu = pfma(uu, radp2, rad);                   // d u'/d u = rad + 2u^2 rad' + 2 p1 v + 6 p2 u
+    Duu = pfma(pk(I.p1x2), v, Duu);
+    Duu = pfma(pk(I.p2x6), u, Duu);
+    P Dvv = pfma(vv, radp2, rad);                   // d v'/d v = rad + 2v^2 rad' + 6 p1 v + 2 p2 u
+    Dvv = pfma(pk(I.p1x6), v, Dvv);
+    Dvv = pfma(pk(I.p2x2), u, Dvv);
+    P Duv = pmul(uv, radp2);                        // d u'/d v = d v'/d u = 2uv rad' + 2 p1 u + 2 p2 v
+    Duv = pfma(pk(I.p1x2), u, Duv);
+    Duv = pfma(pk(I.p2x2), v, Duv);
+    gu = pfma(ru, Duu, pmul(rv, Duv));
+    gv = pfma(ru, Duv, pmul(rv, Dvv));
+    const P t = pfma(ru, u, pmul(rv, v));
+    const P r4 = pmul(r2, r2), r6 = pmul(r4, r2);
+    acc[0] = padd(acc[0], ru);
+    acc[1] = padd(acc[1], rv);
+    acc[2] = pfma(t, r2, acc[2]);
+    acc[3] = pfma(t, r4, acc[3]);
+    acc[4] = pfma(t, r6, acc[4]);
+    acc[5] = pfma(rv, Bv, acc[5]);
+    acc[6] = pfma(ru, A, acc[6]);
+    acc[11] = pfma(ru, uv, acc[11]);
+    acc[12] = pfma(rv, uv, acc[12]);
+    acc[7] = pfma(gu, a, acc[7]);
+    acc[8] = pfma(gu, b, acc[8]);
+    acc[9] = pfma(gv, b, acc[9]);
 }
 
 // d/dp1 = sum (2uv ru + Bv rv), d/dp2 = sum (A ru + 2uv rv): add the 2uv parts once per evaluation.
@@ -107,8 +233,9 @@ struct Distort10Objective {
     using V4 = typename Vec4<T>::type;
     static constexpr bool kUsesSmemMatches = true;
 
+    using P = typename Vec2<T>::type;
     const SolveParams<T>& p;
-    V4* matches;      // this warp's shared-memory slab, N entries
+    V4* matches;      // this warp's shared-memory slab, N + 32 entries (pair layout, see bind)
     T* weights;       // N entries (only if p.has_w)
     uint64_t* bar;    // this warp's mbarrier
     unsigned parity;
@@ -116,11 +243,11 @@ struct Distort10Objective {
 
     __device__ Distort10Objective(const SolveParams<T>& p_, unsigned char* slab, uint64_t* bar_, int lane_)
         : p(p_), matches(reinterpret_cast<V4*>(slab)),
-          weights(reinterpret_cast<T*>(slab + sizeof(V4) * (size_t)p_.N)), bar(bar_), parity(0), lane(lane_) {}
+          weights(reinterpret_cast<T*>(slab + sizeof(V4) * (size_t)(p_.N + 32))), bar(bar_), parity(0), lane(lane_) {}
 
     // bytes of shared memory one warp needs for its slab
     __host__ __device__ static size_t slab_bytes(int N, bool has_w) {
-        size_t b = sizeof(V4) * (size_t)N + (has_w ? sizeof(T) * (size_t)N : 0);
+        size_t b = sizeof(V4) * (size_t)(N + 32) + (has_w ? sizeof(T) * (size_t)N : 0);
         return (b + 127) & ~size_t(127);
     }
 
@@ -128,7 +255,7 @@ struct Distort10Objective {
         // All lanes have finished reading the previous problem's slab (callers sync the warp).
         __syncwarp();
         if (lane == 0) {
-            fence_proxy_async();  // order our earlier generic-proxy reads before the async-proxy write
+            fence_proxy_async();  // order our earlier generic-proxy accesses before the async-proxy write
             const unsigned bytes_m = (unsigned)(sizeof(V4) * (size_t)p.N);
             mbar_expect_tx(bar, bytes_m);
             tma_load_1d(matches, p.data0 + (size_t)b * p.N * 4, bytes_m, bar);
@@ -138,24 +265,53 @@ struct Distort10Objective {
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
+        // Pair layout, once per problem (the slab is then read by every evaluation): this lane's matches i and
+        // i + 32 become entry i = {a_i, a_i+32, b_i, b_i+32} and entry i + 32 = -{u*_i, u*_i+32, v*_i, v*_i+32},
+        // so one LDS.128 yields two aligned register pairs for the packed arithmetic.  A lane only rewrites its
+        // own two entries; a missing second match (ragged N) is zero-filled and masked in eval.
+        for (int i = lane; i < p.N; i += 64) {
+            const V4 m0 = matches[i];
+            V4 m1;
+            m1.x = m1.y = m1.z = m1.w = T(0);
+            if (i + 32 < p.N) m1 = matches[i + 32];
+            V4 ab, ob;
+            ab.x = m0.x; ab.y = m1.x; ab.z = m0.y; ab.w = m1.y;
+            ob.x = -m0.z; ob.y = -m1.z; ob.z = -m0.w; ob.w = -m1.w;
+            matches[i] = ab;
+            matches[i + 32] = ob;
+        }
         __syncwarp();
     }
 
-    // One evaluation.  Inlined at its three call sites (outer iteration, line-search probe, final cost): a
-    // __noinline__ version shrank the kernel from 57 KB to 27 KB of SASS but ran 12 % slower (call + stack).
+    // One evaluation.  Inlined at its call site (solve_one_warp has a single one): a __noinline__ version ran
+    // 12 % slower (call + stack).
     __device__ __forceinline__ void eval(const T* th, T& f, T& g_own) {
         Intrinsics<T> I;
         I.load(th);
+        P acc2[kPairAcc];
+#pragma unroll
+        for (int k = 0; k < kPairAcc; ++k) acc2[k] = pk(T(0));
+        P gu, gv;
+        const int N = p.N;
+#pragma unroll 2
+        for (int i = lane; i < N; i += 64) {
+            const V4 ab = matches[i];
+            const V4 ob = matches[i + 32];
+            P a, b, nus, nvs, w = pk(T(1));
+            a.x = ab.x; a.y = ab.y; b.x = ab.z; b.y = ab.w;
+            nus.x = ob.x; nus.y = ob.y; nvs.x = ob.z; nvs.y = ob.w;
+            const bool second_valid = i + 32 < N;
+            if (kWeighted) {
+                w.x = weights[i];
+                w.y = second_valid ? weights[i + 32] : T(0);
+            }
+            match_pair_cost_grad<T, kWeighted>(I, a, b, nus, nvs, w, second_valid, acc2, gu, gv);
+        }
         T acc[kSlots];
 #pragma unroll
-        for (int k = 0; k < kSlots; ++k) acc[k] = T(0);
-        T gu, gv;
-        const int N = p.N;
-#pragma unroll 4
-        for (int i = lane; i < N; i += 32) {
-            const V4 m = matches[i];
-            match_cost_grad<T, kWeighted>(I, m.x, m.y, m.z, m.w, kWeighted ? weights[i] : T(1), acc, gu, gv);
-        }
+        for (int k = 0; k < kPairAcc; ++k) acc[k] = acc2[k].x + acc2[k].y;
+#pragma unroll
+        for (int k = kPairAcc; k < kSlots; ++k) acc[k] = T(0);
         fold_uv_terms(acc);
         const T mine = reduce_scatter16<true>(acc, lane);  // slot c total in lanes 2c, 2c+1
         f = shfl_idx(mine, 20);                            // slot 10 = cost

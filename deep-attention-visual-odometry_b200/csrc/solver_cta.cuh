@@ -211,25 +211,30 @@ __device__ __forceinline__ void cta_matvec(const T* H, int ld, const T* v, T* ou
     }
 }
 
-// Two products in one pass over H: out_a = H a, out_b = H b.
+// One sweep over H: out_a = H a, out_b = H b (four threads share a ROW) and out_t = a^T H (the same four
+// threads share the COLUMN with the row's index; H rows are padded to n+1 words, so both walks are at most
+// 2-way bank conflicted).
 template <typename T, int W>
-__device__ __forceinline__ void cta_matvec2(const T* H, int ld, const T* a, const T* b, T* out_a, T* out_b, int n) {
+__device__ __forceinline__ void cta_matvec3(const T* H, int ld, const T* a, const T* b, T* out_a, T* out_b,
+                                            T* out_t, int n) {
     const int tid = threadIdx.x, q = tid & 3;
     constexpr int kRowsPerPass = 32 * W / 4;
-    for (int c0 = 0; c0 < n; c0 += kRowsPerPass) {
+    for (int c0 = 0; c0 < n; c0 += kRowsPerPass) {   // CTA-uniform trip count: the shuffles below are safe
         const int c = c0 + (tid >> 2);
-        T sa = T(0), sb = T(0);
+        T sa = T(0), sb = T(0), st = T(0);
         if (c < n)
             for (int j = q; j < n; j += 4) {
                 const T h = H[c * ld + j];
                 sa = fma_t(h, a[j], sa);
                 sb = fma_t(h, b[j], sb);
+                st = fma_t(a[j], H[j * ld + c], st);
             }
-        sa += shfl_xor(sa, 1); sb += shfl_xor(sb, 1);
-        sa += shfl_xor(sa, 2); sb += shfl_xor(sb, 2);
+        sa += shfl_xor(sa, 1); sb += shfl_xor(sb, 1); st += shfl_xor(st, 1);
+        sa += shfl_xor(sa, 2); sb += shfl_xor(sb, 2); st += shfl_xor(st, 2);
         if (c < n && q == 0) {
             out_a[c] = sa;
             out_b[c] = sb;
+            out_t[c] = st;
         }
     }
 }
@@ -321,25 +326,27 @@ __device__ __forceinline__ void solve_one_cta(Obj& obj, const SolveParams<T>& p,
             T rho = div_rn(T(1), sy);                          // func_inverse_curvature.py:8-11
             if (sy <= T(0)) rho = T(0);
             // H' = H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the right
-            // (:263-303), using y^T H = (H y)^T (H stays symmetric to rounding; see solver_warp.cuh).
-            // One pass over H forms H y AND H g; the new direction -H' g (:173-176) then follows from
-            //   H' g = H g + (s rho) [ (1+q) s.g - (H y).g ] - (H y) rho s.g
+            // (:263-303).  y^T H is formed from the COLUMNS of H — never replaced by (H y)^T: H is symmetric
+            // only up to rounding and that shortcut makes the asymmetry grow in float32 (see solver_warp.cuh).
+            // One sweep over H forms H y, H g (rows) and y^T H (columns); the new direction -H' g (:173-176)
+            // then follows from
+            //   H' g = H g + (s rho) [ (1+q) s.g - (y^T H).g ] - (H y) rho s.g
             // without waiting for H' to be written, so the update of H and of d share one barrier.
-            cta_matvec2<T, W>(H, ld, y, g, Hy, yH /* scratch: H g */, n);
+            cta_matvec3<T, W>(H, ld, y, g, Hy, ws.xt /* scratch: H g */, yH, n);
             __syncthreads();
-            const T* Hg = yH;
+            const T* Hg = ws.xt;
             T a0 = T(0), a1 = T(0), a2 = T(0);
             for (int c = lane; c < n; c += 32) {
-                a0 = fma_t(y[c], Hy[c], a0);
+                a0 = fma_t(yH[c], y[c], a0);
                 a1 = fma_t(s[c], g[c], a1);
-                a2 = fma_t(Hy[c], g[c], a2);
+                a2 = fma_t(yH[c], g[c], a2);
             }
             const T q = mul_rn(warp_allreduce(a0), rho);       // y^T H y / (y^T s), :271-274
-            const T sg = warp_allreduce(a1), hyg = warp_allreduce(a2);
+            const T sg = warp_allreduce(a1), yhg = warp_allreduce(a2);
             const T onepq = add_rn(T(1), q);
             if (tid < n) {
                 const T sr = mul_rn(s[tid], rho);
-                const T hpg = fma_t(-Hy[tid] * rho, sg, fma_t(sr, fma_t(onepq, sg, -hyg), Hg[tid]));
+                const T hpg = fma_t(-Hy[tid] * rho, sg, fma_t(sr, fma_t(onepq, sg, -yhg), Hg[tid]));
                 d[tid] = mul_rn(T(-1), hpg);
             }
             {   // four threads share a row (as in cta_matvec2): the row's constants are loaded once
@@ -350,7 +357,7 @@ __device__ __forceinline__ void solve_one_cta(Obj& obj, const SolveParams<T>& p,
                     if (i < n) {
                         const T sri = mul_rn(s[i], rho), nHyrho = -mul_rn(Hy[i], rho);
                         for (int j = qd; j < n; j += 4) {
-                            const T inner = fma_t(s[j], onepq, -Hy[j]);   // s_j (1+q) - (y^T H)_j
+                            const T inner = fma_t(s[j], onepq, -yH[j]);   // s_j (1+q) - (y^T H)_j
                             H[i * ld + j] = fma_t(nHyrho, s[j], fma_t(sri, inner, H[i * ld + j]));
                         }
                     }

@@ -244,6 +244,13 @@ __device__ __forceinline__ void solve_one_warp(Obj& obj, const SolveParams<T>& p
             // The accepted point is bitwise x + alpha d: when the search returns the probe it has just made,
             // that probe's (f, grad) ARE the next outer iteration's evaluation.
             const bool reuse = same_bits(hi, cand);
+#if DAVO_TRACE
+            if (b == p.trace_problem && lane == 0 && k < p.trace_capacity) {
+                T* rec = p.trace + 8 * (size_t)k;
+                rec[0] = T(k); rec[1] = f0; rec[2] = g0; rec[3] = hi; rec[4] = T(ls_i); rec[5] = nrm; rec[6] = cand_f;
+                rec[7] = reuse ? T(1) : T(0);
+            }
+#endif
             ++k;
             const bool stop_step = !(nrm > p.min_step);                   // :203-207 (strict >)
             if (stop_step || k >= p.max_iters) {                          // :118
@@ -319,23 +326,33 @@ __device__ __forceinline__ void solve_one_warp(Obj& obj, const SolveParams<T>& p
                 slot_gather<T, NP>(g, bc_line, lane, gvv);
 #else
                 // Same update, H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the
-                // right (:263-303), using y^T H = (H y)^T: H stays symmetric to rounding under this update, so
-                // the two differ in the last bits only (the float64 gate still matches the reference's step
-                // counts on 100 % of problems).  Saves the reduce-scatter over rows and lets the products fuse.
+                // right (:263-303), same operands, but the products are allowed to fuse into FMAs.
+                // NOTE: y^T H must be formed from the COLUMNS of H.  Replacing it by (H y)^T ("H is symmetric")
+                // is wrong in float32: H is symmetric only up to rounding, the true update maps the
+                // antisymmetric part A to V^T A V (bounded) while the shortcut adds rho s y^T (H^T - H), which
+                // grows on ill-conditioned problems until the directions are useless (config 4: problems that
+                // converge in ~250 iterations ran into the 1000-iteration cap with ~39 probes per search).
                 T yv[NP], sv[NP];
                 slot_gather2<T, NP>(y, s, bc_line, xt_line, lane, yv, sv);
                 T Hy = T(0);                                              // (H y)_c, :293-295
+                T part[kSlots];
 #pragma unroll
-                for (int j = 0; j < NP; ++j) Hy = fma_t(H[j], yv[j], Hy);
-                const T q = mul_rn(slot_allreduce(mul_rn(y, Hy)), rho);   // y^T H y / (y^T s), :271-274
+                for (int j = 0; j < kSlots; ++j) part[j] = T(0);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    Hy = fma_t(H[j], yv[j], Hy);
+                    part[j] = y * H[j];                                   // y_c H[c][j]
+                }
+                const T yH = reduce_scatter16<false>(part, lane);         // (y^T H)_c, :268-270
+                const T q = mul_rn(slot_allreduce(yH * y), rho);          // y^T H y / (y^T s), :271-274
                 const T onepq = add_rn(T(1), q);
                 const T sr = mul_rn(s, rho);                              // :277
                 const T nHyrho = -mul_rn(Hy, rho);
-                T Hyv[NP];
-                slot_gather2<T, NP>(Hy, g, bc_line, xt_line, lane, Hyv, gvv);
+                T yHv[NP];
+                slot_gather2<T, NP>(yH, g, bc_line, xt_line, lane, yHv, gvv);
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
-                    const T inner = fma_t(sv[j], onepq, -Hyv[j]);         // s_j (1+q) - (y^T H)_j
+                    const T inner = fma_t(sv[j], onepq, -yHv[j]);         // s_j (1+q) - (y^T H)_j
                     H[j] = fma_t(nHyrho, sv[j], fma_t(sr, inner, H[j]));
                 }
 #endif

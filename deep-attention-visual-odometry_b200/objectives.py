@@ -135,6 +135,25 @@ class DistortionObjective(CalibrationObjective):
     def is_staged(self) -> bool:
         return self._data0 is not None
 
+    def upload_rows(self, lo: int, hi: int, d_pts: torch.Tensor, d_obs: torch.Tensor, d_pose, weights_out=None) -> None:
+        """Host -> device copy of the raw inputs of problems [lo, hi) into rows lo:hi of preallocated device
+        buffers, on the current stream (the streamed solve runs this on its copy stream)."""
+        pts, obs, pose, w = self._raw
+        d_pts[lo:hi].copy_(pts[lo:hi], non_blocking=True)
+        d_obs[lo:hi].copy_(obs[lo:hi], non_blocking=True)
+        if pose is not None:
+            d_pose[lo:hi].copy_(pose[lo:hi], non_blocking=True)
+        if w is not None and weights_out is not None:
+            weights_out[lo:hi].copy_(w[lo:hi], non_blocking=True)
+
+    def stage_device_rows(self, lo: int, hi: int, d_pts, d_obs, d_pose, staged: torch.Tensor) -> None:
+        """davo_stage_matches on device-resident rows lo:hi, writing staged[lo:hi]; current stream."""
+        desc = self.desc(B=hi - lo)
+        st = _lib.lib().davo_stage_matches(ctypes.byref(desc), _lib.ptr(d_pts[lo:hi]), _lib.ptr(d_obs[lo:hi]),
+                                           _lib.ptr(None if d_pose is None else d_pose[lo:hi]),
+                                           _lib.ptr(staged[lo:hi]), _lib.stream_ptr())
+        _lib.check(st, "davo_stage_matches")
+
     def stage_rows(self, lo: int, hi: int, staged: torch.Tensor, weights_out=None) -> None:
         """Copy problems [lo, hi) to the device (if they are on the host) and run davo_stage_matches on them,
         writing staged[lo:hi].  Stream ordered on the current stream; no host synchronisation."""

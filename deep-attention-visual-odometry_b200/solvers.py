@@ -50,12 +50,12 @@ class SolveBuffers(NamedTuple):
 _STREAMS: dict = {}
 
 
-def _compute_streams(device):
-    """Two side streams per device, created once: the caching allocator keeps one memory pool per stream, so
-    fresh streams on every call would turn every chunk buffer into a cudaMalloc."""
+def _side_streams(device):
+    """One copy stream and two compute streams per device, created once (stream creation is not free and the
+    caching allocator tracks cross-stream use per stream)."""
     key = (device.type, device.index)
     if key not in _STREAMS:
-        _STREAMS[key] = [torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)]
+        _STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(3)]
     return _STREAMS[key]
 
 
@@ -130,35 +130,54 @@ class BFGSSolver(Module):
     #: problems per chunk of the streamed (host-input) path; each chunk is one H2D copy + stage + solve
     stream_chunk = 8192
 
-    def _solve_streamed(self, x0_host: torch.Tensor, obj, error_threshold, iterations, out) -> "SolveBuffers":
-        """Host inputs -> device results with the copies hidden behind compute.
+    @staticmethod
+    def _chunk_spans(B: int, chunk: int):
+        """[lo, hi) spans of `chunk` problems; the last chunk is cut into 1/2, 1/4, 1/4 so that the compute
+        left over once the final copy has landed (the only part the copies cannot hide) is short."""
+        spans = [(lo, min(lo + chunk, B)) for lo in range(0, B, chunk)]
+        if len(spans) > 1 and spans[-1][1] - spans[-1][0] >= 1024:
+            lo, hi = spans.pop()
+            size = hi - lo
+            a, b = lo + size // 2, lo + size // 2 + size // 4
+            spans += [(lo, a), (a, b), (b, hi)]
+        return spans
 
-        The batch is cut into chunks of `stream_chunk` problems.  A copy stream moves chunk k+1's points,
-        observations and start parameters host -> device while chunk k is staged (davo_stage_matches) and
-        solved (davo_solve_calibration) on a compute stream; chunks alternate between two compute streams so
-        that the next chunk's persistent grid fills the SMs as the previous chunk's tail drains.  The staged
-        matches stay resident in `obj` afterwards.  Nothing here synchronises the host."""
+    def _solve_streamed(self, x0_host: torch.Tensor, obj, error_threshold, iterations, out) -> "SolveBuffers":
+        """Host inputs -> device results with the compute hidden behind the copies.
+
+        The batch is cut into chunks of `stream_chunk` problems.  ONE copy stream moves every chunk's points,
+        observations and start parameters host -> device back to back, so the copy engine never waits for
+        compute (at 64K x 256 the 338 MB of raw inputs take longer over PCIe than the solve takes on the SMs);
+        an event per chunk releases its staging (davo_stage_matches) and solve (davo_solve_calibration) on
+        one of two compute streams, alternating so that the next chunk's persistent grid fills the SMs as the
+        previous chunk's tail drains.  The staged matches stay resident in `obj` afterwards.  Nothing here
+        synchronises the host."""
         device = obj.device
-        B, n = obj.B, obj.n
+        B, n, N = obj.B, obj.n, obj.N
         with torch.cuda.device(device):
             buf = out if out is not None else SolveBuffers.allocate(B, n, obj.dtype, device)
-            staged = torch.empty(B, obj.N, 4, dtype=obj.dtype, device=device)
-            has_w = obj._raw[3] is not None
-            wdev = torch.empty(B, obj.N, dtype=obj.dtype, device=device) if has_w else None
-            x0_dev = torch.empty(B, n, dtype=obj.dtype, device=device)
+            new = lambda *shape: torch.empty(*shape, dtype=obj.dtype, device=device)
+            staged, d_pts, d_obs, x0_dev = new(B, N, 4), new(B, N, 3), new(B, N, 2), new(B, n)
+            d_pose = new(B, 6) if obj._raw[2] is not None else None
+            wdev = new(B, N) if obj._raw[3] is not None else None
             main = torch.cuda.current_stream()
             start = torch.cuda.Event()
             start.record(main)
-            compute = _compute_streams(device)
-            chunk = max(1, int(self.stream_chunk))
-            spans = [(lo, min(lo + chunk, B)) for lo in range(0, B, chunk)]
+            copy, *compute = _side_streams(device)
+            copy.wait_event(start)
+            spans = self._chunk_spans(B, max(1, int(self.stream_chunk)))
             workspaces = torch.empty(len(spans), _lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)
             for k, (lo, hi) in enumerate(spans):
+                with torch.cuda.stream(copy):
+                    obj.upload_rows(lo, hi, d_pts, d_obs, d_pose, wdev)
+                    x0_dev[lo:hi].copy_(x0_host[lo:hi], non_blocking=True)
+                    landed = torch.cuda.Event()
+                    landed.record(copy)
                 cs = compute[k % 2]
                 cs.wait_event(start)
+                cs.wait_event(landed)
                 with torch.cuda.stream(cs):
-                    obj.stage_rows(lo, hi, staged, wdev)                       # H2D + davo_stage_matches
-                    x0_dev[lo:hi].copy_(x0_host[lo:hi], non_blocking=True)
+                    obj.stage_device_rows(lo, hi, d_pts, d_obs, d_pose, staged)
                     sub = type(obj).from_staged(staged[lo:hi], None if wdev is None else wdev[lo:hi])
                     view = SolveBuffers(buf.x[lo:hi], buf.cost[lo:hi], buf.converged[lo:hi], buf.iterations[lo:hi],
                                         buf.evaluations[lo:hi], buf.reason[lo:hi], workspaces[k])
@@ -168,8 +187,10 @@ class BFGSSolver(Module):
                     done.record(cs)
                 main.wait_event(done)
             obj.data0, obj.weights = staged, wdev
-            for t in (staged, x0_dev, workspaces) + ((wdev,) if wdev is not None else ()):
-                t.record_stream(compute[0]); t.record_stream(compute[1])
+            for t in (staged, d_pts, d_obs, x0_dev, workspaces, d_pose, wdev):
+                if t is not None:
+                    for s in (copy, *compute):
+                        t.record_stream(s)
         return buf
 
     def solve_into(self, x0: torch.Tensor, obj: CalibrationObjective, *, error_threshold=None, iterations=None,
