@@ -31,7 +31,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_MATCH_EVAL = {"distort10": 93.0, "joint": 145.0}
+CFG5_TOTAL = 1 << 20   # BASELINE.json configs[4]: 1M problems sharded over the GPUs (strong scaling)
 SOLVER_KW = {"cfg2": dict(error_threshold=1e-7, iterations=1000),
+             "cfg5": dict(error_threshold=1e-7, iterations=1000),
              "cfg3": dict(error_threshold=1e-5, iterations=1000),
              "cfg4": dict(error_threshold=1e-5, iterations=1000)}
 
@@ -41,6 +43,9 @@ def make_batch(config: str, B: int, seed: int):
     syn = davo_b200.synthetic
     if config == "cfg2":
         return syn.make_distort10(B, 256, seed=seed, dtype=np.float32)
+    if config == "cfg5":  # 1M problems: generated with torch on the GPU when there is one (numpy needs minutes)
+        import torch
+        return syn.make_distort10_torch(B, 256, seed=seed, device="cuda" if torch.cuda.is_available() else "cpu")
     if config == "cfg4":
         return syn.make_distort10(B, 256, seed=seed, dtype=np.float32, ill_conditioned=True, pathological=0.02)
     if config == "cfg3":
@@ -48,12 +53,16 @@ def make_batch(config: str, B: int, seed: int):
     raise ValueError(config)
 
 
-def default_B(config: str) -> int:
+def default_B(config: str, world: int = 1) -> int:
+    if config == "cfg5":
+        return CFG5_TOTAL // world
     return 16384 if config == "cfg3" else 65536
 
 
 def workload_name(config: str, B: int) -> str:
     return {"cfg2": f"configs[1]: intrinsics+distortion fit, {B} problems x 256 matches, n=10",
+            "cfg5": f"configs[4]: {CFG5_TOTAL} intrinsics+distortion problems x 256 matches sharded by problem, "
+                    f"{B} per GPU, n=10",
             "cfg3": f"configs[2]: joint intrinsics + 4 view poses, {B} problems x 1024 matches, n=34",
             "cfg4": f"configs[3]: ill-conditioned heavy distortion, {B} problems x 256 matches, n=10"}[config]
 
@@ -156,16 +165,39 @@ def run_reference_arm(args):
             "gpu_launches": 0,
             "note": "reference is pure Python/PyTorch and is not present on the GPU box; this arm times the C "
                     "port of its algorithm (oracle/calib_oracle.c, -O2, OpenMP over problems)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """Keep the real stdout for the ONE JSON line and point fd 1 at stderr for everything else: NCCL (and any
+    other native library) prints banners such as "NCCL version ..." straight to fd 1."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -191,7 +223,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch or default_B(args.config)
+    B = args.batch or default_B(args.config, world)
     batch = make_batch(args.config, B, 0xB200 + rank)
     kw = SOLVER_KW[args.config]
     solver = davo_b200.BFGSSolver(**kw).eval()
@@ -316,7 +348,7 @@ def main():
     traffic = stage_traffic = None
     try:  # DRAM bytes per launch of the solve kernel from the committed ncu --set full capture of this workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if B == default_B(args.config) and args.config in ("cfg2", "cfg3"):
+        if B == default_B(args.config, world) and args.config in ("cfg2", "cfg3"):
             traffic = tj["solve_" + args.config]["bytes"]
         stage_traffic = tj["stage_cfg2"]["bytes"] if (args.config == "cfg2" and B == default_B("cfg2")) else None
     except (OSError, KeyError):
@@ -327,7 +359,8 @@ def main():
         "fevals_per_sec": float(stats[1].item()) / (ms_per_step * 1e-3),
         "converged_frac": float(stats[2].item()) / total_B,
         "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
         "config": {"workload": workload_name(args.config, B), "problems_per_gpu": B, "solver": kw,
                    "l2": f"inputs larger than L2 (staged matches {batch.N * batch.views * B * 16 / 1e6:.0f} MB per GPU)",
                    "seed": "0xB200 + rank", "collective": "one all_gather_into_tensor of the solved records"
@@ -352,7 +385,7 @@ def main():
         c = cpu_arm(args.config, B, 15.0)
         line["cpu_baseline"] = {"value": c["value"], "unit": "solves/s", "cores": c["cores"], "kind": "port",
                                 "sample": c["sample"]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -201,3 +201,47 @@ def stage_numpy(batch: CalibrationBatch) -> np.ndarray:
     z[z == 0] += 1e-8
     return np.stack([xp[..., 0] / z, xp[..., 1] / z, batch.obs[..., 0].astype(np.float64),
                      batch.obs[..., 1].astype(np.float64)], axis=-1)
+
+
+def make_distort10_torch(B: int, N: int = 256, seed: int = 0xB200, device="cpu", fov: float = 0.5,
+                         chunk: int = 65536) -> CalibrationBatch:
+    """make_distort10 (well-conditioned, identity pose) with torch on `device`, for batches too large to
+    generate with single-threaded numpy in reasonable time (BASELINE.json config 5, 1M problems).  Same
+    distributions, float64 arithmetic, float32 result on the host; torch's generator, so the problems are
+    not the numpy generator's."""
+    import torch
+
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    f64 = dict(dtype=torch.float64, device=dev, generator=gen)
+    pts_out = np.empty((B, N, 3), np.float32)
+    obs_out = np.empty((B, N, 2), np.float32)
+    x0_out = np.zeros((B, 10), np.float32)
+    truth_out = np.zeros((B, 10), np.float32)
+    for lo in range(0, B, chunk):
+        b = min(chunk, B - lo)
+        th = torch.zeros(b, 10, dtype=torch.float64, device=dev)
+        th[:, FX] = 1.0 + 0.5 * torch.rand(b, **f64)
+        th[:, FY] = th[:, FX] * (1.0 + 0.02 * torch.randn(b, **f64))
+        th[:, CX] = (0.1 * torch.randn(b, **f64)).clamp(-0.5, 0.5)
+        th[:, CY] = (0.1 * torch.randn(b, **f64)).clamp(-0.5, 0.5)
+        for col, scale in ((K1, 0.05), (K2, 0.005), (K3, 0.0005), (P1, 0.005), (P2, 0.005)):
+            th[:, col] = scale * torch.randn(b, **f64)
+        z = (4.0 + torch.randn(b, N, **f64)).abs() + 1.0
+        xy = z[..., None] * fov * (2.0 * torch.rand(b, N, 2, **f64) - 1.0)
+        a, bb = xy[..., 0] / z, xy[..., 1] / z
+        p = th[:, None, :]
+        u = p[..., FX] * a + p[..., S] * bb
+        v = p[..., FY] * bb
+        r2 = u * u + v * v
+        rad = 1.0 + p[..., K1] * r2 + p[..., K2] * r2 * r2 + p[..., K3] * r2 * r2 * r2
+        up = u * rad + 2.0 * p[..., P1] * u * v + p[..., P2] * (r2 + 2 * u * u) + p[..., CX]
+        vp = v * rad + 2.0 * p[..., P2] * u * v + p[..., P1] * (r2 + 2 * v * v) + p[..., CY]
+        f0 = th[:, FX] * (1.0 + 0.2 * (2.0 * torch.rand(b, **f64) - 1.0))
+        pts_out[lo:lo + b] = torch.cat([xy, z[..., None]], dim=-1).float().cpu().numpy()
+        obs_out[lo:lo + b] = torch.stack([up, vp], dim=-1).float().cpu().numpy()
+        x0_out[lo:lo + b, FX] = f0.float().cpu().numpy()
+        x0_out[lo:lo + b, FY] = x0_out[lo:lo + b, FX]
+        truth_out[lo:lo + b] = th.float().cpu().numpy()
+    return CalibrationBatch("distort10", pts_out, obs_out, np.zeros((B, 6), np.float32), x0_out, truth_out, 1)
