@@ -17,6 +17,13 @@ namespace davo {
 
 constexpr int kSlots = 16;  // distributed-vector width of the warp-per-problem solver (n <= 16)
 constexpr unsigned kFull = 0xffffffffu;
+// Per-warp shared-memory scratch of the warp-per-problem solver: 32 rows x kRedPitch words.  Cross-lane sums go
+// through it as a transpose (every lane stores its partial sums as a row, lane pair c adds up column c) instead
+// of a shuffle reduce-scatter: the shuffle form costs two selects per exchanged value, and the kernel is bound
+// by instruction issue.  Pitch 20 words: rows stay 16-byte aligned and 8 consecutive rows start in distinct
+// 4-bank groups (STS.128 conflict free); a column read hits bank (20 r + c) mod 32.
+constexpr int kRedPitch = 20;
+constexpr int kScratch = 32 * kRedPitch;
 
 // ---- vector-of-4 type per arithmetic type -----------------------------------------------------
 template <typename T> struct Vec4;

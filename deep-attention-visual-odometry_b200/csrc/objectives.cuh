@@ -237,13 +237,16 @@ struct Distort10Objective {
     const SolveParams<T>& p;
     V4* matches;      // this warp's shared-memory slab, N + 32 entries (pair layout, see bind)
     T* weights;       // N entries (only if p.has_w)
+    T* scratch;       // this warp's kScratch-word transpose area (davo_common.cuh)
     uint64_t* bar;    // this warp's mbarrier
     unsigned parity;
     int lane;
 
-    __device__ Distort10Objective(const SolveParams<T>& p_, unsigned char* slab, uint64_t* bar_, int lane_)
+    __device__ Distort10Objective(const SolveParams<T>& p_, unsigned char* slab, T* scratch_, uint64_t* bar_,
+                                  int lane_)
         : p(p_), matches(reinterpret_cast<V4*>(slab)),
-          weights(reinterpret_cast<T*>(slab + sizeof(V4) * (size_t)(p_.N + 32))), bar(bar_), parity(0), lane(lane_) {}
+          weights(reinterpret_cast<T*>(slab + sizeof(V4) * (size_t)(p_.N + 32))), scratch(scratch_), bar(bar_),
+          parity(0), lane(lane_) {}
 
     // bytes of shared memory one warp needs for its slab
     __host__ __device__ static size_t slab_bytes(int N, bool has_w) {
@@ -283,14 +286,10 @@ struct Distort10Objective {
         __syncwarp();
     }
 
-    // One evaluation.  Inlined at its call site (solve_one_warp has a single one): a __noinline__ version ran
-    // 12 % slower (call + stack).
-    __device__ __forceinline__ void eval(const T* th, T& f, T& g_own) {
-        Intrinsics<T> I;
-        I.load(th);
-        P acc2[kPairAcc];
-#pragma unroll
-        for (int k = 0; k < kPairAcc; ++k) acc2[k] = pk(T(0));
+    // The match loop.  kRagged = false (N a multiple of 64: every lane has only complete pairs) drops the
+    // per-pair validity test and the selects that zero the second match's residuals.
+    template <bool kRagged>
+    __device__ __forceinline__ void accumulate(const Intrinsics<T>& I, P (&acc2)[kPairAcc]) {
         P gu, gv;
         const int N = p.N;
 #pragma unroll 2
@@ -300,20 +299,50 @@ struct Distort10Objective {
             P a, b, nus, nvs, w = pk(T(1));
             a.x = ab.x; a.y = ab.y; b.x = ab.z; b.y = ab.w;
             nus.x = ob.x; nus.y = ob.y; nvs.x = ob.z; nvs.y = ob.w;
-            const bool second_valid = i + 32 < N;
+            const bool second_valid = !kRagged || i + 32 < N;
             if (kWeighted) {
                 w.x = weights[i];
                 w.y = second_valid ? weights[i + 32] : T(0);
             }
             match_pair_cost_grad<T, kWeighted>(I, a, b, nus, nvs, w, second_valid, acc2, gu, gv);
         }
+    }
+
+    // One evaluation.  Inlined at its call site (solve_one_warp has a single one): a __noinline__ version ran
+    // 12 % slower (call + stack).
+    __device__ __forceinline__ void eval(const T* th, T& f, T& g_own) {
+        Intrinsics<T> I;
+        I.load(th);
+        P acc2[kPairAcc];
+#pragma unroll
+        for (int k = 0; k < kPairAcc; ++k) acc2[k] = pk(T(0));
+        if ((p.N & 63) == 0) accumulate<false>(I, acc2);
+        else                 accumulate<true>(I, acc2);
         T acc[kSlots];
 #pragma unroll
         for (int k = 0; k < kPairAcc; ++k) acc[k] = acc2[k].x + acc2[k].y;
+        fold_uv_terms(acc);  // acc[11], acc[12] are folded into acc[5], acc[6]: 11 sums remain
+        // Sum over the 32 lanes as a transpose through shared memory: lane L stores its 11 partial sums as row
+        // L, lane pair c adds up column c (lane 2c the even rows, lane 2c+1 the odd rows) and one shuffle joins
+        // the two halves, so lanes 2c and 2c+1 both end with total c.  (The caller's eval_at has synchronised
+        // the warp since the previous evaluation read the scratch area.)
+        V4* row = reinterpret_cast<V4*>(scratch + lane * kRedPitch);
+        V4 q0, q1, q2;
+        q0.x = acc[0]; q0.y = acc[1]; q0.z = acc[2]; q0.w = acc[3];
+        q1.x = acc[4]; q1.y = acc[5]; q1.z = acc[6]; q1.w = acc[7];
+        q2.x = acc[8]; q2.y = acc[9]; q2.z = acc[10]; q2.w = T(0);
+        row[0] = q0; row[1] = q1; row[2] = q2;
+        __syncwarp();
+        const int c = min(lane >> 1, 10), h = lane & 1;
+        const T* col = scratch + h * kRedPitch + c;
+        T part[16];
 #pragma unroll
-        for (int k = kPairAcc; k < kSlots; ++k) acc[k] = T(0);
-        fold_uv_terms(acc);
-        const T mine = reduce_scatter16<true>(acc, lane);  // slot c total in lanes 2c, 2c+1
+        for (int i = 0; i < 16; ++i) part[i] = col[2 * i * kRedPitch];
+#pragma unroll
+        for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+            for (int i = 0; i < w; ++i) part[i] += part[i + w];
+        const T mine = part[0] + shfl_xor(part[0], 1);
         f = shfl_idx(mine, 20);                            // slot 10 = cost
         g_own = (lane < 20) ? T(2) * mine : T(0);          // least_squares_utils.py:43 (factor 2)
     }
@@ -329,7 +358,7 @@ struct AnalyticObjective {
     const T* target;
     int lane;
 
-    __device__ AnalyticObjective(const SolveParams<T>& p_, unsigned char*, uint64_t*, int lane_)
+    __device__ AnalyticObjective(const SolveParams<T>& p_, unsigned char*, T*, uint64_t*, int lane_)
         : p(p_), target(nullptr), lane(lane_) {}
     __host__ __device__ static size_t slab_bytes(int, bool) { return 0; }
     __device__ __forceinline__ void bind(int b) { target = p.data0 ? p.data0 + (size_t)b * p.n : nullptr; }

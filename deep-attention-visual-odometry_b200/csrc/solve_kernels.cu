@@ -13,12 +13,13 @@ namespace davo {
 
 constexpr int kWarpsPerCta = 4;
 #ifndef DAVO_MIN_BLOCKS
-#define DAVO_MIN_BLOCKS 5  // 96 registers: 5 CTAs = 20 warps per SM measured fastest (4.80 ms vs 5.15 at 4, 4.87 at 6)
+#define DAVO_MIN_BLOCKS 4  // 128 registers: no spills (at 5 CTAs = 96 registers the line-search state spills to local memory)
 #endif
 
 template <typename T>
 __host__ __device__ constexpr size_t warp_lines_bytes() {
-    return 2 * kSlots * sizeof(T) + 16;  // trial-point line, broadcast line, mbarrier
+    // trial-point line, broadcast line, transpose scratch (kScratch words), mbarrier
+    return (2 * kSlots + kScratch) * sizeof(T) + 16;
 }
 
 template <typename T, typename Obj>
@@ -38,7 +39,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DAVO_MIN_BLOCKS) warp_probl
     const size_t slab = Obj::slab_bytes(p.N, p.has_w != 0);
     T* xt_line = reinterpret_cast<T*>(mine + slab);
     T* bc_line = xt_line + kSlots;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(bc_line + kSlots);
+    T* scratch = bc_line + kSlots;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(scratch + kScratch);
     if (Obj::kUsesSmemMatches) {
         if (lane == 0) {
             mbar_init(bar, 1);
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DAVO_MIN_BLOCKS) warp_probl
         }
         __syncwarp();
     }
-    Obj obj(p, mine, bar, lane);
+    Obj obj(p, mine, scratch, bar, lane);
     const int n = p.n;
     const int c = lane >> 1;
     const bool own = c < n;
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DAVO_MIN_BLOCKS) warp_probl
         if (b >= (unsigned)p.B) break;
         obj.bind((int)b);
         if (kMode == Mode::kSolve) {
-            solve_one_warp<T, NP, Obj>(obj, p, (int)b, xt_line, bc_line, lane);
+            solve_one_warp<T, NP, Obj>(obj, p, (int)b, xt_line, bc_line, scratch, lane);
         } else if (kMode == Mode::kLineSearch) {
             const size_t o = (size_t)b * n + c;
             const T x = own ? p.x0[o] : T(0);

@@ -165,7 +165,7 @@ __device__ __forceinline__ bool same_bits<double>(double a, double b) {
 //   kEvalFinal  the cost at the returned parameters                       networks/calibration_network.py:71
 template <typename T, int NP, typename Obj>
 __device__ __forceinline__ void solve_one_warp(Obj& obj, const SolveParams<T>& p, int b, T* xt_line, T* bc_line,
-                                               int lane) {
+                                               T* scratch, int lane) {
     enum { kEvalOuter, kEvalProbe, kEvalFinal };
     const int n = p.n;
     const int c = lane >> 1;
@@ -332,18 +332,43 @@ __device__ __forceinline__ void solve_one_warp(Obj& obj, const SolveParams<T>& p
                 // antisymmetric part A to V^T A V (bounded) while the shortcut adds rho s y^T (H^T - H), which
                 // grows on ill-conditioned problems until the directions are useless (config 4: problems that
                 // converge in ~250 iterations ran into the 1000-iteration cap with ~39 probes per search).
+                // (y^T H)_c = sum_j y_j H[j][c] needs COLUMN c while lane pair c holds ROW c: the rows go through
+                // the warp's scratch area (row pitch kRedPitch) and come back as columns, 3 stores + NP loads
+                // instead of a 15-shuffle reduce-scatter with two selects per exchanged value.
                 T yv[NP], sv[NP];
                 slot_gather2<T, NP>(y, s, bc_line, xt_line, lane, yv, sv);
-                T Hy = T(0);                                              // (H y)_c, :293-295
-                T part[kSlots];
+                if (c < NP) {  // every row the column walk below touches is written (rows >= n keep their identity row)
+                    using V4 = typename Vec4<T>::type;
+                    using V2 = typename Vec2<T>::type;
+                    static_assert(NP <= kRedPitch && NP >= 8, "row layout below assumes 8 <= NP <= kRedPitch");
+                    T* rowp = scratch + c * kRedPitch;
+                    if (!(lane & 1)) {
+                        V4 r0, r1;
+                        r0.x = H[0]; r0.y = H[1]; r0.z = H[2]; r0.w = H[3];
+                        r1.x = H[4]; r1.y = H[5]; r1.z = H[6]; r1.w = H[7];
+                        reinterpret_cast<V4*>(rowp)[0] = r0;
+                        reinterpret_cast<V4*>(rowp)[1] = r1;
+                    } else {
 #pragma unroll
-                for (int j = 0; j < kSlots; ++j) part[j] = T(0);
-#pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    Hy = fma_t(H[j], yv[j], Hy);
-                    part[j] = y * H[j];                                   // y_c H[c][j]
+                        for (int j = 8; j + 1 < NP; j += 2) {
+                            V2 r;
+                            r.x = H[j]; r.y = H[j + 1];
+                            *reinterpret_cast<V2*>(rowp + j) = r;
+                        }
+                        if (NP & 1) rowp[NP - 1] = H[NP - 1];
+                    }
                 }
-                const T yH = reduce_scatter16<false>(part, lane);         // (y^T H)_c, :268-270
+                __syncwarp();
+                T Hy = T(0), yH = T(0);                                   // (H y)_c :293-295, (y^T H)_c :268-270
+                {
+                    const T* colp = scratch + (own ? c : 0);
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) {
+                        Hy = fma_t(H[j], yv[j], Hy);
+                        yH = fma_t(yv[j], colp[j * kRedPitch], yH);       // y_j H[j][c]; rows j >= n hold y_j = 0
+                    }
+                    if (!own) yH = T(0);
+                }
                 const T q = mul_rn(slot_allreduce(yH * y), rho);          // y^T H y / (y^T s), :271-274
                 const T onepq = add_rn(T(1), q);
                 const T sr = mul_rn(s, rho);                              // :277
