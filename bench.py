@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — the batched calibration solve on N GPUs of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2|cfg3|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2|cfg3|cfg4|cfg5|ba]
 
 A step = one pass of the hot path over one batch: stage the matches (davo_stage_matches) and solve
 every problem (davo_solve_calibration); with N > 1 also the single all-gather of the solved records.
@@ -30,12 +30,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOP_PER_MATCH_EVAL = {"distort10": 93.0, "joint": 145.0}
+# SURVEY.md §8(d); angle_ba: counted from csrc/objectives_ba.cuh per (view, point) pair per cost+gradient evaluation
+FLOP_PER_MATCH_EVAL = {"distort10": 93.0, "joint": 145.0, "angle_ba": 200.0}
+L2_BYTES = 126 << 20
 CFG5_TOTAL = 1 << 20   # BASELINE.json configs[4]: 1M problems sharded over the GPUs (strong scaling)
 SOLVER_KW = {"cfg2": dict(error_threshold=1e-7, iterations=1000),
              "cfg5": dict(error_threshold=1e-7, iterations=1000),
              "cfg3": dict(error_threshold=1e-5, iterations=1000),
-             "cfg4": dict(error_threshold=1e-5, iterations=1000)}
+             "cfg4": dict(error_threshold=1e-5, iterations=1000),
+             # the entry script's objective with the driver's eval threshold
+             # (networks/calibration_network.py:44), 4 views x 8 points as in its config
+             "ba": dict(error_threshold=1e-7, iterations=1000)}
 
 
 def make_batch(config: str, B: int, seed: int):
@@ -50,6 +55,8 @@ def make_batch(config: str, B: int, seed: int):
         return syn.make_distort10(B, 256, seed=seed, dtype=np.float32, ill_conditioned=True, pathological=0.02)
     if config == "cfg3":
         return syn.make_joint(B, 256, 4, seed=seed, dtype=np.float32)
+    if config == "ba":
+        return syn.make_angle_ba(B, 8, 4, seed=seed, dtype=np.float32)
     raise ValueError(config)
 
 
@@ -64,7 +71,9 @@ def workload_name(config: str, B: int) -> str:
             "cfg5": f"configs[4]: {CFG5_TOTAL} intrinsics+distortion problems x 256 matches sharded by problem, "
                     f"{B} per GPU, n=10",
             "cfg3": f"configs[2]: joint intrinsics + 4 view poses, {B} problems x 1024 matches, n=34",
-            "cfg4": f"configs[3]: ill-conditioned heavy distortion, {B} problems x 256 matches, n=10"}[config]
+            "cfg4": f"configs[3]: ill-conditioned heavy distortion, {B} problems x 256 matches, n=10",
+            "ba": f"entry-script objective (SURVEY 8f row 1): bundle adjustment with angular error, {B} problems x "
+                  f"4 views x 8 points, n=45"}[config]
 
 
 def algorithmic_flops(batch, fevals: np.ndarray, iters: np.ndarray) -> float:
@@ -197,7 +206,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "ba"])
     ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the BASELINE size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -230,21 +239,30 @@ def main():
     steps, warm = args.steps, max(args.warmup, 3)
 
     # ---- raw inputs resident in HBM (value) and in pinned host memory (e2e) ------------------------------
-    h_pts = torch.from_numpy(batch.points_3d).pin_memory()
+    # (angle_ba has no 3-D points: its second input is the visibility mask)
+    second = batch.weights if batch.model == "angle_ba" else batch.points_3d
+    h_pts = torch.from_numpy(second).pin_memory()
     h_obs = torch.from_numpy(batch.obs).pin_memory()
     h_x0 = torch.from_numpy(batch.x0).pin_memory()
     d_pts, d_obs, d_x0 = h_pts.to(dev), h_obs.to(dev), h_x0.to(dev)
+    input_bytes = (h_pts.numel() + h_obs.numel() + h_x0.numel()) * 4
+    # timing rule: inputs larger than L2, or flush L2 between timed iterations (outside the per-step events)
+    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev) if input_bytes <= L2_BYTES else None
     slab = ResultSlab(B * world, batch.n, torch.float32, world, dev)
     out = slab.buffers(rank)
 
     def make_objective(pts, obs):
         if batch.model == "distort10":
             return davo_b200.DistortionObjective(pts, obs)  # runs davo_stage_matches
+        if batch.model == "angle_ba":
+            return davo_b200.AngleDistanceObjective(obs, pts)
         return davo_b200.JointPoseObjective(pts, obs)
 
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
     def step(record=False):
+        if flush is not None:
+            flush.zero_()
         if record:
             ev[0].record()
         obj = make_objective(d_pts, d_obs)
@@ -254,6 +272,8 @@ def main():
         if record:
             ev[2].record()
         slab.all_gather(rank)
+        if record:
+            ev[3].record()
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,7 +289,7 @@ def main():
         sampler.start()
     launches0 = _lib.launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    solve_ms, stage_ms = [], []
+    solve_ms, stage_ms, step_ms = [], [], []
     barrier()
     t_start.record()
     for _ in range(steps):
@@ -277,12 +297,15 @@ def main():
         # per-kernel events are read after the loop; recording them does not synchronise
         solve_ms.append((ev[1], ev[2]))
         stage_ms.append((ev[0], ev[1]))
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        step_ms.append((ev[0], ev[3]))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     t_end.record()
     barrier()
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = t_start.elapsed_time(t_end)
+    # with an L2 flush between the steps the timed region is the sum of the per-step event pairs (flush excluded)
+    total_ms = (t_start.elapsed_time(t_end) if flush is None
+                else float(sum(a.elapsed_time(b) for a, b in step_ms)))
     solve_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in solve_ms]))
     stage_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in stage_ms]))
     if world > 1:
@@ -320,7 +343,7 @@ def main():
             t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        h2d = h_pts.numel() * 4 + h_obs.numel() * 4 + h_x0.numel() * 4
+        h2d = input_bytes
         d2h = sum(t.numel() * t.element_size() for t in info)
         e2e = {"value": total_B / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}
@@ -362,15 +385,17 @@ def main():
         "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(args.config, B), "problems_per_gpu": B, "solver": kw,
-                   "l2": f"inputs larger than L2 (staged matches {batch.N * batch.views * B * 16 / 1e6:.0f} MB per GPU)",
+                   "l2": (f"inputs larger than L2 ({input_bytes / 1e6:.0f} MB of raw inputs per GPU)" if flush is None
+                          else f"L2 flushed between timed steps (a {2 * L2_BYTES >> 20} MiB buffer is rewritten, outside "
+                               f"the per-step events; inputs are {input_bytes / 1e6:.0f} MB per GPU)"),
                    "seed": "0xB200 + rank", "collective": "one all_gather_into_tensor of the solved records"
                    if world > 1 else "none (single GPU)"},
         "kernel_ms": {"solve": solve_kernel_ms, "stage": stage_kernel_ms},
         "mean_iters": float(iters.mean()), "mean_fevals": float(fevals.mean()), "reasons_rank0": reasons,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp32_peak, "traffic": traffic,
-                     "traffic_note": "DRAM bytes per launch (ncu); the kernel is FP32-pipe bound, its staged matches "
-                                     f"are {batch.N * batch.views * B * 16} B and are read from HBM once",
+                     "traffic_note": "DRAM bytes per launch (ncu); the kernel is FP32-pipe bound, its per-problem inputs "
+                                     "are read from HBM once and kept in shared memory",
                      "executed_frac": achieved / fp32_peak * float((fevals - iters).sum()) / float(fevals.sum()),
                      "peak_source": f"{props.multi_processor_count} SMs x 128 lanes x 2 x {sm_max_mhz:.0f} MHz "
                                     "(no FP32 figure in MEASURED_PEAKS.json; sm_max_mhz taken from it)",

@@ -6,13 +6,15 @@ fallback: calling a compute function without the built library or without a CUDA
 """
 from . import synthetic  # noqa: F401
 from . import _lib  # noqa: F401
-from .objectives import AnalyticObjective, CalibrationObjective, DistortionObjective, JointPoseObjective
+from .objectives import (AnalyticObjective, AngleDistanceObjective, CalibrationObjective, DistortionObjective,
+                         JointPoseObjective)
 from .solvers import BFGSSolver, SolveInfo, line_search_wolfe_conditions
 from .camera_model import compute_distorted_camera_model, compute_distorted_camera_model_and_jacobian
+from .networks import CalibrationNetwork, unpack_calibration_parameters
 from .least_squares_utils import find_error, find_error_gradient, find_residuals
 
 __all__ = [
-    "AnalyticObjective", "BFGSSolver", "CalibrationObjective", "DistortionObjective", "JointPoseObjective",
+    "AnalyticObjective", "AngleDistanceObjective", "BFGSSolver", "CalibrationNetwork", "CalibrationObjective", "DistortionObjective", "JointPoseObjective",
     "SolveInfo", "compute_distorted_camera_model", "compute_distorted_camera_model_and_jacobian", "find_error",
-    "find_error_gradient", "find_residuals", "line_search_wolfe_conditions", "synthetic",
+    "find_error_gradient", "find_residuals", "line_search_wolfe_conditions", "synthetic", "unpack_calibration_parameters",
 ]

@@ -21,7 +21,7 @@ ABI_VERSION = 1
 WORKSPACE_BYTES = 256
 F32, F64 = 0, 1
 
-MODEL_IDS = {"distort10": 0, "joint": 1, "sphere": 16, "sphere_offset": 17, "log_sphere": 18,
+MODEL_IDS = {"distort10": 0, "joint": 1, "angle_ba": 2, "sphere": 16, "sphere_offset": 17, "log_sphere": 18,
              "rosenbrock": 19, "cosine": 20, "x2_sine": 21, "distance": 22}
 REASON_NAMES = {0: "threshold", 1: "step", 2: "cap", 3: "nan"}
 

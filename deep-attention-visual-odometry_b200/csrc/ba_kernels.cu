@@ -1,0 +1,24 @@
+// ba_kernels.cu — the ANGLE_BA model (the entry script's bundle-adjustment objective,
+// networks/calibration_network.py:58-67; n = 3 + 3N + 6(V-1) <= 64) on the generic warp-per-problem
+// kernels of wide_kernel.cuh: solve, line search, cost + gradient.
+#include "davo_common.cuh"
+#include "objectives_ba.cuh"
+#include "wide_kernel.cuh"
+#include "launch.h"
+
+namespace davo {
+
+template <typename T, WMode kMode>
+static int launch_ba(const SolveParams<T>& p, cudaStream_t s) {
+    if (p.V < 2 || p.N < 1 || p.n != 3 + 3 * p.N + 6 * (p.V - 1)) return DAVO_ERR_BAD_SHAPE;
+    return launch_wide<T, AngleBAObjective<T>, kMode>(p, s);
+}
+
+int launch_solve_ba_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_ba<float, WMode::kSolve>(p, s); }
+int launch_solve_ba_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_ba<double, WMode::kSolve>(p, s); }
+int launch_eval_ba_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_ba<float, WMode::kEval>(p, s); }
+int launch_eval_ba_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_ba<double, WMode::kEval>(p, s); }
+int launch_line_search_ba_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_ba<float, WMode::kLineSearch>(p, s); }
+int launch_line_search_ba_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_ba<double, WMode::kLineSearch>(p, s); }
+
+}  // namespace davo

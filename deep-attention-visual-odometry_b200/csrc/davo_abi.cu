@@ -27,6 +27,8 @@ static int check_desc(const davo_problem_desc* d) {
         if (d->n != 10 || d->V != 1) return DAVO_ERR_BAD_SHAPE;
     } else if (d->model == DAVO_MODEL_JOINT) {
         if (d->n != 10 + 6 * d->V) return DAVO_ERR_BAD_SHAPE;
+    } else if (d->model == DAVO_MODEL_ANGLE_BA) {
+        if (d->V < 2 || d->N < 1 || d->n != 3 + 3 * d->N + 6 * (d->V - 1)) return DAVO_ERR_BAD_SHAPE;
     } else if (is_analytic(d->model)) {
         if (d->model == DAVO_MODEL_ROSENBROCK && d->n != 2) return DAVO_ERR_BAD_SHAPE;
         if (d->n > kSlots) return DAVO_ERR_UNSUPPORTED;
@@ -44,7 +46,7 @@ static int check_data(const davo_problem_desc* d, const void* data0, const void*
     } else if (d->model == DAVO_MODEL_JOINT) {
         if (!data0 || !data1) return DAVO_ERR_NULL_POINTER;
         if (!aligned16(data0) || !aligned16(data1)) return DAVO_ERR_MISALIGNED;
-    } else if (d->model == DAVO_MODEL_DISTANCE) {
+    } else if (d->model == DAVO_MODEL_DISTANCE || d->model == DAVO_MODEL_ANGLE_BA) {
         if (!data0) return DAVO_ERR_NULL_POINTER;
     }
     if (d->has_weights && !w) return DAVO_ERR_NULL_POINTER;
@@ -69,6 +71,12 @@ static SolveParams<T> make_params(const davo_problem_desc* d, const void* data0,
 #endif
     return p;
 }
+
+// model -> launcher (f32 / f64 instantiations live in solve_kernels.cu, joint_kernels.cu, ba_kernels.cu)
+#define DAVO_DISPATCH(what, suffix, p, s)                                           \
+    ((p).model == DAVO_MODEL_JOINT      ? launch_##what##_joint_##suffix((p), (s))  \
+     : (p).model == DAVO_MODEL_ANGLE_BA ? launch_##what##_ba_##suffix((p), (s))     \
+                                        : launch_##what##_warp_##suffix((p), (s)))
 }  // namespace davo
 
 using namespace davo;
@@ -115,14 +123,14 @@ int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, con
         p.cost_out = static_cast<float*>(cost_out); p.converged_out = converged_out;
         p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
         p.queue = static_cast<unsigned*>(workspace);
-        return desc->model == DAVO_MODEL_JOINT ? launch_solve_joint_f32(p, s) : launch_solve_warp_f32(p, s);
+        return DAVO_DISPATCH(solve, f32, p, s);
     }
     SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
     p.x0 = static_cast<const double*>(x0); p.x_out = static_cast<double*>(x_out);
     p.cost_out = static_cast<double*>(cost_out); p.converged_out = converged_out;
     p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
     p.queue = static_cast<unsigned*>(workspace);
-    return desc->model == DAVO_MODEL_JOINT ? launch_solve_joint_f64(p, s) : launch_solve_warp_f64(p, s);
+    return DAVO_DISPATCH(solve, f64, p, s);
 }
 
 int davo_eval_cost_grad(const davo_problem_desc* desc, const void* data0, const void* data1,
@@ -137,12 +145,12 @@ int davo_eval_cost_grad(const davo_problem_desc* desc, const void* data0, const 
         SolveParams<float> p = make_params<float>(desc, data0, data1, weights);
         p.x0 = static_cast<const float*>(x); p.cost_out = static_cast<float*>(cost);
         p.x_out = static_cast<float*>(grad);
-        return desc->model == DAVO_MODEL_JOINT ? launch_eval_joint_f32(p, s) : launch_eval_warp_f32(p, s);
+        return DAVO_DISPATCH(eval, f32, p, s);
     }
     SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
     p.x0 = static_cast<const double*>(x); p.cost_out = static_cast<double*>(cost);
     p.x_out = static_cast<double*>(grad);
-    return desc->model == DAVO_MODEL_JOINT ? launch_eval_joint_f64(p, s) : launch_eval_warp_f64(p, s);
+    return DAVO_DISPATCH(eval, f64, p, s);
 }
 
 int davo_line_search(const davo_problem_desc* desc, const void* data0, const void* data1,
@@ -159,13 +167,13 @@ int davo_line_search(const davo_problem_desc* desc, const void* data0, const voi
         p.x0 = static_cast<const float*>(x); p.dir = static_cast<const float*>(direction);
         p.base_cost = static_cast<const float*>(base_cost); p.base_grad = static_cast<const float*>(base_grad);
         p.alpha_out = static_cast<float*>(alpha_out); p.fevals_out = fevals_out;
-        return desc->model == DAVO_MODEL_JOINT ? launch_line_search_joint_f32(p, s) : launch_line_search_warp_f32(p, s);
+        return DAVO_DISPATCH(line_search, f32, p, s);
     }
     SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
     p.x0 = static_cast<const double*>(x); p.dir = static_cast<const double*>(direction);
     p.base_cost = static_cast<const double*>(base_cost); p.base_grad = static_cast<const double*>(base_grad);
     p.alpha_out = static_cast<double*>(alpha_out); p.fevals_out = fevals_out;
-    return desc->model == DAVO_MODEL_JOINT ? launch_line_search_joint_f64(p, s) : launch_line_search_warp_f64(p, s);
+    return DAVO_DISPATCH(line_search, f64, p, s);
 }
 
 int davo_stage_matches(const davo_problem_desc* desc, const void* points_3d, const void* obs,

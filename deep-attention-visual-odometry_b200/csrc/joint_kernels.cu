@@ -1,102 +1,19 @@
-// joint_kernels.cu — persistent warp-per-problem kernels for the JOINT model (intrinsics + per-view
-// pose, n = 10 + 6V <= 64): solve, line search, cost + gradient.  Same scheduling as
-// solve_kernels.cu: the solve pulls problems from an atomic queue, the other two use a static
-// round-robin.  Each warp owns a slab of shared memory: staged world points + observations, the
-// solver's n-vectors and the n x n inverse Hessian.
+// joint_kernels.cu — kernels for the JOINT model (intrinsics + per-view pose, n = 10 + 6V <= 64): the
+// CTA-per-problem solve (solver_cta.cuh) and, through the generic warp-per-problem kernels of
+// wide_kernel.cuh, line search and cost + gradient (and the warp solve kept for A/B runs).
 #include "davo_common.cuh"
 #include "objectives_joint.cuh"
 #include "solver_wide.cuh"
+#include "wide_kernel.cuh"
 #include "solver_cta.cuh"
 #include "launch.h"
 
 namespace davo {
 
-constexpr int kJointWarpsPerCta = 2;
-enum class JMode { kSolve, kLineSearch, kEval };
-
-template <typename T>
-__host__ __device__ inline size_t joint_warp_stride(int N, int V, int n, bool has_w) {
-    size_t b = JointObjective<T>::slab_bytes(N, V, has_w) + WideWorkspace<T>::bytes(n);
-    return (b + 127) & ~size_t(127);
-}
-
-template <typename T, JMode kMode>
-__global__ void __launch_bounds__(kJointWarpsPerCta * 32) joint_problem_kernel(const SolveParams<T> p) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* mine = smem + (size_t)warp * joint_warp_stride<T>(p.N, p.V, p.n, p.has_w != 0);
-    JointObjective<T> obj(p, mine, lane);
-    obj.init();
-    WideWorkspace<T> ws;
-    ws.carve(mine + JointObjective<T>::slab_bytes(p.N, p.V, p.has_w != 0), p.n);
-    const int n = p.n;
-    const unsigned total_warps = gridDim.x * kJointWarpsPerCta;
-    unsigned b_static = blockIdx.x * kJointWarpsPerCta + warp;
-    for (;;) {
-        unsigned b = 0;
-        if (kMode == JMode::kSolve) {
-            if (lane == 0) b = atomicAdd(p.queue, 1u);
-            b = __shfl_sync(kFull, b, 0);
-        } else {
-            b = b_static;
-            b_static += total_warps;
-        }
-        if (b >= (unsigned)p.B) break;
-        obj.bind((int)b);
-        if (kMode == JMode::kSolve) {
-            solve_one_wide<T>(obj, p, (int)b, ws, lane);
-        } else {
-            for (int c = lane; c < n; c += 32) ws.x[c] = p.x0[(size_t)b * n + c];
-            __syncwarp();
-            if (kMode == JMode::kLineSearch) {
-                for (int c = lane; c < n; c += 32) {
-                    ws.d[c] = p.dir[(size_t)b * n + c];
-                    ws.g[c] = p.base_grad[(size_t)b * n + c];
-                }
-                __syncwarp();
-                const LineSearchResult<T> r =
-                    line_search_wide(obj, p, ws.x, ws.d, p.base_cost[b], ws.g, ws.xt, ws.gt, lane);
-                if (lane == 0) {
-                    p.alpha_out[b] = r.alpha;
-                    if (p.fevals_out) p.fevals_out[b] = r.probes;
-                }
-            } else {
-                const T f = obj.eval(ws.x, ws.g);
-                if (lane == 0 && p.cost_out) p.cost_out[b] = f;
-                if (p.x_out)
-                    for (int c = lane; c < n; c += 32) p.x_out[(size_t)b * n + c] = ws.g[c];
-            }
-            __syncwarp();
-        }
-    }
-}
-
-template <typename T, JMode kMode>
+template <typename T, WMode kMode>
 static int launch_joint(const SolveParams<T>& p, cudaStream_t stream) {
-    if (p.V < 1 || p.V > kMaxViews || p.n > kWideMax) return DAVO_ERR_UNSUPPORTED;
-    auto kernel = joint_problem_kernel<T, kMode>;
-    const size_t smem = joint_warp_stride<T>(p.N, p.V, p.n, p.has_w != 0) * kJointWarpsPerCta;
-    int dev = 0, sms = 0, max_optin = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return DAVO_ERR_CUDA;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kJointWarpsPerCta * 32, smem) != cudaSuccess ||
-        per_sm < 1)
-        return DAVO_ERR_CUDA;
-    long long grid = (long long)per_sm * sms;
-    const long long need = ((long long)p.B + kJointWarpsPerCta - 1) / kJointWarpsPerCta;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    if (kMode == JMode::kSolve && cudaMemsetAsync(p.queue, 0, sizeof(unsigned), stream) != cudaSuccess)
-        return DAVO_ERR_CUDA;
-    kernel<<<(unsigned)grid, kJointWarpsPerCta * 32, smem, stream>>>(p);
-    count_launch();
-    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+    if (p.V < 1 || p.V > kMaxViews) return DAVO_ERR_UNSUPPORTED;
+    return launch_wide<T, JointObjective<T>, kMode>(p, stream);
 }
 
 // ---- CTA-per-problem solve (W warps cooperate on one problem) -------------------------------------------
@@ -165,15 +82,15 @@ static int launch_joint_solve(const SolveParams<T>& p, cudaStream_t s) {
 }
 
 #if DAVO_JOINT_WARP_SOLVE  // A/B: the warp-per-problem wide solver
-int launch_solve_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint<float, JMode::kSolve>(p, s); }
-int launch_solve_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint<double, JMode::kSolve>(p, s); }
+int launch_solve_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint<float, WMode::kSolve>(p, s); }
+int launch_solve_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint<double, WMode::kSolve>(p, s); }
 #else
 int launch_solve_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint_solve<float>(p, s); }
 int launch_solve_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint_solve<double>(p, s); }
 #endif
-int launch_eval_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint<float, JMode::kEval>(p, s); }
-int launch_eval_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint<double, JMode::kEval>(p, s); }
-int launch_line_search_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint<float, JMode::kLineSearch>(p, s); }
-int launch_line_search_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint<double, JMode::kLineSearch>(p, s); }
+int launch_eval_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint<float, WMode::kEval>(p, s); }
+int launch_eval_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint<double, WMode::kEval>(p, s); }
+int launch_line_search_joint_f32(const SolveParams<float>& p, cudaStream_t s) { return launch_joint<float, WMode::kLineSearch>(p, s); }
+int launch_line_search_joint_f64(const SolveParams<double>& p, cudaStream_t s) { return launch_joint<double, WMode::kLineSearch>(p, s); }
 
 }  // namespace davo

@@ -21,6 +21,13 @@ int launch_eval_joint_f64(const SolveParams<double>& p, cudaStream_t s);
 int launch_line_search_joint_f32(const SolveParams<float>& p, cudaStream_t s);
 int launch_line_search_joint_f64(const SolveParams<double>& p, cudaStream_t s);
 
+int launch_solve_ba_f32(const SolveParams<float>& p, cudaStream_t s);
+int launch_solve_ba_f64(const SolveParams<double>& p, cudaStream_t s);
+int launch_eval_ba_f32(const SolveParams<float>& p, cudaStream_t s);
+int launch_eval_ba_f64(const SolveParams<double>& p, cudaStream_t s);
+int launch_line_search_ba_f32(const SolveParams<float>& p, cudaStream_t s);
+int launch_line_search_ba_f64(const SolveParams<double>& p, cudaStream_t s);
+
 template <typename T>
 int launch_stage(int B, int N, const T* pts, const T* obs, const T* pose, T* staged, cudaStream_t s);
 template <typename T>

@@ -214,6 +214,36 @@ class JointPoseObjective(CalibrationObjective):
         self.weights = None if weights is None else _to_device(weights, dtype, device).reshape(self.B, V, N)
 
 
+class AngleDistanceObjective(CalibrationObjective):
+    """The entry script's objective (networks/calibration_network.py:58-67): bundle adjustment of
+    (f, cx, cy | N world points | M-1 translations | M-1 axis-angle rotations), n = 3 + 3N + 6(M-1), with the
+    visibility-weighted angle between each pixel's ray and its camera-relative point as the error.
+
+    true_projected_points [(B..),M,N,2], visibility_mask [(B..),M,N] (bool or float; None = all visible):
+    the two tensors CalibrationNetwork.forward receives.
+    """
+
+    model = "angle_ba"
+
+    def __init__(self, true_projected_points, visibility_mask=None, dtype=None, device=None):
+        device = _lib.require_cuda() if device is None else torch.device(device)
+        obs = torch.as_tensor(true_projected_points)
+        if obs.dim() < 3 or obs.shape[-1] != 2:
+            raise ValueError("true_projected_points must be (B..) x M x N x 2")
+        dtype = dtype or obs.dtype
+        batch_shape, M, N = obs.shape[:-3], obs.shape[-3], obs.shape[-2]
+        if M < 2:
+            raise ValueError("the bundle-adjustment objective needs at least two views")
+        super().__init__(batch_shape, 3 + 3 * N + 6 * (M - 1), N, dtype, device)
+        self.views = M
+        self.data0 = _to_device(obs, dtype, device).reshape(self.B, M, N, 2)
+        if visibility_mask is not None:
+            vis = torch.as_tensor(visibility_mask)
+            if tuple(vis.shape) != tuple(batch_shape) + (M, N):
+                raise ValueError(f"visibility_mask must be {tuple(batch_shape) + (M, N)}, got {tuple(vis.shape)}")
+            self.weights = _to_device(vis, dtype, device).reshape(self.B, M, N)
+
+
 class AnalyticObjective(CalibrationObjective):
     """The reference's analytic test objectives (tests/autograd_solvers/reference_functions.py:20-62,
     test_bfgs_solver.py:33-46, line_search/test_wolffe_conditions.py:214-305), compiled into the solver

@@ -63,7 +63,8 @@ def _require_descriptor(error_function) -> CalibrationObjective:
     if not isinstance(error_function, CalibrationObjective):
         raise TypeError(
             "the B200 solver runs the objective inside a CUDA kernel and needs a CalibrationObjective "
-            "descriptor (DistortionObjective, JointPoseObjective, AnalyticObjective), not an arbitrary Python "
+            "descriptor (DistortionObjective, JointPoseObjective, AngleDistanceObjective, AnalyticObjective), not an "
+            "arbitrary Python "
             f"callable (got {type(error_function).__name__}); there is no CPU / autograd fallback")
     return error_function
 

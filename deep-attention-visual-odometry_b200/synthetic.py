@@ -57,6 +57,10 @@ class CalibrationBatch:
     model "distort10": points_3d [B,N,3], obs [B,N,2], pose [B,6] fixed, x0/truth [B,10].
     model "joint":     points_3d [B,N,3] world points shared by V views, obs [B,V,N,2],
                        x0/truth [B,10+6V] = intrinsics then (rx,ry,rz,tx,ty,tz) per view.
+    model "angle_ba":  the driver's bundle-adjustment objective (networks/calibration_network.py:58-67):
+                       points_3d None (the world points are parameters), obs [B,V,N,2] pixel coordinates,
+                       weights [B,V,N] visibility mask, x0/truth [B, 3 + 3N + 6(V-1)] =
+                       (f, cx, cy), N world points, V-1 translations, V-1 axis-angle rotations.
     """
 
     model: str
@@ -66,14 +70,15 @@ class CalibrationBatch:
     x0: np.ndarray
     truth: np.ndarray
     views: int = 1
+    weights: np.ndarray | None = None
 
     @property
     def B(self) -> int:
-        return self.points_3d.shape[0]
+        return self.obs.shape[0]
 
     @property
     def N(self) -> int:
-        return self.points_3d.shape[1]
+        return self.obs.shape[-2]
 
     @property
     def n(self) -> int:
@@ -82,18 +87,18 @@ class CalibrationBatch:
     def astype(self, dtype) -> "CalibrationBatch":
         cast = lambda a: None if a is None else np.ascontiguousarray(a, dtype=dtype)
         return CalibrationBatch(self.model, cast(self.points_3d), cast(self.obs), cast(self.pose),
-                                cast(self.x0), cast(self.truth), self.views)
+                                cast(self.x0), cast(self.truth), self.views, cast(self.weights))
 
     def slice(self, lo: int, hi: int) -> "CalibrationBatch":
         cut = lambda a: None if a is None else np.ascontiguousarray(a[lo:hi])
         return CalibrationBatch(self.model, cut(self.points_3d), cut(self.obs), cut(self.pose),
-                                cut(self.x0), cut(self.truth), self.views)
+                                cut(self.x0), cut(self.truth), self.views, cut(self.weights))
 
     def digest(self) -> str:
         """sha256 over the float32 image of the inputs: golden fixtures store it so that a drifting
         generator is detected instead of silently comparing different problems."""
         h = hashlib.sha256()
-        for a in (self.points_3d, self.obs, self.pose, self.x0):
+        for a in (self.points_3d, self.obs, self.pose, self.x0, self.weights):
             if a is not None:
                 h.update(np.ascontiguousarray(a, dtype=np.float32).tobytes())
         return h.hexdigest()
@@ -188,6 +193,47 @@ def make_joint(B: int, N: int = 256, V: int = 4, seed: int = 0xB200, dtype=np.fl
     x0[:, 10:] = start.reshape(B, 6 * V)
     truth = np.concatenate([intr, poses.reshape(B, 6 * V)], axis=1)
     return CalibrationBatch("joint", pts, obs, None, x0, truth, V).astype(dtype)
+
+
+def rotate_axis_angle_numpy(x: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """Rodrigues rotation of x [...,3] by the axis-angle vector w [...,3] (geometry/axis_angle_rotation.py:25-54),
+    float64, for generating observations only."""
+    ang = np.sqrt((w * w).sum(-1, keepdims=True))
+    safe = np.where(ang > 1e-12, ang, 1.0)
+    s_on = np.where(ang > 1e-12, np.sin(ang) / safe, 1.0)
+    omc = np.where(ang > 1e-12, (1.0 - np.cos(ang)) / (safe * safe), 0.5)
+    dot = (x * w).sum(-1, keepdims=True)
+    wb, xb = np.broadcast_arrays(w, x)
+    return x * np.cos(ang) + omc * dot * w + np.cross(wb, xb) * s_on
+
+
+def make_angle_ba(B: int, N: int = 8, V: int = 4, seed: int = 0xB200, dtype=np.float32,
+                  start_noise: float = 1.0) -> CalibrationBatch:
+    """The entry script's problem (camera_calibration_from_oracle_matches.py:29-75 -> CalibrationNetwork):
+    V views of N world points, unknown focal length / principal point, world points and the pose of views
+    1..V-1 relative to view 0.  Distributions follow the reference generator
+    (data/camera_and_parameters_dataset.py:48-61,85-94,147-151; that file does not parse at HEAD): world points
+    xy ~ 3 N(0,1), z ~ |20 + 5 N(0,1)|, camera offsets ~ 3 N(0,1), f' = 1/tan(U(30,120 deg)/2), principal point
+    ~ clamp(0.2 N(0,1), +-0.5); rotations are small (0.3 N(0,1) rad) so that most points stay in view.  The start
+    is the truth perturbed by start_noise * (0.1, 0.05, 0.05 | 0.3 | 0.3 | 0.03) (the reference starts from an
+    MLP's guess).  `weights` is the visibility mask |u|,|v| < 1 (:165-169 of the generator)."""
+    if V < 2:
+        raise ValueError("the bundle-adjustment objective needs at least two views")
+    rng = np.random.default_rng(seed)
+    X = np.concatenate([3.0 * rng.standard_normal((B, N, 2)), np.abs(20.0 + 5.0 * rng.standard_normal((B, N, 1)))], -1)
+    t = 3.0 * rng.standard_normal((B, V - 1, 3))
+    w = 0.3 * rng.standard_normal((B, V - 1, 3))
+    fov = 3 * np.pi / 18 + (9 * np.pi / 18) * rng.uniform(size=B)
+    fp = 1.0 / np.tan(fov / 2.0)
+    c = np.clip(0.2 * rng.standard_normal((B, 2)), -0.5, 0.5)
+    f = np.where(fp > 1.0, fp - 1.0, np.log(fp))  # f' = elu(f) + 1, geometry/homogeneous_projection.py:37
+    truth = np.concatenate([f[:, None], c, X.reshape(B, -1), t.reshape(B, -1), w.reshape(B, -1)], -1)
+    rel = np.concatenate([X[:, None], rotate_axis_angle_numpy(X[:, None], w[:, :, None]) + t[:, :, None]], 1)
+    uv = fp[:, None, None, None] * rel[..., :2] / rel[..., 2:3] + c[:, None, None, :]
+    vis = ((np.abs(uv) < 1.0).all(-1) & (rel[..., 2] > 0)).astype(np.float64)
+    sig = np.concatenate([[0.1, 0.05, 0.05], np.full(3 * N, 0.3), np.full(3 * (V - 1), 0.3), np.full(3 * (V - 1), 0.03)])
+    x0 = truth + start_noise * sig * rng.standard_normal(truth.shape)
+    return CalibrationBatch("angle_ba", None, uv, None, x0, truth, V, vis).astype(dtype)
 
 
 def stage_numpy(batch: CalibrationBatch) -> np.ndarray:

@@ -57,6 +57,18 @@ typedef enum davo_status {
  */
 #define DAVO_MODEL_DISTORT10 0
 #define DAVO_MODEL_JOINT 1
+/* ANGLE_BA:  the entry script's bundle-adjustment objective (networks/calibration_network.py:58-67):
+ *            parameters (f, cx, cy | N world points | V-1 translations | V-1 axis-angle rotations),
+ *            n = 3 + 3N + 6(V-1), V >= 2; error = sum over views and points of
+ *            visibility * angle(pixel ray, camera-relative point), with
+ *            unpack_calibration_parameters / get_camera_relative_points
+ *            (camera_model/calibration_pinhole_camera_model.py:33-117), rotate_vector_axis_angle
+ *            (geometry/axis_angle_rotation.py:25-54), pixel_coordinates_to_homogeneous
+ *            (geometry/homogeneous_projection.py:21-44) and projective_plane_angle_distance
+ *            (geometry/projective_plane_angle_distance.py:20-64).
+ *            data0 = true_projected_points [B,V,N,2]; data1 unused;
+ *            weights [B,V,N] = visibility mask (has_weights = 0: every point visible). */
+#define DAVO_MODEL_ANGLE_BA 2
 #define DAVO_MODEL_SPHERE 16        /* sum x^2                                   */
 #define DAVO_MODEL_SPHERE_OFFSET 17 /* sum x^2 + 10                              */
 #define DAVO_MODEL_LOG_SPHERE 18    /* log(1 + sum x^2)                          */

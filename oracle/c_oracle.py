@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libdavo_oracle.so")
 
-MODEL_IDS = {"distort10": 0, "joint": 1, "sphere": 16, "sphere_offset": 17, "log_sphere": 18,
+MODEL_IDS = {"distort10": 0, "joint": 1, "angle_ba": 2, "sphere": 16, "sphere_offset": 17, "log_sphere": 18,
              "rosenbrock": 19, "cosine": 20, "x2_sine": 21, "distance": 22}
 REASONS = {0: "threshold", 1: "step", 2: "cap", 3: "nan"}
 
@@ -185,5 +185,8 @@ def solve_batch(batch, threads=0, **solver_kwargs):
         return solve("distort10", batch.x0, staged, N=batch.N, V=1, threads=threads, **solver_kwargs)
     if batch.model == "joint":
         return solve("joint", batch.x0, batch.points_3d, batch.obs, N=batch.N, V=batch.views, threads=threads,
+                     **solver_kwargs)
+    if batch.model == "angle_ba":
+        return solve("angle_ba", batch.x0, batch.obs, None, batch.weights, N=batch.N, V=batch.views, threads=threads,
                      **solver_kwargs)
     raise ValueError(batch.model)

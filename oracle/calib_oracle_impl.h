@@ -24,7 +24,7 @@
 
 typedef struct {
     int model, n, N, V, has_weights;
-    const REAL* data0; /* DISTORT10: staged [N,4];  JOINT: world [N,3] */
+    const REAL* data0; /* DISTORT10: staged [N,4];  JOINT: world [N,3];  ANGLE_BA: obs [V,N,2] */
     const REAL* data1; /* JOINT: obs [V,N,2]                           */
     const REAL* w;     /* [V,N] or NULL                                */
 } FN(problem);
@@ -107,9 +107,161 @@ static inline void FN(transform)(const REAL Rm[9], const REAL t[3], const REAL X
     if (Xp[2] == R(0.0)) Xp[2] += R(1e-8);
 }
 
+/* sin(a)/a, (1 - cos a)/a^2 and their derivatives as the reference's custom autograd Functions compute them:
+ * utils/func_sin_x_on_x.py:5-43 (Taylor below 0.01, backward = x * (cos x / x^2 - sin x / x^3) with that
+ * function's own Taylor branch below 0.01, :45-75) and utils/func_one_minus_cos_x_on_x_squared.py:6-58
+ * (Taylor below 0.05, backward = (1/x) (sin x / x - 2 result), 1/x := 0 at x == 0). */
+static void FN(sinc_terms)(REAL a, REAL* s, REAL* oc, REAL* ds, REAL* doc) {
+    const REAL a2 = a * a;
+    REAL k;
+    if (R(fabs((double)a)) < R(0.01)) {
+        const REAL a4 = a2 * a2, a6 = a4 * a2;
+        *s = R(1.0) - a2 / R(6.0) + a4 / R(120.0) - a6 / R(5040.0);
+        k = R(-1.0) / R(3.0) + a2 / R(30.0) - a4 / R(840.0) + a6 / R(45360.0);
+    } else {
+        const REAL sn = R(sin((double)a)), cs = R(cos((double)a));
+        *s = sn / a;
+        k = cs / a2 - sn / (a * a2);
+    }
+    *ds = a * k;
+    if (R(fabs((double)a)) < R(0.05)) {
+        const REAL a4 = a2 * a2, a6 = a4 * a2;
+        *oc = R(0.5) - a2 / R(24.0) + a4 / R(720.0) - a6 / R(40320.0);
+    } else {
+        *oc = (R(1.0) - R(cos((double)a))) / a2;
+    }
+    const REAL rec = (a == R(0.0)) ? R(0.0) : R(1.0) / a;
+    *doc = rec * (*s - R(2.0) * *oc);
+}
+
+/* The entry script's objective, networks/calibration_network.py:58-67, and its gradient (reverse mode written
+ * out by hand; matches torch.autograd of the reference functions to 1e-15 relative in float64, including the
+ * zero sub-gradients autograd uses for |x| at 0, vector_norm at 0 and the clamp in the normalisation).
+ * x = (f, cx, cy | X[N][3] | t[V-1][3] | w[V-1][3]); obs [V,N,2]; vis [V,N] or NULL. */
+static REAL FN(angle_ba)(const FN(problem)* p, const REAL* x, REAL* g) {
+    const int N = p->N, V = p->V, n = p->n;
+    const REAL EPS = R(2.220446049250313e-16); /* projective_plane_angle_distance.py:48,51 */
+    const REAL* X = x + 3;
+    const REAL* t = X + 3 * N;
+    const REAL* w = t + 3 * (V - 1);
+    /* geometry/homogeneous_projection.py:37: f' = elu(f) + 1 */
+    const REAL fp = x[0] > R(0.0) ? x[0] + R(1.0) : R(exp((double)x[0]));
+    const REAL dfp = x[0] > R(0.0) ? R(1.0) : R(exp((double)x[0]));
+    /* calibration_pinhole_camera_model.py:98-104: one scale for points and translations */
+    REAL ps = 0, cs = 0;
+    for (int i = 0; i < 3 * N; ++i) ps += R(fabs((double)X[i]));
+    for (int i = 0; i < 3 * (V - 1); ++i) cs += R(fabs((double)t[i]));
+    ps /= R(3 * N);
+    cs /= R(3 * (V - 1));
+    const REAL sig = (ps * R(N) + cs * R(V)) / R(N + V);
+    REAL gsig_num = 0; /* sum gXs . Xs + sum gts . ts */
+    REAL cost = 0;
+    if (g) for (int j = 0; j < n; ++j) g[j] = 0;
+    REAL* gX = g ? g + 3 : NULL;           /* accumulates d/dXs first */
+    REAL* gt = g ? gX + 3 * N : NULL;      /* d/dts */
+    REAL* gw = g ? gt + 3 * (V - 1) : NULL;
+    for (int m = 0; m < V; ++m) {
+        REAL om[3] = {0, 0, 0}, ts[3] = {0, 0, 0}, ang = 0, c = 1, sn = 0, s = 1, oc = R(0.5), ds = 0, doc = 0;
+        if (m > 0) {
+            for (int k = 0; k < 3; ++k) { om[k] = w[3 * (m - 1) + k]; ts[k] = t[3 * (m - 1) + k] / sig; }
+            ang = R(sqrt((double)(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]))); /* axis_angle_rotation.py:37 */
+            c = R(cos((double)ang));
+            sn = R(sin((double)ang));
+            FN(sinc_terms)(ang, &s, &oc, &ds, &doc);
+        }
+        for (int j = 0; j < N; ++j) {
+            const REAL xs[3] = {X[3 * j] / sig, X[3 * j + 1] / sig, X[3 * j + 2] / sig};
+            REAL P[3], cr[3] = {0, 0, 0}, dot = 0;
+            if (m == 0) {
+                P[0] = xs[0]; P[1] = xs[1]; P[2] = xs[2];
+            } else { /* axis_angle_rotation.py:38-48, then + translation (calibration_pinhole_camera_model.py:110) */
+                dot = xs[0] * om[0] + xs[1] * om[1] + xs[2] * om[2];
+                cr[0] = om[1] * xs[2] - om[2] * xs[1];
+                cr[1] = om[2] * xs[0] - om[0] * xs[2];
+                cr[2] = om[0] * xs[1] - om[1] * xs[0];
+                for (int k = 0; k < 3; ++k) P[k] = xs[k] * c + oc * dot * om[k] + cr[k] * s + ts[k];
+            }
+            const REAL* ob = p->data0 + 2 * ((size_t)m * N + j);
+            const REAL vis = p->w ? p->w[(size_t)m * N + j] : R(1.0);
+            const REAL h[3] = {ob[0] - x[1], ob[1] - x[2], fp}; /* homogeneous_projection.py:38-44 */
+            REAL nh = R(sqrt((double)(h[0] * h[0] + h[1] * h[1] + h[2] * h[2])));
+            REAL nP = R(sqrt((double)(P[0] * P[0] + P[1] * P[1] + P[2] * P[2])));
+            if (nh < EPS) nh = EPS;
+            if (nP < EPS) nP = EPS;
+            REAL a[3], b[3], sv[3], dv[3];
+            for (int k = 0; k < 3; ++k) {
+                a[k] = h[k] / nh; b[k] = P[k] / nP;
+                sv[k] = a[k] + b[k]; dv[k] = a[k] - b[k];
+            }
+            const REAL S = R(sqrt((double)(sv[0] * sv[0] + sv[1] * sv[1] + sv[2] * sv[2])));
+            const REAL D = R(sqrt((double)(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2])));
+            cost += R(2.0) * R(atan2((double)D, (double)S)) * vis; /* projective_plane_angle_distance.py:53-60 */
+            if (!g) continue;
+            const REAL den = S * S + D * D;
+            const REAL gD = R(2.0) * vis * S / den, gS = R(-2.0) * vis * D / den;
+            REAL ga[3], gb[3], gaa = 0, gbb = 0;
+            for (int k = 0; k < 3; ++k) {
+                const REAL uD = (D != R(0.0)) ? dv[k] / D : R(0.0);
+                const REAL uS = (S != R(0.0)) ? sv[k] / S : R(0.0);
+                ga[k] = gD * uD + gS * uS;
+                gb[k] = gS * uS - gD * uD;
+                gaa += ga[k] * a[k];
+                gbb += gb[k] * b[k];
+            }
+            REAL gh[3], gP[3];
+            for (int k = 0; k < 3; ++k) {
+                gh[k] = (ga[k] - a[k] * gaa) / nh;
+                gP[k] = (gb[k] - b[k] * gbb) / nP;
+            }
+            g[1] -= gh[0];
+            g[2] -= gh[1];
+            g[0] += gh[2] * dfp;
+            REAL gxs[3];
+            if (m == 0) {
+                gxs[0] = gP[0]; gxs[1] = gP[1]; gxs[2] = gP[2];
+            } else {
+                const REAL wg = om[0] * gP[0] + om[1] * gP[1] + om[2] * gP[2];
+                const REAL xg = xs[0] * gP[0] + xs[1] * gP[1] + xs[2] * gP[2];
+                const REAL crg = cr[0] * gP[0] + cr[1] * gP[1] + cr[2] * gP[2];
+                const REAL gxo[3] = {gP[1] * om[2] - gP[2] * om[1], gP[2] * om[0] - gP[0] * om[2],
+                                     gP[0] * om[1] - gP[1] * om[0]};                       /* gP x w */
+                const REAL xxg[3] = {xs[1] * gP[2] - xs[2] * gP[1], xs[2] * gP[0] - xs[0] * gP[2],
+                                     xs[0] * gP[1] - xs[1] * gP[0]};                       /* Xs x gP */
+                const REAL gang = -sn * xg + doc * dot * wg + ds * crg;
+                for (int k = 0; k < 3; ++k) {
+                    gxs[k] = c * gP[k] + oc * wg * om[k] + s * gxo[k];
+                    REAL gwk = oc * (dot * gP[k] + wg * xs[k]) + s * xxg[k];
+                    if (ang != R(0.0)) gwk += gang * om[k] / ang;
+                    gw[3 * (m - 1) + k] += gwk;
+                    gt[3 * (m - 1) + k] += gP[k];
+                    gsig_num += gP[k] * ts[k];
+                }
+            }
+            for (int k = 0; k < 3; ++k) {
+                gX[3 * j + k] += gxs[k];
+                gsig_num += gxs[k] * xs[k];
+            }
+        }
+    }
+    if (g) {
+        const REAL gsig = -gsig_num / sig;
+        const REAL cX = gsig / R(3 * (N + V)), cT = gsig * R(V) / R(3 * (V - 1) * (N + V));
+        for (int i = 0; i < 3 * N; ++i) {
+            const REAL sg = X[i] > R(0.0) ? R(1.0) : (X[i] < R(0.0) ? R(-1.0) : R(0.0));
+            gX[i] = gX[i] / sig + cX * sg;
+        }
+        for (int i = 0; i < 3 * (V - 1); ++i) {
+            const REAL sg = t[i] > R(0.0) ? R(1.0) : (t[i] < R(0.0) ? R(-1.0) : R(0.0));
+            gt[i] = gt[i] / sig + cT * sg;
+        }
+    }
+    return cost;
+}
+
 /* cost and gradient of one problem.  g may be NULL (cost only). */
 static REAL FN(objective)(const FN(problem)* p, const REAL* x, REAL* g) {
     const int n = p->n;
+    if (p->model == DAVO_MODEL_ANGLE_BA) return FN(angle_ba)(p, x, g);
     /* Sums over matches.  The reference sums with ATen's vectorised cascade kernels (torch.sum and the
      * sum_to_size reductions of autograd's broadcast backward: SIMD lanes x 4 interleaved accumulators, then a
      * tree over the partial sums), NOT one running scalar sum.  In float32 that difference is visible at
@@ -415,6 +567,7 @@ static void FN(bind)(FN(problem)* p, const davo_problem_desc* d, const REAL* dat
     p->w = (d->has_weights && w) ? w + (size_t)b * d->V * d->N : NULL;
     if (d->model == DAVO_MODEL_DISTORT10) p->data0 = data0 + (size_t)b * d->N * 4;
     else if (d->model == DAVO_MODEL_DISTANCE) p->data0 = data0 + (size_t)b * d->n;
+    else if (d->model == DAVO_MODEL_ANGLE_BA) p->data0 = data0 + (size_t)b * d->V * d->N * 2;
     else if (d->model == DAVO_MODEL_JOINT) {
         p->data0 = data0 + (size_t)b * d->N * 3;
         p->data1 = data1 + (size_t)b * d->V * d->N * 2;
@@ -427,6 +580,8 @@ static int FN(check_desc)(const davo_problem_desc* d) {
     if (d->model == DAVO_MODEL_DISTORT10 && (d->n != 10 || d->V != 1)) return DAVO_ERR_BAD_SHAPE;
     if (d->model == DAVO_MODEL_JOINT && (d->V < 1 || d->n != 10 + 6 * d->V)) return DAVO_ERR_BAD_SHAPE;
     if (d->model == DAVO_MODEL_ROSENBROCK && d->n != 2) return DAVO_ERR_BAD_SHAPE;
+    if (d->model == DAVO_MODEL_ANGLE_BA && (d->V < 2 || d->N < 1 || d->n != 3 + 3 * d->N + 6 * (d->V - 1)))
+        return DAVO_ERR_BAD_SHAPE;
     return DAVO_OK;
 }
 

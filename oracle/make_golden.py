@@ -53,6 +53,20 @@ SOLVE_CASES = {
                        "float64", dict(error_threshold=1e-10, iterations=1000)),
     "solve_cfg4_f32": ("make_distort10", dict(B=384, N=256, seed=0xB204, ill_conditioned=True, pathological=0.02),
                        "float32", dict(error_threshold=1e-5, iterations=1000)),
+    # the entry script's bundle-adjustment objective (M=4 views, N=8 points, n=45).  The
+    # error is a sum of angles (not squares): BFGS crawls along its kinks for ~900 iterations and single
+    # trajectories are chaotic even in float64, so the tight gate is a run capped at 30 accepted steps and the
+    # full-length runs are compared at population level against the reference's own band.
+    "solve_ba_f64_30steps": ("make_angle_ba", dict(B=64, N=8, V=4, seed=0xB205), "float64",
+                             dict(error_threshold=1e-7, iterations=30)),
+    "solve_ba_f32_30steps": ("make_angle_ba", dict(B=64, N=8, V=4, seed=0xB205), "float32",
+                             dict(error_threshold=1e-7, iterations=30)),
+    "solve_ba_f64": ("make_angle_ba", dict(B=256, N=8, V=4, seed=0xB205), "float64",
+                     dict(error_threshold=1e-7, iterations=1000)),
+    "solve_ba_f32": ("make_angle_ba", dict(B=256, N=8, V=4, seed=0xB205), "float32",
+                     dict(error_threshold=1e-4, iterations=1000)),
+    "solve_ba_small_f64": ("make_angle_ba", dict(B=32, N=5, V=2, seed=0xB206), "float64",
+                           dict(error_threshold=1e-7, iterations=40)),
 }
 
 
@@ -76,10 +90,22 @@ def gen_solve(name):
     # The reference's own reproducibility band: the same problems with the order of
     # the matches permuted, i.e. nothing but a different floating-point summation order.
     perm = np.random.default_rng(0x5EED).permutation(batch.N)
-    pb = syn.CalibrationBatch(batch.model, batch.points_3d[:, perm],
-                              batch.obs[:, perm] if batch.model == "distort10" else batch.obs[:, :, perm],
-                              batch.pose, batch.x0, batch.truth, batch.views)
-    rp = rh.reference_solve(rh.make_objective(pb, getattr(torch, dt)), torch.as_tensor(batch.x0), **skw)
+    if batch.model == "angle_ba":
+        # the world points are parameters here: permute them in the observations AND in the parameter vector,
+        # and undo the permutation on the result
+        cols = np.arange(batch.n)
+        cols[3:3 + 3 * batch.N] = 3 + (3 * perm[:, None] + np.arange(3)[None, :]).reshape(-1)
+        pb = syn.CalibrationBatch(batch.model, None, batch.obs[:, :, perm], None, batch.x0[:, cols],
+                                  batch.truth[:, cols], batch.views, batch.weights[:, :, perm])
+        rp = rh.reference_solve(rh.make_objective(pb, getattr(torch, dt)), torch.as_tensor(pb.x0), **skw)
+        back = np.empty_like(cols)
+        back[cols] = np.arange(batch.n)
+        rp["x"] = rp["x"][:, back]
+    else:
+        pb = syn.CalibrationBatch(batch.model, batch.points_3d[:, perm],
+                                  batch.obs[:, perm] if batch.model == "distort10" else batch.obs[:, :, perm],
+                                  batch.pose, batch.x0, batch.truth, batch.views)
+        rp = rh.reference_solve(rh.make_objective(pb, getattr(torch, dt)), torch.as_tensor(batch.x0), **skw)
     print(f"  {name}: self-consistency under a permutation of the matches: identical steps "
           f"{(rp['iters'] == r['iters']).mean():.4f}, identical reason {(rp['reason'] == r['reason']).mean():.4f}",
           flush=True)
@@ -112,6 +138,33 @@ def gen_camera_model():
     _save("camera_model", points_3d=pts, params16=th, u=u, v=v, u32=u32, v32=v32, J_autograd=J,
           d10_points=b.points_3d, d10_obs=b.obs, d10_pose=b.pose, d10_x=x, d10_cost=f, d10_grad=g,
           joint_points=j.points_3d, joint_obs=j.obs, joint_x=xj, joint_cost=fj, joint_grad=gj)
+
+
+def gen_angle_ba():
+    """Cost, autograd gradient and line search of the entry script's objective (networks/calibration_network.py:
+    58-67) from the reference's own functions, at several (views, points) shapes; rows 1-4 of each case exercise
+    the Taylor branches of sin(x)/x and (1-cos x)/x^2, the negative-f branch of elu and a zero rotation."""
+    rng = np.random.default_rng(15)
+    out = {}
+    for tag, (V, N) in (("a", (4, 8)), ("b", (2, 5)), ("c", (3, 11)), ("d", (6, 7))):
+        b = syn.make_angle_ba(12, N, V, seed=40 + V, dtype=np.float64)
+        x = b.x0.copy()
+        x[1, -3 * (V - 1):] *= 0.1
+        x[2, -3 * (V - 1):] *= 1e-3
+        x[3, 0] = -0.7
+        x[4, -3 * (V - 1):] = 0.0
+        obj = rh.make_objective(b)
+        fix = obj.check_against_unbatched_reference(torch.tensor(x))
+        assert fix <= 1e-12, fix  # the keepdim fix changes nothing for a single problem
+        f, g = rh.reference_cost_grad(obj, torch.tensor(x))
+        b32 = b.astype(np.float32)
+        f32, g32 = rh.reference_cost_grad(rh.make_objective(b32, torch.float32), torch.tensor(x.astype(np.float32)))
+        d = -g * rng.choice([1e-3, 1e-2, 0.1], size=(12, 1))
+        a, p, _, _ = rh.reference_line_search(obj, torch.tensor(x), torch.tensor(d), strong=True)
+        out.update({f"{tag}_obs": b.obs, f"{tag}_vis": b.weights, f"{tag}_x": x, f"{tag}_cost": f, f"{tag}_grad": g,
+                    f"{tag}_cost32": f32, f"{tag}_grad32": g32, f"{tag}_d": d, f"{tag}_alpha": a, f"{tag}_probes": p,
+                    f"{tag}_unbatched_diff": np.float64(fix)})
+    _save("angle_ba", **out)
 
 
 def gen_bfgs_update():
@@ -204,7 +257,7 @@ def main():
     ap.add_argument("--only", nargs="*", default=None)
     args = ap.parse_args()
     small = {"camera_model": gen_camera_model, "bfgs_update": gen_bfgs_update, "line_search": gen_line_search,
-             "analytic_solves": gen_analytic_solves}
+             "analytic_solves": gen_analytic_solves, "angle_ba": gen_angle_ba}
     names = args.only or (list(small) + list(SOLVE_CASES))
     for name in names:
         print(name, flush=True)

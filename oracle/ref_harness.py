@@ -76,6 +76,59 @@ class JointObjective:
         return self.lsq.find_error(self.lsq.find_residuals(est, self.obs[m]))
 
 
+class AngleBAObjective:
+    """The entry script's objective, networks/calibration_network.py:58-67, composed from the reference's own
+    unpack_calibration_parameters (camera_model/calibration_pinhole_camera_model.py:33-75),
+    pixel_coordinates_to_homogeneous (geometry/homogeneous_projection.py:21-44), rotate_vector_axis_angle
+    (geometry/axis_angle_rotation.py:25-54) and projective_plane_angle_distance
+    (geometry/projective_plane_angle_distance.py:20-64).
+
+    get_camera_relative_points (calibration_pinhole_camera_model.py:78-117) crashes on batched input at HEAD
+    (the scale is reduced to shape (B,) and divided into (B,M-1,1,3)); `relative_points` below is
+    that function with keepdim=True in the three means and nothing else changed, and
+    `check_against_unbatched_reference` verifies it against the UNMODIFIED function problem by problem."""
+
+    def __init__(self, obs, visibility, views, points):
+        if not available():
+            raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
+        _import_reference()
+        from deep_attention_visual_odometry import camera_model as cm, geometry as geo
+        self.cm, self.geo = cm, geo
+        self.obs, self.vis, self.M, self.N = obs, visibility, int(views), int(points)
+
+    def relative_points(self, world_points, camera_translations, camera_rotations):
+        num_points = world_points.size(-2)
+        num_views = camera_translations.size(-3) + 1
+        points_scale = world_points.abs().mean(dim=(-1, -2, -3), keepdim=True)
+        camera_scale = camera_translations.abs().mean(dim=(-1, -2, -3), keepdim=True)
+        overall_scale = (points_scale * num_points + camera_scale * num_views) / (num_points + num_views)
+        camera_translations = camera_translations / overall_scale
+        world_points = world_points / overall_scale
+        rel = self.geo.rotate_vector_axis_angle(world_points, camera_rotations) + camera_translations
+        return torch.concatenate([world_points, rel], dim=-3)
+
+    def error(self, params, obs, vis, relative_points=None):
+        cp = self.cm.unpack_calibration_parameters(params, self.M, self.N)
+        homogeneous = self.geo.pixel_coordinates_to_homogeneous(obs, cp.intrinsics)
+        rel = (relative_points or self.relative_points)(world_points=cp.world_points,
+                                                        camera_translations=cp.camera_translations,
+                                                        camera_rotations=cp.camera_rotations)
+        distance = self.geo.projective_plane_angle_distance(homogeneous, rel)
+        return (distance * vis).sum(dim=(-1, -2))
+
+    def __call__(self, params, mask):
+        m = mask.reshape(-1)
+        return self.error(params, self.obs[m], self.vis[m])
+
+    def check_against_unbatched_reference(self, params):
+        """max |error(batched, keepdim fix) - error(one problem at a time, unmodified reference function)|."""
+        with torch.no_grad():
+            batched = self.error(params, self.obs, self.vis)
+            single = torch.stack([self.error(params[b], self.obs[b], self.vis[b], self.cm.get_camera_relative_points)
+                                  for b in range(params.shape[0])])
+        return float((batched - single).abs().max())
+
+
 def _norm(x):
     return torch.linalg.vector_norm(x, dim=-1, keepdim=True)
 
@@ -99,6 +152,8 @@ def make_objective(batch_or_name, dtype=torch.float64):
     t = lambda a: torch.as_tensor(np.asarray(a), dtype=dtype)
     if b.model == "distort10":
         return Distort10Objective(t(b.points_3d), t(b.obs), t(b.pose))
+    if b.model == "angle_ba":
+        return AngleBAObjective(t(b.obs), t(b.weights), b.views, b.N)
     return JointObjective(t(b.points_3d), t(b.obs), b.views)
 
 

@@ -49,6 +49,12 @@ def test_validation_status_codes_without_gpu():
     assert L.davo_solve_calibration(ctypes.byref(d), *([None] * 12)) == -2
     d = _lib.make_desc(4, 8, 2, 20, "joint", torch.float32)  # n must be 10 + 6 V = 22
     assert L.davo_eval_cost_grad(ctypes.byref(d), *([None] * 7)) == -2
+    d = _lib.make_desc(4, 8, 4, 44, "angle_ba", torch.float32)  # n must be 3 + 3 N + 6 (V - 1) = 45
+    assert L.davo_solve_calibration(ctypes.byref(d), *([None] * 12)) == -2
+    d = _lib.make_desc(4, 8, 1, 27, "angle_ba", torch.float32)  # a single view has no relative pose
+    assert L.davo_eval_cost_grad(ctypes.byref(d), *([None] * 7)) == -2
+    d = _lib.make_desc(4, 8, 4, 45, "angle_ba", torch.float32)
+    assert L.davo_solve_calibration(ctypes.byref(d), *([None] * 12)) == -1  # NULL pointers
     d = _lib.make_desc(4, 8, 1, 10, 99, torch.float32)  # unknown model
     assert L.davo_solve_calibration(ctypes.byref(d), *([None] * 12)) == -3
     d = _lib.make_desc(4, 0, 1, 17, "sphere", torch.float32)  # analytic n > 16 slots
@@ -87,3 +93,21 @@ def test_solver_constructor_matches_reference_defaults():
     s = davo_b200.BFGSSolver(error_threshold=1e-7, training_error_threshold=1e-3, training_iterations=5)
     assert s.training_error_threshold == 1e-3 and s.training_iterations == 5
     assert s.training  # nn.Module default, as in the reference
+
+
+def test_calibration_network_mirrors_reference_module_layout():
+    """networks/calibration_network.py:26-52: same sub-module names and shapes (a reference checkpoint loads),
+    same solver thresholds; unpack_calibration_parameters slices like calibration_pinhole_camera_model.py:33-75."""
+    net = davo_b200.CalibrationNetwork(4, 8)
+    assert net.num_views == 4 and net.num_points == 8
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert shapes["initial_estimator.0.weight"] == (256, 64)
+    assert shapes["initial_estimator.3.weight"] == (256, 256)
+    assert shapes["initial_estimator.6.weight"] == (45, 256)
+    assert net.solver.error_threshold == 1e-7 and net.solver.training_error_threshold == 1e-3
+    x = torch.arange(2 * 45, dtype=torch.float32).reshape(2, 45)
+    intr, pts, tr, rot = davo_b200.unpack_calibration_parameters(x, 4, 8)
+    assert intr.shape == (2, 1, 1, 3) and pts.shape == (2, 1, 8, 3) and tr.shape == (2, 3, 1, 3) and rot.shape == (2, 3, 1, 3)
+    assert pts[1, 0, 7, 2] == 45 + 26 and tr[0, 0, 0, 0] == 27 and rot[0, 2, 0, 2] == 44
+    with pytest.raises(ValueError):
+        davo_b200.unpack_calibration_parameters(x, 4, 7)

@@ -115,9 +115,33 @@ def test_analytic_solves(name):
     assert (r32["iters"] == g[f"{name}_float32_iters"]).mean() >= 0.6  # fp32 trajectories are chaotic near the floor
 
 
+BA_SHAPES = {"a": (4, 8), "b": (2, 5), "c": (3, 11), "d": (6, 7)}
+
+
+@pytest.mark.parametrize("tag", sorted(BA_SHAPES))
+def test_angle_ba_cost_gradient_line_search_match_reference(tag):
+    """The entry script's objective (networks/calibration_network.py:58-67): the oracle's hand-written reverse
+    mode against torch.autograd of the reference's own functions, and the line search on it."""
+    g = load_golden("angle_ba")
+    V, N = BA_SHAPES[tag]
+    assert g[f"{tag}_unbatched_diff"] <= 1e-12  # batched (keepdim fix) == unmodified reference, one problem at a time
+    x, obs, vis = g[f"{tag}_x"], g[f"{tag}_obs"], g[f"{tag}_vis"]
+    f, gr = c_oracle.eval_cost_grad("angle_ba", x, obs, None, vis, N=N, V=V)
+    assert np.allclose(f, g[f"{tag}_cost"], rtol=1e-13)
+    assert np.all(np.abs(gr - g[f"{tag}_grad"]) <= 1e-12 * np.abs(g[f"{tag}_grad"]).max(axis=1, keepdims=True))
+    f32, gr32 = c_oracle.eval_cost_grad("angle_ba", x.astype(np.float32), obs.astype(np.float32), None,
+                                        vis.astype(np.float32), N=N, V=V)
+    assert np.allclose(f32, g[f"{tag}_cost32"], rtol=2e-6)
+    assert np.all(np.abs(gr32 - g[f"{tag}_grad32"]) <= 2e-5 * np.abs(g[f"{tag}_grad32"]).max(axis=1, keepdims=True))
+    a, probes = c_oracle.line_search("angle_ba", x, g[f"{tag}_d"], f, gr, obs, None, vis, N=N, V=V, strong=True)
+    assert np.array_equal(probes, g[f"{tag}_probes"])
+    assert np.allclose(a, g[f"{tag}_alpha"], rtol=1e-12)
+
+
 F64_CASES = ["solve_cfg2_f64", "solve_cfg2_pose_f64", "solve_cfg3_small_f64", "solve_cfg3_f64", "solve_cfg4_f64",
-             "solve_cfg2_noisy_f64"]
-F32_CASES = ["solve_cfg2_f32", "solve_cfg2_f32_thr1e-7", "solve_cfg3_f32", "solve_cfg4_f32"]
+             "solve_cfg2_noisy_f64", "solve_ba_f64_30steps", "solve_ba_small_f64", "solve_ba_f64"]
+F32_CASES = ["solve_cfg2_f32", "solve_cfg2_f32_thr1e-7", "solve_cfg3_f32", "solve_cfg4_f32", "solve_ba_f32_30steps",
+             "solve_ba_f32"]
 
 
 @pytest.mark.parametrize("name", F64_CASES + F32_CASES)
@@ -134,6 +158,9 @@ def test_solve_matches_reference_within_its_own_band(name):
     print(name, "oracle vs reference", summary(m))
     print(name, "reference vs itself", summary(band))
     assert_within_band(m, band)
-    if name in ("solve_cfg2_f64", "solve_cfg2_pose_f64", "solve_cfg3_small_f64"):
+    if name in ("solve_cfg2_f64", "solve_cfg2_pose_f64", "solve_cfg3_small_f64", "solve_ba_f64_30steps",
+                "solve_ba_small_f64"):
         assert m["steps_equal"] == 1.0 and m["fevals_equal"] == 1.0 and m["reason_equal"] == 1.0
-        assert m["dtheta_max"] <= 1e-6
+        # the 2-view, 5-point bundle adjustment has nearly flat directions: the reference reproduces itself to
+        # 9e-6 there under a permutation of the points; the north_star tolerance is 1e-4
+        assert m["dtheta_max"] <= (1e-4 if name == "solve_ba_small_f64" else 1e-6)
