@@ -29,6 +29,8 @@ struct AngleBAObjective {
     T* contrib;  // [V*N][kRow]
     T* rot;      // [V-1][8]: cos a, sin a, sin a / a, (1 - cos a)/a^2, d(sin a / a)/da, d((1 - cos a)/a^2)/da, 1/a | 0
     int lane;
+    int m0, j0;  // (view, point) of this lane's first pair
+    T wX, wT;    // d sigma / d|X_jk| = 1 / (3 (N + V)),  d sigma / d|t_mk| = V / (3 (V - 1) (N + V))
 
     __host__ __device__ static size_t slab_bytes(int N, int V, bool) {
         size_t b = sizeof(T) * ((size_t)V * N * (3 + kRow) + 8 * (size_t)(V > 1 ? V - 1 : 1));
@@ -40,6 +42,11 @@ struct AngleBAObjective {
         vis = obs + (size_t)p.V * p.N * 2;
         contrib = vis + (size_t)p.V * p.N;
         rot = contrib + (size_t)p.V * p.N * kRow;
+        m0 = lane / p.N;
+        j0 = lane - m0 * p.N;
+        // sigma = (N mean|X| + V mean|t|) / (N + V) with mean|X| over 3N entries, mean|t| over 3(V-1) entries
+        wX = T(1) / T(3 * (p.N + p.V));
+        wT = T(p.V) / T(3 * (p.V - 1) * (p.N + p.V));
     }
 
     __device__ __forceinline__ void init() {}
@@ -65,13 +72,13 @@ struct AngleBAObjective {
         const T* t = X + 3 * N;
         const T* w = t + 3 * (V - 1);
         const T kEps = T(2.220446049250313e-16);  // projective_plane_angle_distance.py:48,51
-        // one scale for points and translations, calibration_pinhole_camera_model.py:98-104
-        T ps = T(0), cs = T(0);
-        for (int i = lane; i < 3 * N; i += 32) ps += fabs(X[i]);
-        for (int i = lane; i < 3 * (V - 1); i += 32) cs += fabs(t[i]);
-        ps = warp_allreduce(ps) / T(3 * N);
-        cs = warp_allreduce(cs) / T(3 * (V - 1));
-        const T sig = (ps * T(N) + cs * T(V)) / T(N + V);
+        const int tb = 3 + 3 * N, wb = tb + 3 * (V - 1);   // first translation / rotation parameter
+        // one scale for points and translations, calibration_pinhole_camera_model.py:98-104 (X and t are
+        // contiguous in the parameter vector: one weighted sum of absolute values)
+        T part = T(0);
+        for (int i = 3 + lane; i < wb; i += 32) part = fma_t(fabs(th[i]), i < tb ? wX : wT, part);
+        const T sig = warp_allreduce(part);
+        const T isig = T(1) / sig;  // the divisions by sigma, |h|, |P| below are multiplications by one reciprocal each
         __syncwarp();  // the previous evaluation's readers of rot / contrib are done
         if (lane < V - 1) {
             const T w0 = w[3 * lane], w1 = w[3 * lane + 1], w2 = w[3 * lane + 2];
@@ -108,8 +115,12 @@ struct AngleBAObjective {
         const T dfp = f > T(0) ? T(1) : ef;
         T cost = T(0), gf = T(0), gcx = T(0), gcy = T(0);
         for (int i = lane; i < MN; i += 32) {
-            const int m = i / N, j = i - m * N;
-            const T x0 = X[3 * j] / sig, x1 = X[3 * j + 1] / sig, x2 = X[3 * j + 2] / sig;
+            int m = m0, j = j0;
+            if (i != lane) {
+                m = i / N;
+                j = i - m * N;
+            }
+            const T x0 = X[3 * j] * isig, x1 = X[3 * j + 1] * isig, x2 = X[3 * j + 2] * isig;
             T P0 = x0, P1 = x1, P2 = x2;
             T o0 = T(0), o1 = T(0), o2 = T(0), c0 = T(0), c1 = T(0), c2 = T(0), dot = T(0);
             T cn = T(1), sn = T(0), s = T(1), oc = T(0.5), ds = T(0), doc = T(0), rec = T(0);
@@ -118,7 +129,7 @@ struct AngleBAObjective {
                 const T* r = rot + 8 * (m - 1);
                 cn = r[0]; sn = r[1]; s = r[2]; oc = r[3]; ds = r[4]; doc = r[5]; rec = r[6];
                 o0 = w[3 * (m - 1)]; o1 = w[3 * (m - 1) + 1]; o2 = w[3 * (m - 1) + 2];
-                ts0 = t[3 * (m - 1)] / sig; ts1 = t[3 * (m - 1) + 1] / sig; ts2 = t[3 * (m - 1) + 2] / sig;
+                ts0 = t[3 * (m - 1)] * isig; ts1 = t[3 * (m - 1) + 1] * isig; ts2 = t[3 * (m - 1) + 2] * isig;
                 dot = x0 * o0 + x1 * o1 + x2 * o2;
                 c0 = o1 * x2 - o2 * x1; c1 = o2 * x0 - o0 * x2; c2 = o0 * x1 - o1 * x0;
                 const T od = oc * dot;
@@ -131,24 +142,24 @@ struct AngleBAObjective {
             T nP = sqrt_rn(P0 * P0 + P1 * P1 + P2 * P2);
             nh = nh < kEps ? kEps : nh;
             nP = nP < kEps ? kEps : nP;
-            const T a0 = h0 / nh, a1 = h1 / nh, a2 = h2 / nh;
-            const T b0 = P0 / nP, b1 = P1 / nP, b2 = P2 / nP;
+            const T inh = T(1) / nh, inP = T(1) / nP;
+            const T a0 = h0 * inh, a1 = h1 * inh, a2 = h2 * inh;
+            const T b0 = P0 * inP, b1 = P1 * inP, b2 = P2 * inP;
             const T s0 = a0 + b0, s1 = a1 + b1, s2 = a2 + b2;
             const T d0 = a0 - b0, d1 = a1 - b1, d2 = a2 - b2;
             const T S = sqrt_rn(s0 * s0 + s1 * s1 + s2 * s2);
             const T D = sqrt_rn(d0 * d0 + d1 * d1 + d2 * d2);
             const T vz = vis[i];
             cost += T(2) * atan2(D, S) * vz;  // projective_plane_angle_distance.py:53-60
-            const T den = S * S + D * D;
-            const T gD = T(2) * vz * S / den, gS = T(-2) * vz * D / den;
-            const T iD = (D != T(0)) ? gD / D : T(0);   // vector_norm backward: zero sub-gradient at 0
-            const T iS = (S != T(0)) ? gS / S : T(0);
+            const T w2 = T(2) * vz / (S * S + D * D);   // atan2 backward: d/dD = S / (S^2 + D^2), d/dS = -D / (S^2 + D^2)
+            const T iD = (D != T(0)) ? w2 * S / D : T(0);   // vector_norm backward: zero sub-gradient at 0
+            const T iS = (S != T(0)) ? -w2 * D / S : T(0);
             const T ga0 = iD * d0 + iS * s0, ga1 = iD * d1 + iS * s1, ga2 = iD * d2 + iS * s2;
             const T gb0 = iS * s0 - iD * d0, gb1 = iS * s1 - iD * d1, gb2 = iS * s2 - iD * d2;
             const T gaa = ga0 * a0 + ga1 * a1 + ga2 * a2;
             const T gbb = gb0 * b0 + gb1 * b1 + gb2 * b2;
-            const T gh0 = (ga0 - a0 * gaa) / nh, gh1 = (ga1 - a1 * gaa) / nh, gh2 = (ga2 - a2 * gaa) / nh;
-            const T g0 = (gb0 - b0 * gbb) / nP, g1 = (gb1 - b1 * gbb) / nP, g2 = (gb2 - b2 * gbb) / nP;
+            const T gh0 = (ga0 - a0 * gaa) * inh, gh1 = (ga1 - a1 * gaa) * inh, gh2 = (ga2 - a2 * gaa) * inh;
+            const T g0 = (gb0 - b0 * gbb) * inP, g1 = (gb1 - b1 * gbb) * inP, g2 = (gb2 - b2 * gbb) * inP;
             gcx -= gh0;
             gcy -= gh1;
             gf += gh2;
@@ -176,32 +187,42 @@ struct AngleBAObjective {
         gcx = warp_allreduce(gcx);
         gcy = warp_allreduce(gcy);
         __syncwarp();
-        // gather: the lane that owns parameter c adds the rows that touch c
-        const int tb = 3 + 3 * N, wb = tb + 3 * (V - 1);
+        // gather: the lane that owns parameter c (c = lane, lane + 32) adds the rows that touch c
+        T own[2];
         T dsig = T(0);  // sum d/dXs . Xs + sum d/dts . ts  (-> d/d sigma)
-        for (int c = lane; c < n; c += 32) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
             T a = T(0);
             if (c < 3) {
                 a = (c == 0) ? gf * dfp : (c == 1 ? gcx : gcy);
             } else if (c < tb) {
                 const int j = (c - 3) / 3, k = (c - 3) - 3 * j;
-                for (int m = 0; m < V; ++m) a += contrib[kRow * (m * N + j) + k];
-                dsig += a * (X[c - 3] / sig);
-            } else {
-                const int q = (c < wb) ? c - tb : c - wb;
-                const int m = q / 3 + 1, k = q - 3 * (m - 1) + ((c < wb) ? 3 : 6);
-                for (int j = 0; j < N; ++j) a += contrib[kRow * (m * N + j) + k];
-                if (c < wb) dsig += a * (t[q] / sig);
+                const T* q = contrib + kRow * j + k;
+                for (int m = 0; m < V; ++m, q += kRow * N) a += *q;
+                dsig = fma_t(a, th[c] * isig, dsig);
+            } else if (c < n) {
+                const int r = (c < wb) ? c - tb : c - wb;
+                const int m = r / 3 + 1, k = r - 3 * (m - 1) + ((c < wb) ? 3 : 6);
+                const T* q = contrib + kRow * (m * N) + k;
+                for (int j = 0; j < N; ++j, q += kRow) a += *q;
+                if (c < wb) dsig = fma_t(a, th[c] * isig, dsig);
             }
-            gout[c] = a;
+            own[h] = a;
         }
-        const T gsig = -warp_allreduce(dsig) / sig;
-        const T cX = gsig / T(3 * (N + V)), cT = gsig * T(V) / T(3 * (V - 1) * (N + V));
-        for (int c = lane; c < wb; c += 32) {  // every lane revisits exactly the entries it wrote above
-            if (c < 3) continue;
-            const T v = th[c];
-            const T sg = v > T(0) ? T(1) : (v < T(0) ? T(-1) : T(0));  // d|x|/dx with sign(0) = 0
-            gout[c] = gout[c] / sig + (c < tb ? cX : cT) * sg;
+        const T gsig = -warp_allreduce(dsig) * isig;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = lane + 32 * h;
+            if (c < n) {
+                T a = own[h];
+                if (c >= 3 && c < wb) {
+                    const T v = th[c];
+                    const T sg = v > T(0) ? T(1) : (v < T(0) ? T(-1) : T(0));  // d|x|/dx with sign(0) = 0
+                    a = fma_t(a, isig, gsig * (c < tb ? wX : wT) * sg);
+                }
+                gout[c] = a;
+            }
         }
         __syncwarp();
         return cost;

@@ -4,8 +4,8 @@
 //   autograd_solvers/line_search/wolfe_conditions.py:23-253,
 // but with the n-vectors and the n x n inverse Hessian in this warp's SHARED memory (n = 34 needs
 // 4.6 KB for H; registers could not hold two rows per lane next to the match arithmetic).  Lane L
-// works on components L and L + 32.  H rows are padded to n + 1 words, so a lane walking its row and
-// 32 lanes reading one column are both bank-conflict free.  Scalars are replicated and bitwise
+// works on components L and L + 32.  H rows are padded to an odd stride (n | 1 words), so a lane walking
+// its row and 32 lanes reading one column are both bank-conflict free.  Scalars are replicated and bitwise
 // identical across lanes; reductions over components are per-lane partial sums + a 5-step butterfly.
 #pragma once
 #include "davo_common.cuh"
@@ -14,6 +14,10 @@
 namespace davo {
 
 constexpr int kWideMax = 64;
+
+#ifndef DAVO_WIDE_FAITHFUL
+#define DAVO_WIDE_FAITHFUL 0  // 1: op-by-op rounding of the BFGS update (A/B builds)
+#endif
 
 template <typename T>
 __device__ __forceinline__ T warp_allreduce(T v) {
@@ -38,14 +42,16 @@ struct WideWorkspace {
         x = p; g = x + kWideMax; gprev = g + kWideMax; d = gprev + kWideMax; s = d + kWideMax;
         y = s + kWideMax; yH = y + kWideMax; Hy = yH + kWideMax; xt = Hy + kWideMax; gt = xt + kWideMax;
         H = gt + kWideMax;
-        ld = n + 1;
+        ld = n | 1;  // odd row stride: a lane walking its row and 32 lanes reading one column are both conflict free
     }
 };
 
+// a . b over the n <= 64 components: lane L contributes components L and L + 32 (no loop: the kernel is bound
+// by instruction issue, and a loop with a run-time trip count costs more than the two guarded products).
 template <typename T>
 __device__ __forceinline__ T wide_dot(const T* a, const T* b, int n, int lane) {
-    T acc = T(0);
-    for (int c = lane; c < n; c += 32) acc = add_rn(acc, mul_rn(a[c], b[c]));
+    T acc = (lane < n) ? mul_rn(a[lane], b[lane]) : T(0);
+    if (lane + 32 < n) acc = add_rn(acc, mul_rn(a[lane + 32], b[lane + 32]));
     return warp_allreduce(acc);
 }
 
@@ -69,7 +75,8 @@ __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const 
             if (zooming) cand = mul_rn(T(0.5), add_rn(lo, hi));                      // :128-131
         }
         __syncwarp();
-        for (int c = lane; c < n; c += 32) xt[c] = add_rn(x[c], mul_rn(cand, d[c]));  // :139
+        if (lane < n) xt[lane] = add_rn(x[lane], mul_rn(cand, d[lane]));             // :139
+        if (lane + 32 < n) xt[lane + 32] = add_rn(x[lane + 32], mul_rn(cand, d[lane + 32]));
         __syncwarp();
         cand_f = obj.eval(xt, gt);
         const T dphi = wide_dot(d, gt, n, lane);                                    // :141
@@ -125,9 +132,11 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
         }
         __syncwarp();
         if (k == 0) {
-            for (int c = lane; c < n; c += 32) d[c] = mul_rn(T(-1), g[c]);  // :152-155
+            if (lane < n) d[lane] = mul_rn(T(-1), g[lane]);                 // :152-155
+            if (lane + 32 < n) d[lane + 32] = mul_rn(T(-1), g[lane + 32]);
         } else {
-            for (int c = lane; c < n; c += 32) y[c] = sub_rn(g[c], gprev[c]);  // :157
+            if (lane < n) y[lane] = sub_rn(g[lane], gprev[lane]);              // :157
+            if (lane + 32 < n) y[lane + 32] = sub_rn(g[lane + 32], gprev[lane + 32]);
             __syncwarp();
             const T sy = wide_dot(s, y, n, lane);
             if (k == 1) {                                                      // :159-167, :217-233
@@ -141,6 +150,8 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             }
             T rho = div_rn(T(1), sy);                                          // func_inverse_curvature.py:8-11
             if (sy <= T(0)) rho = T(0);
+#if DAVO_WIDE_FAITHFUL
+            // Literal restatement: every product rounded before the next operation, one element at a time.
             for (int c = lane; c < n; c += 32) {
                 T a = T(0), bsum = T(0);
                 for (int i = 0; i < n; ++i) {
@@ -169,17 +180,89 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
                 for (int j = 0; j < n; ++j) a = fma_t(H[c * ld + j], g[j], a);
                 d[c] = mul_rn(T(-1), a);
             }
+#else
+            // H' = H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the right (:263-303),
+            // same operands as the literal form, products allowed to fuse.  Lane L owns columns/rows L and L+32.
+            // Sweep 1 walks H once and forms, per owned index c, (y^T H)_c from COLUMN c (never replaced by
+            // (H y)^T: H is symmetric only up to rounding, see solver_warp.cuh), (H y)_c and (H g)_c from ROW c:
+            // six independent FMA chains per lane, no cross-lane traffic.  ld is odd, so both walks are bank
+            // conflict free.  The new direction -H' g (:173-176) follows from
+            //   H' g = H g + (s rho) [ (1+q) s.g - (y^T H).g ] - (H y) rho s.g
+            // without reading H' back.  Sweep 2 rewrites the owned columns.
+            const int c0 = lane, c1 = lane + 32;
+            const bool in0 = c0 < n, in1 = c1 < n;
+            const int k0 = in0 ? c0 : 0, k1 = in1 ? c1 : 0;    // safe indices for lanes beyond n (results discarded)
+            T yH0 = T(0), yH1 = T(0), Hy0 = T(0), Hy1 = T(0), Hg0 = T(0), Hg1 = T(0);
+            {
+                const T* col0 = H + k0;
+                const T* col1 = H + k1;
+                const T* row0 = H + k0 * ld;
+                const T* row1 = H + k1 * ld;
+#pragma unroll 4
+                for (int i = 0; i < n; ++i) {
+                    const T yi = y[i], gi = g[i];
+                    const T hc0 = *col0, hc1 = *col1, hr0 = row0[i], hr1 = row1[i];
+                    col0 += ld;
+                    col1 += ld;
+                    yH0 = fma_t(yi, hc0, yH0); yH1 = fma_t(yi, hc1, yH1);
+                    Hy0 = fma_t(hr0, yi, Hy0); Hy1 = fma_t(hr1, yi, Hy1);
+                    Hg0 = fma_t(hr0, gi, Hg0); Hg1 = fma_t(hr1, gi, Hg1);
+                }
+            }
+            const T y0 = in0 ? y[k0] : T(0), y1 = in1 ? y[k1] : T(0);
+            const T s0 = in0 ? s[k0] : T(0), s1 = in1 ? s[k1] : T(0);
+            const T gg0 = in0 ? g[k0] : T(0), gg1 = in1 ? g[k1] : T(0);
+            if (!in0) { yH0 = T(0); Hy0 = T(0); Hg0 = T(0); }
+            if (!in1) { yH1 = T(0); Hy1 = T(0); Hg1 = T(0); }
+            const T q = mul_rn(warp_allreduce(fma_t(yH0, y0, yH1 * y1)), rho);  // y^T H y / (y^T s), :271-274
+            const T sg = warp_allreduce(fma_t(s0, gg0, s1 * gg1));
+            const T yhg = warp_allreduce(fma_t(yH0, gg0, yH1 * gg1));
+            const T onepq = add_rn(T(1), q);
+            const T dir = fma_t(onepq, sg, -yhg);
+            __syncwarp();  // sweep 1's reads of y are done before it is overwritten with the row constants
+            if (in0) {
+                d[c0] = mul_rn(T(-1), fma_t(-Hy0 * rho, sg, fma_t(s0 * rho, dir, Hg0)));
+                y[c0] = mul_rn(s0, rho);        // row constants of sweep 2: s_i rho ...
+                Hy[c0] = -mul_rn(Hy0, rho);     // ... and -(H y)_i rho
+            }
+            if (in1) {
+                d[c1] = mul_rn(T(-1), fma_t(-Hy1 * rho, sg, fma_t(s1 * rho, dir, Hg1)));
+                y[c1] = mul_rn(s1, rho);
+                Hy[c1] = -mul_rn(Hy1, rho);
+            }
+            __syncwarp();
+            {
+                const T inner0 = fma_t(s0, onepq, -yH0), inner1 = fma_t(s1, onepq, -yH1);  // s_j (1+q) - (y^T H)_j
+                T* col0 = H + k0;
+                T* col1 = H + k1;
+                if (!in1) col1 = ws.xt + lane;  // a lane without a second column updates a scratch word instead of predicating
+                const int st0 = in0 ? ld : 0, st1 = in1 ? ld : 0;
+                if (!in0) col0 = ws.xt + 32 + lane;
+#pragma unroll 4
+                for (int i = 0; i < n; ++i) {
+                    const T sri = y[i], nhr = Hy[i];
+                    *col0 = fma_t(nhr, s0, fma_t(sri, inner0, *col0));
+                    *col1 = fma_t(nhr, s1, fma_t(sri, inner1, *col1));
+                    col0 += st0;
+                    col1 += st1;
+                }
+            }
+#endif
         }
         __syncwarp();
         const LineSearchResult<T> ls = line_search_wide(obj, p, x, d, f, g, ws.xt, gt, lane);  // :181-190
         fevals += ls.probes;
         ++iters;
         T nrm2 = T(0);
-        for (int c = lane; c < n; c += 32) {                                   // :191-199
-            const T sc = mul_rn(ls.alpha, d[c]);
-            s[c] = sc;
-            x[c] = add_rn(x[c], sc);
-            nrm2 = add_rn(nrm2, mul_rn(sc, sc));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                                          // :191-199
+            const int c = lane + 32 * h;
+            if (c < n) {
+                const T sc = mul_rn(ls.alpha, d[c]);
+                s[c] = sc;
+                x[c] = add_rn(x[c], sc);
+                nrm2 = add_rn(nrm2, mul_rn(sc, sc));
+            }
         }
         const T nrm = sqrt_rn(warp_allreduce(nrm2));
         have_fg = same_bits(ls.alpha, ls.last_cand);
