@@ -7,6 +7,7 @@
 #include "davo_common.cuh"
 #include "objectives.cuh"
 #include "solver_warp.cuh"
+#include "solver_half.cuh"
 #include "launch.h"
 
 namespace davo {
@@ -114,8 +115,45 @@ static int launch_warp_kernel(const SolveParams<T>& p, cudaStream_t stream) {
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
 }
 
+#ifndef DAVO_HALF_SOLVE
+#define DAVO_HALF_SOLVE 1  // 0: A/B builds solve DISTORT10 with one warp per problem
+#endif
+
+// DISTORT10 solve, unweighted: two problems per warp (solver_half.cuh).
+template <typename T>
+static int launch_half_kernel(const SolveParams<T>& p, cudaStream_t stream) {
+    auto kernel = (p.N % 32 == 0) ? half_problem_kernel<T, false> : half_problem_kernel<T, true>;
+    const size_t smem = half_stride<T>(p.N) * 2 * kWarpsPerCta;
+    int dev = 0, sms = 0, max_optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DAVO_ERR_CUDA;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerCta * 32, smem) != cudaSuccess ||
+        per_sm < 1)
+        return DAVO_ERR_CUDA;
+    long long grid = (long long)per_sm * sms;
+    const long long need = ((long long)p.B + 2 * kWarpsPerCta - 1) / (2 * kWarpsPerCta);
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    if (cudaMemsetAsync(p.queue, 0, sizeof(unsigned), stream) != cudaSuccess) return DAVO_ERR_CUDA;
+    kernel<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+}
+
 template <typename T, Mode kMode>
 static int dispatch_model(const SolveParams<T>& p, cudaStream_t stream) {
+#if DAVO_HALF_SOLVE
+    if (kMode == Mode::kSolve && p.model == DAVO_MODEL_DISTORT10 && !p.has_w && p.n == 10) {
+        const int st = launch_half_kernel<T>(p, stream);
+        if (st != DAVO_ERR_UNSUPPORTED) return st;  // N too large for two slabs per warp: one warp per problem
+    }
+#endif
     if (p.model == DAVO_MODEL_DISTORT10)
         return p.has_w ? launch_warp_kernel<T, 10, Distort10Objective<T, true>, kMode>(p, stream)
                        : launch_warp_kernel<T, 10, Distort10Objective<T, false>, kMode>(p, stream);
