@@ -15,6 +15,7 @@
 
 namespace davo {
 
+constexpr int kReasonHandoff = 4;  // internal value of reason_out between the two launches of a DISTORT10 solve
 constexpr int kSlots = 16;  // distributed-vector width of the warp-per-problem solver (n <= 16)
 constexpr unsigned kFull = 0xffffffffu;
 // Per-warp shared-memory scratch of the warp-per-problem solver: 32 rows x kRedPitch words.  Cross-lane sums go
@@ -168,6 +169,10 @@ struct SolveParams {
     int32_t* fevals_out;
     int32_t* reason_out;
     unsigned* queue;  // atomic work-queue counter in the caller's workspace
+    // Straggler hand-off (solver_half.cuh): a problem whose reference-equivalent evaluation count passes eval_cap
+    // at the top of an outer iteration is abandoned with reason_out = kReasonHandoff, and a second launch
+    // (Mode::kResolve, one warp per problem) solves exactly those problems again from x0.  0 = no cap.
+    int eval_cap;
     // line-search-only entry point
     const T* dir;
     const T* base_cost;

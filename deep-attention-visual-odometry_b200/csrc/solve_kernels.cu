@@ -29,7 +29,7 @@ __host__ __device__ inline size_t warp_smem_stride(int N, bool has_w) {
     return (b + 127) & ~size_t(127);
 }
 
-enum class Mode { kSolve, kLineSearch, kEval };
+enum class Mode { kSolve, kLineSearch, kEval, kResolve };  // kResolve: solve the problems a first launch handed off
 
 template <typename T, int NP, typename Obj, Mode kMode>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, DAVO_MIN_BLOCKS) warp_problem_kernel(const SolveParams<T> p) {
@@ -55,6 +55,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DAVO_MIN_BLOCKS) warp_probl
     const bool own = c < n;
     const unsigned total_warps = gridDim.x * kWarpsPerCta;
     unsigned b_static = blockIdx.x * kWarpsPerCta + warp;
+    if (kMode == Mode::kResolve) {
+        // Second launch of a DISTORT10 solve: warps pull 32 problem indices at a time, look at their reason flags
+        // and solve the ones the first launch handed off (normally none: one coalesced read per 32 problems).
+        for (;;) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(p.queue, 32u);
+            base = __shfl_sync(kFull, base, 0);
+            if (base >= (unsigned)p.B) break;
+            const unsigned idx = base + lane;
+            unsigned todo = __ballot_sync(kFull, idx < (unsigned)p.B && p.reason_out[idx] == kReasonHandoff);
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                obj.bind((int)(base + j));
+                solve_one_warp<T, NP, Obj>(obj, p, (int)(base + j), xt_line, bc_line, scratch, lane);
+            }
+        }
+        return;
+    }
     for (;;) {
         unsigned b = 0;
         if (kMode == Mode::kSolve) {  // iteration counts vary 10x between problems: dynamic queue
@@ -105,11 +124,12 @@ static int launch_warp_kernel(const SolveParams<T>& p, cudaStream_t stream) {
         per_sm < 1)
         return DAVO_ERR_CUDA;
     long long grid = (long long)per_sm * sms;
-    const long long need = ((long long)p.B + kWarpsPerCta - 1) / kWarpsPerCta;
+    const long long need = (kMode == Mode::kResolve) ? ((long long)p.B + 32 * kWarpsPerCta - 1) / (32 * kWarpsPerCta)
+                                                      : ((long long)p.B + kWarpsPerCta - 1) / kWarpsPerCta;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (kMode == Mode::kSolve && cudaMemsetAsync(p.queue, 0, sizeof(unsigned), stream) != cudaSuccess)
-        return DAVO_ERR_CUDA;
+        return DAVO_ERR_CUDA;  // (kResolve: the first launch has zeroed both counters)
     kernel<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(p);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
@@ -119,9 +139,16 @@ static int launch_warp_kernel(const SolveParams<T>& p, cudaStream_t stream) {
 #define DAVO_HALF_SOLVE 1  // 0: A/B builds solve DISTORT10 with one warp per problem
 #endif
 
-// DISTORT10 solve, unweighted: two problems per warp (solver_half.cuh).
+#ifndef DAVO_EVAL_CAP
+#define DAVO_EVAL_CAP 4096  // reference-equivalent evaluations after which the two-per-warp launch hands a problem off
+#endif
+
+// DISTORT10 solve, unweighted: two problems per warp (solver_half.cuh), then one warp per problem for the
+// stragglers the first launch handed off.
 template <typename T>
-static int launch_half_kernel(const SolveParams<T>& p, cudaStream_t stream) {
+static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
+    SolveParams<T> p = p_in;
+    p.eval_cap = p.reason_out ? DAVO_EVAL_CAP : 0;  // the hand-off flag lives in reason_out
     auto kernel = (p.N % 32 == 0) ? half_problem_kernel<T, false> : half_problem_kernel<T, true>;
     const size_t smem = half_stride<T>(p.N) * 2 * kWarpsPerCta;
     int dev = 0, sms = 0, max_optin = 0;
@@ -140,10 +167,18 @@ static int launch_half_kernel(const SolveParams<T>& p, cudaStream_t stream) {
     const long long need = ((long long)p.B + 2 * kWarpsPerCta - 1) / (2 * kWarpsPerCta);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    if (cudaMemsetAsync(p.queue, 0, sizeof(unsigned), stream) != cudaSuccess) return DAVO_ERR_CUDA;
+    // fewer than ~3 problems per resident half: the batch cannot keep two problems per warp busy and a problem's
+    // latency matters more than the instruction count (the streamed host-input path solves 8K-problem chunks)
+    if ((long long)p.B < 3 * 2 * kWarpsPerCta * (long long)per_sm * sms) return DAVO_ERR_UNSUPPORTED;
+    if (cudaMemsetAsync(p.queue, 0, 2 * sizeof(unsigned), stream) != cudaSuccess) return DAVO_ERR_CUDA;
     kernel<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(p);
     count_launch();
-    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+    if (cudaGetLastError() != cudaSuccess) return DAVO_ERR_CUDA;
+    if (p.eval_cap == 0) return DAVO_OK;
+    SolveParams<T> p2 = p_in;
+    p2.queue = p.queue + 1;
+    p2.eval_cap = 0;
+    return launch_warp_kernel<T, 10, Distort10Objective<T, false>, Mode::kResolve>(p2, stream);
 }
 
 template <typename T, Mode kMode>

@@ -308,6 +308,14 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
                 if (!(f > p.thr)) {                                           // :143 (strict >; NaN retires)
                     reason = (f <= p.thr) ? DAVO_REASON_THRESHOLD : DAVO_REASON_NAN;
                     finished = true;
+                } else if (p.eval_cap > 0 && fevals > p.eval_cap) {
+                    // A straggler (a problem that bisects every line search down to lo == hi for hundreds of
+                    // iterations): its latency, not the batch's throughput, would set the launch time.  Hand it
+                    // to the second launch, which gives it a whole warp.  The test depends on the problem's own
+                    // trajectory only, so which problems are handed off is deterministic.
+                    if (l == 0) p.reason_out[b] = kReasonHandoff;
+                    have = false;
+                    mode = kEvalFinal;
                 } else {
                     if (k == 0) {
                         d = mul_rn(T(-1), g);                                 // :152-155
