@@ -8,6 +8,7 @@
 #include "objectives.cuh"
 #include "solver_warp.cuh"
 #include "solver_half.cuh"
+#include "solver_cta.cuh"
 #include "launch.h"
 
 namespace davo {
@@ -139,6 +140,12 @@ static int launch_warp_kernel(const SolveParams<T>& p, cudaStream_t stream) {
 #define DAVO_HALF_SOLVE 1  // 0: A/B builds solve DISTORT10 with one warp per problem
 #endif
 
+template <typename T>
+static int launch_resolve_cta(const SolveParams<T>& p, cudaStream_t stream);
+
+#ifndef DAVO_RESOLVE_WARP
+#define DAVO_RESOLVE_WARP 0  // 1: A/B builds re-solve the stragglers one warp per problem
+#endif
 #ifndef DAVO_EVAL_CAP
 #define DAVO_EVAL_CAP 4096  // reference-equivalent evaluations after which the two-per-warp launch hands a problem off
 #endif
@@ -178,7 +185,81 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
     SolveParams<T> p2 = p_in;
     p2.queue = p.queue + 1;
     p2.eval_cap = 0;
+#if DAVO_RESOLVE_WARP
     return launch_warp_kernel<T, 10, Distort10Objective<T, false>, Mode::kResolve>(p2, stream);
+#else
+    return launch_resolve_cta<T>(p2, stream);
+#endif
+}
+
+// ---- second launch of a DISTORT10 solve: one CTA (4 warps) per handed-off problem ------------------------------
+constexpr int kResolveWarps = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(32 * kResolveWarps) resolve_cta_kernel(const SolveParams<T> p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using Obj = Distort10CtaObjective<T, kResolveWarps>;
+    const size_t data = Obj::data_bytes(p.N, 1, false);
+    CtaWorkspace<T> ws;
+    ws.carve(smem + data, p.n, kResolveWarps);
+    unsigned char* tail = smem + data + CtaWorkspace<T>::bytes(p.n, kResolveWarps);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+    volatile unsigned* slot = reinterpret_cast<volatile unsigned*>(tail + 16);  // [0] chunk base, [1] flag mask
+    Obj obj(p, smem, ws.red, bar);
+    obj.init();
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        // warp 0 pulls 32 problem indices and looks at their reason flags (normally none is set)
+        if (threadIdx.x < 32) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(p.queue, 32u);
+            base = __shfl_sync(kFull, base, 0);
+            const unsigned idx = base + lane;
+            const unsigned todo =
+                __ballot_sync(kFull, idx < (unsigned)p.B && p.reason_out[idx] == kReasonHandoff);
+            if (lane == 0) {
+                slot[0] = base;
+                slot[1] = todo;
+            }
+        }
+        __syncthreads();
+        const unsigned base = slot[0];
+        unsigned todo = slot[1];
+        __syncthreads();  // everyone has read the slots before warp 0 may rewrite them
+        if (base >= (unsigned)p.B) break;
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            obj.bind((int)(base + j));
+            solve_one_cta<T, kResolveWarps>(obj, p, (int)(base + j), ws);
+        }
+    }
+}
+
+template <typename T>
+static int launch_resolve_cta(const SolveParams<T>& p, cudaStream_t stream) {
+    using Obj = Distort10CtaObjective<T, kResolveWarps>;
+    auto kernel = resolve_cta_kernel<T>;
+    const size_t smem = Obj::data_bytes(p.N, 1, false) + CtaWorkspace<T>::bytes(p.n, kResolveWarps) + 32;
+    int dev = 0, sms = 0, max_optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return DAVO_ERR_CUDA;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * kResolveWarps, smem) != cudaSuccess ||
+        per_sm < 1)
+        return DAVO_ERR_CUDA;
+    long long grid = (long long)per_sm * sms;
+    const long long need = ((long long)p.B + 31) / 32;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kernel<<<(unsigned)grid, 32 * kResolveWarps, smem, stream>>>(p);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
 }
 
 template <typename T, Mode kMode>

@@ -193,6 +193,99 @@ struct JointCtaObjective {
     }
 };
 
+// The DISTORT10 objective (objectives.cuh) evaluated by a whole CTA: the second launch of a DISTORT10 solve gives
+// each straggler W warps, because there the latency of one evaluation — not the batch's throughput — sets the
+// launch time.  Thread t handles the match pair (t, t + 32 W) of every block of 64 W matches; the 11 sums are
+// reduced inside each warp (reduce-scatter) and across warps through `red` with one barrier.
+template <typename T, int W>
+struct Distort10CtaObjective {
+    using V4 = typename Vec4<T>::type;
+    using P = typename Vec2<T>::type;
+    const SolveParams<T>& p;
+    V4* matches;  // [N] {a, b, -u*, -v*} (observations negated once per problem)
+    T* red;       // [W][16]
+    uint64_t* bar;
+    unsigned parity;
+    int lane, warp, tid;
+
+    __host__ __device__ static size_t data_bytes(int N, int, bool) {
+        return (sizeof(V4) * (size_t)N + 127) & ~size_t(127);
+    }
+
+    __device__ Distort10CtaObjective(const SolveParams<T>& p_, unsigned char* slab, T* red_, uint64_t* bar_)
+        : p(p_), matches(reinterpret_cast<V4*>(slab)), red(red_), bar(bar_), parity(0) {
+        tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
+    }
+
+    __device__ __forceinline__ void init() {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ void bind(int b) {
+        fence_proxy_async();
+        __syncthreads();  // every warp is done with the previous problem's slab
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)(sizeof(V4) * (size_t)p.N);
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(matches, p.data0 + (size_t)b * p.N * 4, bytes, bar);
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        for (int i = tid; i < p.N; i += 32 * W) {
+            V4 m = matches[i];
+            m.z = -m.z;
+            m.w = -m.w;
+            matches[i] = m;
+        }
+        __syncthreads();
+    }
+
+    __device__ __forceinline__ T eval(const T* th, T* gout) {
+        Intrinsics<T> I;
+        I.load(th);
+        P acc2[kPairAcc];
+#pragma unroll
+        for (int k = 0; k < kPairAcc; ++k) acc2[k] = pk(T(0));
+        P gu, gv;
+        const int N = p.N;
+        for (int i = tid; i < N; i += 64 * W) {
+            const V4 m0 = matches[i];
+            const bool second_valid = i + 32 * W < N;
+            V4 m1;
+            m1.x = m1.y = m1.z = m1.w = T(0);
+            if (second_valid) m1 = matches[i + 32 * W];
+            P a, b, nus, nvs;
+            a.x = m0.x; a.y = m1.x; b.x = m0.y; b.y = m1.y;
+            nus.x = m0.z; nus.y = m1.z; nvs.x = m0.w; nvs.y = m1.w;
+            match_pair_cost_grad<T, false>(I, a, b, nus, nvs, pk(T(1)), second_valid, acc2, gu, gv);
+        }
+        T acc[kSlots];
+#pragma unroll
+        for (int k = 0; k < kPairAcc; ++k) acc[k] = acc2[k].x + acc2[k].y;
+#pragma unroll
+        for (int k = kPairAcc; k < kSlots; ++k) acc[k] = T(0);
+        fold_uv_terms(acc);
+        const T mine = reduce_scatter16<true>(acc, lane);
+        if (!(lane & 1)) red[warp * kSlots + (lane >> 1)] = mine;
+        __syncthreads();
+        T f = T(0);
+#pragma unroll
+        for (int w = 0; w < W; ++w) f += red[w * kSlots + 10];
+        if (tid < 10) {
+            T gsum = T(0);
+#pragma unroll
+            for (int w = 0; w < W; ++w) gsum += red[w * kSlots + tid];
+            gout[tid] = T(2) * gsum;  // least_squares_utils.py:43
+        }
+        __syncthreads();
+        return f;
+    }
+};
+
 // out[c] = scale * sum_j H[c][j] v[j].  n is small (34 at config 3), so a whole warp per row would idle
 // most lanes and pay a 5-step butterfly per row; instead FOUR threads share a row (j = q, q+4, ...) and
 // combine with two shuffles, i.e. 8 rows per warp and 32 rows per pass of a 4-warp CTA.
