@@ -175,7 +175,7 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     // fewer than ~3 problems per resident half: the batch cannot keep two problems per warp busy and a problem's
-    // latency matters more than the instruction count (the streamed host-input path solves 8K-problem chunks)
+    // latency matters more than the instruction count (the streamed host-input path solves 4K-problem chunks)
     if ((long long)p.B < 3 * 2 * kWarpsPerCta * (long long)per_sm * sms) return DAVO_ERR_UNSUPPORTED;
     if (cudaMemsetAsync(p.queue, 0, 2 * sizeof(unsigned), stream) != cudaSuccess) return DAVO_ERR_CUDA;
     kernel<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(p);

@@ -19,6 +19,13 @@
 #include "solver_warp.cuh"  // LineSearchResult, same_bits
 #include "solver_wide.cuh"  // warp_allreduce, wide_dot, kWideMax
 
+#ifndef DAVO_JOINT_PACKED
+// 1: evaluate the JOINT matches two per instruction (FFMA2).  Measured slower on config 3 (16K x 1024): 32.3 ms at 4
+// CTAs/SM (128 registers, spills), 35.7 ms at 5 CTAs/SM (96 registers, heavy spills) against 30.2 ms for the scalar
+// loop at 5 CTAs/SM: the 12 pose sums double the accumulator registers.  Kept for A/B builds.
+#define DAVO_JOINT_PACKED 0
+#endif
+
 namespace davo {
 
 template <typename T>
@@ -109,9 +116,18 @@ struct JointCtaObjective {
         const int N = p.N, V = p.V;
         Intrinsics<T> I;
         I.load(th);
+#if DAVO_JOINT_PACKED
+        // Two matches per instruction (FFMA2 / FMUL2 / FADD2, see objectives.cuh): the kernel is bound by
+        // instruction issue, not by the FMA pipe, so lane L works on the pair (i, i + 32) of every block of 64.
+        using P = V2;
+        P acc2[kPairAcc];
+#pragma unroll
+        for (int k = 0; k < kPairAcc; ++k) acc2[k] = pk(T(0));
+#else
         T acc[kSlots];
 #pragma unroll
         for (int k = 0; k < kSlots; ++k) acc[k] = T(0);
+#endif
         for (int v = warp; v < V; v += W) {
             const T* pose = th + 10 + 6 * v;
             // sin/cos of this view's three Euler angles: lanes 0..2 compute, everyone receives
@@ -129,6 +145,42 @@ struct JointCtaObjective {
             for (int k = 0; k < kSlots; ++k) part[k] = T(0);
             const V2* ob = reinterpret_cast<const V2*>(obs) + (size_t)v * N;
             const T* wv = wts + (size_t)v * N;
+#if DAVO_JOINT_PACKED
+            P part2[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) part2[k] = pk(T(0));
+            for (int i = lane; i < N; i += 64) {
+                const bool second_valid = i + 32 < N;
+                const int i1 = second_valid ? i + 32 : i;  // a missing second match re-reads the first; its residuals are zeroed
+                P X, Y, Z, nus, nvs, w2 = pk(T(1));
+                X.x = world[3 * i]; Y.x = world[3 * i + 1]; Z.x = world[3 * i + 2];
+                X.y = world[3 * i1]; Y.y = world[3 * i1 + 1]; Z.y = world[3 * i1 + 2];
+                const V2 o0 = ob[i], o1 = ob[i1];
+                nus.x = -o0.x; nus.y = -o1.x; nvs.x = -o0.y; nvs.y = -o1.y;
+                if (kWeighted) { w2.x = wv[i]; w2.y = second_valid ? wv[i1] : T(0); }
+                const P xp = pfma(X, pk(r00), pfma(Y, pk(r01), pfma(Z, pk(r02), pk(t0))));
+                const P yp = pfma(X, pk(r10), pfma(Y, pk(r11), pfma(Z, pk(r12), pk(t1))));
+                P zp = pfma(X, pk(r20), pfma(Y, pk(r21), pfma(Z, pk(r22), pk(t2))));
+                if (zp.x == T(0)) zp.x += T(1e-8);  // :57
+                if (zp.y == T(0)) zp.y += T(1e-8);
+                P iz;
+                iz.x = div_rn(T(1), zp.x);
+                iz.y = div_rn(T(1), zp.y);
+                const P a = pmul(xp, iz), b = pmul(yp, iz);
+                P gu, gv;
+                match_pair_cost_grad<T, kWeighted>(I, a, b, nus, nvs, w2, second_valid, acc2, gu, gv);
+                const P gA = pmul(gu, pk(I.fx));
+                const P gB = pfma(gu, pk(I.s), pmul(gv, pk(I.fy)));
+                const P gx = pmul(gA, iz), gy = pmul(gB, iz);
+                const P gz = pmul(pfma(gA, a, pmul(gB, b)), pmul(pk(T(-1)), iz));
+                part2[0] = pfma(gx, X, part2[0]); part2[1] = pfma(gx, Y, part2[1]); part2[2] = pfma(gx, Z, part2[2]);
+                part2[3] = pfma(gy, X, part2[3]); part2[4] = pfma(gy, Y, part2[4]); part2[5] = pfma(gy, Z, part2[5]);
+                part2[6] = pfma(gz, X, part2[6]); part2[7] = pfma(gz, Y, part2[7]); part2[8] = pfma(gz, Z, part2[8]);
+                part2[9] = padd(part2[9], gx); part2[10] = padd(part2[10], gy); part2[11] = padd(part2[11], gz);
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k) part[k] = part2[k].x + part2[k].y;
+#else
 #pragma unroll 2
             for (int i = lane; i < N; i += 32) {
                 const T X = world[3 * i], Y = world[3 * i + 1], Z = world[3 * i + 2];
@@ -150,6 +202,7 @@ struct JointCtaObjective {
                 part[6] = fma_t(gz, X, part[6]); part[7] = fma_t(gz, Y, part[7]); part[8] = fma_t(gz, Z, part[8]);
                 part[9] += gx; part[10] += gy; part[11] += gz;
             }
+#endif
             const T mine = reduce_scatter16<true>(part, lane);  // total of slot lane >> 1
             // every lane needs all of M for <dR/dr_k, M>_F: 12 broadcasts from the owning lanes
             const T m0 = shfl_idx(mine, 0), m1 = shfl_idx(mine, 2), m2 = shfl_idx(mine, 4), m3 = shfl_idx(mine, 6),
@@ -175,6 +228,13 @@ struct JointCtaObjective {
             }
             if (lane >= 18 && lane < 24 && !(lane & 1)) gout[10 + 6 * v + 3 + ((lane - 18) >> 1)] = T(2) * mine;  // d/dt
         }
+#if DAVO_JOINT_PACKED
+        T acc[kSlots];
+#pragma unroll
+        for (int k = 0; k < kPairAcc; ++k) acc[k] = acc2[k].x + acc2[k].y;
+#pragma unroll
+        for (int k = kPairAcc; k < kSlots; ++k) acc[k] = T(0);
+#endif
         fold_uv_terms(acc);
         const T mine = reduce_scatter16<true>(acc, lane);
         if (!(lane & 1)) red[warp * kSlots + (lane >> 1)] = mine;

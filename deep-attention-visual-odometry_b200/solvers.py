@@ -121,6 +121,19 @@ class BFGSSolver(Module):
                                   out=out)
         else:  # host-resident problem set: overlap the copies with staging + solve, chunk by chunk
             buf = self._solve_streamed(parameters.detach().reshape(obj.B, n), obj, error_threshold, iterations, out)
+        if out_dev.type == "cpu":
+            # host caller: every output goes device -> pinned host memory on the solve's stream, then ONE wait
+            # (six blocking copies would each pay a synchronisation)
+            wanted = (buf.x, buf.cost, buf.converged, buf.iterations, buf.evaluations, buf.reason) if return_info else (buf.x,)
+            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in wanted]
+            for h, t in zip(host, wanted):
+                h.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(obj.device).synchronize()
+            result = host[0].reshape(parameters.shape).to(parameters.dtype)
+            if not return_info:
+                return result
+            shaped = [h.reshape(batch_shape) for h in host[1:]]
+            return SolveInfo(result, shaped[0], shaped[1].bool(), shaped[2], shaped[3], shaped[4])
         result = buf.x.reshape(parameters.shape).to(device=out_dev, dtype=parameters.dtype)
         if not return_info:
             return result
@@ -129,18 +142,24 @@ class BFGSSolver(Module):
                          back(buf.evaluations), back(buf.reason))
 
     #: problems per chunk of the streamed (host-input) path; each chunk is one H2D copy + stage + solve
-    stream_chunk = 8192
+    stream_chunk = 4096
 
-    @staticmethod
-    def _chunk_spans(B: int, chunk: int):
-        """[lo, hi) spans of `chunk` problems; the last chunk is cut into 1/2, 1/4, 1/4 so that the compute
-        left over once the final copy has landed (the only part the copies cannot hide) is short."""
+    #: the last chunk is halved repeatedly down to this many problems
+    stream_tail = 1024
+
+    @classmethod
+    def _chunk_spans(cls, B: int, chunk: int):
+        """[lo, hi) spans of `chunk` problems; the last chunk is cut into 1/2, 1/4, ... down to `stream_tail`
+        problems so that the compute left over once the final copy has landed (the only part the copies cannot
+        hide) is short."""
         spans = [(lo, min(lo + chunk, B)) for lo in range(0, B, chunk)]
-        if len(spans) > 1 and spans[-1][1] - spans[-1][0] >= 1024:
+        if len(spans) > 1:
             lo, hi = spans.pop()
-            size = hi - lo
-            a, b = lo + size // 2, lo + size // 2 + size // 4
-            spans += [(lo, a), (a, b), (b, hi)]
+            while hi - lo >= 2 * max(1, cls.stream_tail):
+                mid = lo + (hi - lo) // 2
+                spans.append((lo, mid))
+                lo = mid
+            spans.append((lo, hi))
         return spans
 
     def _solve_streamed(self, x0_host: torch.Tensor, obj, error_threshold, iterations, out) -> "SolveBuffers":

@@ -489,7 +489,7 @@ def test_solve_full_size_properties():
 def test_stragglers_are_handed_off_and_solved():
     """Config 4 (ill-conditioned) at full size: problems that pass the evaluation cap of the two-per-warp launch are
     re-solved by the second launch; every row is written, no hand-off flag survives, and the population agrees with
-    the one-warp-per-problem kernel (which solves the same problems in 8K chunks through the streamed path)."""
+    the one-warp-per-problem kernel (which solves the same problems in 4K chunks through the streamed path)."""
     B = 65536
     batch = davo_b200.synthetic.make_distort10(B, 256, seed=0xB200, dtype=np.float32, ill_conditioned=True,
                                                pathological=0.02)
