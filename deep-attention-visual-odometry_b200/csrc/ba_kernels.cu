@@ -11,6 +11,8 @@ namespace davo {
 template <typename T, WMode kMode>
 static int launch_ba(const SolveParams<T>& p, cudaStream_t s) {
     if (p.V < 2 || p.N < 1 || p.n != 3 + 3 * p.N + 6 * (p.V - 1)) return DAVO_ERR_BAD_SHAPE;
+    // the entry script's configuration (4 views x 8 points, n = 45) has its own instantiation
+    if (p.V == 4 && p.N == 8) return launch_wide<T, AngleBAObjective<T, 4, 8>, kMode>(p, s);
     return launch_wide<T, AngleBAObjective<T>, kMode>(p, s);
 }
 

@@ -20,9 +20,12 @@
 
 namespace davo {
 
-template <typename T>
+// kV, kN > 0 fix the number of views / points at compile time (the entry script's configuration is 4 views x 8
+// points, camera_calibration_from_oracle_matches.py:34-35: loops unroll, index arithmetic folds); 0 = run time.
+template <typename T, int kV = 0, int kN = 0>
 struct AngleBAObjective {
     static constexpr int kRow = 9;  // odd pitch: consecutive rows start in different banks
+    static constexpr int kParams = (kV > 0 && kN > 0) ? 3 + 3 * kN + 6 * (kV - 1) : 0;  // compile-time n (0: run time)
     const SolveParams<T>& p;
     T* obs;      // [V*N][2]
     T* vis;      // [V*N]
@@ -67,7 +70,7 @@ struct AngleBAObjective {
 
     // th: parameters in shared memory; gout: gradient written to shared memory; returns the error.
     __device__ __forceinline__ T eval(const T* th, T* gout) {
-        const int N = p.N, V = p.V, MN = V * N, n = p.n;
+        const int N = kN > 0 ? kN : p.N, V = kV > 0 ? kV : p.V, MN = V * N, n = kParams > 0 ? kParams : p.n;
         const T* X = th + 3;
         const T* t = X + 3 * N;
         const T* w = t + 3 * (V - 1);
@@ -78,7 +81,7 @@ struct AngleBAObjective {
         T part = T(0);
         for (int i = 3 + lane; i < wb; i += 32) part = fma_t(fabs(th[i]), i < tb ? wX : wT, part);
         const T sig = warp_allreduce(part);
-        const T isig = T(1) / sig;  // the divisions by sigma, |h|, |P| below are multiplications by one reciprocal each
+        const T isig = rcp_rn(sig);  // the divisions by sigma, |h|, |P| below are multiplications by one reciprocal each
         __syncwarp();  // the previous evaluation's readers of rot / contrib are done
         if (lane < V - 1) {
             const T w0 = w[3 * lane], w1 = w[3 * lane + 1], w2 = w[3 * lane + 2];
@@ -87,21 +90,22 @@ struct AngleBAObjective {
             T sn, cn;
             sincos(a, &sn, &cn);
             T s, k, oc;
+            const T rec = (a == T(0)) ? T(0) : rcp_rn(a);   // 1/a once; the quotients below multiply by it
+            const T rec2 = rec * rec;
             if (fabs(a) < T(0.01)) {  // func_sin_x_on_x.py:10-22, :45-66
                 const T a4 = a2 * a2, a6 = a4 * a2;
-                s = T(1) - a2 / T(6) + a4 / T(120) - a6 / T(5040);
-                k = T(-1) / T(3) + a2 / T(30) - a4 / T(840) + a6 / T(45360);
+                s = T(1) - a2 * T(1.0 / 6.0) + a4 * T(1.0 / 120.0) - a6 * T(1.0 / 5040.0);
+                k = T(-1.0 / 3.0) + a2 * T(1.0 / 30.0) - a4 * T(1.0 / 840.0) + a6 * T(1.0 / 45360.0);
             } else {
-                s = sn / a;
-                k = cn / a2 - sn / (a * a2);
+                s = sn * rec;
+                k = (cn - sn * rec) * rec2;              // cos a / a^2 - sin a / a^3
             }
             if (fabs(a) < T(0.05)) {  // func_one_minus_cos_x_on_x_squared.py:12-28
                 const T a4 = a2 * a2, a6 = a4 * a2;
-                oc = T(0.5) - a2 / T(24) + a4 / T(720) - a6 / T(40320);
+                oc = T(0.5) - a2 * T(1.0 / 24.0) + a4 * T(1.0 / 720.0) - a6 * T(1.0 / 40320.0);
             } else {
-                oc = (T(1) - cn) / a2;
+                oc = (T(1) - cn) * rec2;
             }
-            const T rec = (a == T(0)) ? T(0) : T(1) / a;
             T* r = rot + 8 * lane;
             r[0] = cn; r[1] = sn; r[2] = s; r[3] = oc;
             r[4] = a * k;                   // SinXonX.backward
@@ -142,7 +146,7 @@ struct AngleBAObjective {
             T nP = sqrt_rn(P0 * P0 + P1 * P1 + P2 * P2);
             nh = nh < kEps ? kEps : nh;
             nP = nP < kEps ? kEps : nP;
-            const T inh = T(1) / nh, inP = T(1) / nP;
+            const T inh = rcp_rn(nh), inP = rcp_rn(nP);
             const T a0 = h0 * inh, a1 = h1 * inh, a2 = h2 * inh;
             const T b0 = P0 * inP, b1 = P1 * inP, b2 = P2 * inP;
             const T s0 = a0 + b0, s1 = a1 + b1, s2 = a2 + b2;
@@ -151,9 +155,9 @@ struct AngleBAObjective {
             const T D = sqrt_rn(d0 * d0 + d1 * d1 + d2 * d2);
             const T vz = vis[i];
             cost += T(2) * atan2(D, S) * vz;  // projective_plane_angle_distance.py:53-60
-            const T w2 = T(2) * vz / (S * S + D * D);   // atan2 backward: d/dD = S / (S^2 + D^2), d/dS = -D / (S^2 + D^2)
-            const T iD = (D != T(0)) ? w2 * S / D : T(0);   // vector_norm backward: zero sub-gradient at 0
-            const T iS = (S != T(0)) ? -w2 * D / S : T(0);
+            const T w2 = T(2) * vz * rcp_rn(S * S + D * D);  // atan2 backward: d/dD = S / (S^2 + D^2), d/dS = -D / (S^2 + D^2)
+            const T iD = (D != T(0)) ? w2 * S * rcp_rn(D) : T(0);   // vector_norm backward: zero sub-gradient at 0
+            const T iS = (S != T(0)) ? -w2 * D * rcp_rn(S) : T(0);
             const T ga0 = iD * d0 + iS * s0, ga1 = iD * d1 + iS * s1, ga2 = iD * d2 + iS * s2;
             const T gb0 = iS * s0 - iD * d0, gb1 = iS * s1 - iD * d1, gb2 = iS * s2 - iD * d2;
             const T gaa = ga0 * a0 + ga1 * a1 + ga2 * a2;

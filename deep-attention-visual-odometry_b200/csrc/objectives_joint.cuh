@@ -18,6 +18,7 @@ constexpr int kMaxViews = 9;  // n = 10 + 6 V <= 64
 
 template <typename T>
 struct JointObjective {
+    static constexpr int kParams = 0;  // n is a run-time value (wide_kernel.cuh)
     const SolveParams<T>& p;
     T* world;   // [N,3]
     T* obs;     // [V,N,2]

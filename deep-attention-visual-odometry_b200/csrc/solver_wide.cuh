@@ -61,7 +61,7 @@ template <typename T, typename Obj>
 __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const SolveParams<T>& p, const T* x,
                                                                 const T* d, T f0, const T* g, T* xt, T* gt,
                                                                 int lane) {
-    const int n = p.n;
+    const int n = Obj::kParams > 0 ? Obj::kParams : p.n;
     const T g0 = wide_dot(d, g, n, lane);       // :77
     bool widening = true, zooming = false;      // :80-82
     T lo = T(0), hi = T(0), cand = T(1);        // :97-108
@@ -106,7 +106,9 @@ __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const 
 template <typename T, typename Obj>
 __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p, int b, WideWorkspace<T>& ws,
                                                int lane) {
-    const int n = p.n, ld = ws.ld;
+    // an objective with a compile-time parameter count (Obj::kParams > 0) turns n and the row stride into
+    // constants: the sweeps over H below unroll with immediate offsets
+    const int n = Obj::kParams > 0 ? Obj::kParams : p.n, ld = Obj::kParams > 0 ? (Obj::kParams | 1) : ws.ld;
     T *x = ws.x, *g = ws.g, *gprev = ws.gprev, *gt = ws.gt;
     T *d = ws.d, *s = ws.s, *y = ws.y, *yH = ws.yH, *Hy = ws.Hy, *H = ws.H;
     __syncwarp();
@@ -198,7 +200,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
                 const T* col1 = H + k1;
                 const T* row0 = H + k0 * ld;
                 const T* row1 = H + k1 * ld;
-#pragma unroll 4
+#pragma unroll 9
                 for (int i = 0; i < n; ++i) {
                     const T yi = y[i], gi = g[i];
                     const T hc0 = *col0, hc1 = *col1, hr0 = row0[i], hr1 = row1[i];
@@ -238,7 +240,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
                 if (!in1) col1 = ws.xt + lane;  // a lane without a second column updates a scratch word instead of predicating
                 const int st0 = in0 ? ld : 0, st1 = in1 ? ld : 0;
                 if (!in0) col0 = ws.xt + 32 + lane;
-#pragma unroll 4
+#pragma unroll 9
                 for (int i = 0; i < n; ++i) {
                     const T sri = y[i], nhr = Hy[i];
                     *col0 = fma_t(nhr, s0, fma_t(sri, inner0, *col0));
