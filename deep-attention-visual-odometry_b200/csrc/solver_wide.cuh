@@ -120,168 +120,243 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
     for (int i = 0; i < n; ++i)
         for (int j = lane; j < n; j += 32) H[i * ld + j] = (i == j) ? T(1) : T(0);  // :112-117
     __syncwarp();
+    // The outer loop and the line search are ONE loop around ONE objective evaluation (as in solver_warp.cuh):
+    // the evaluator is most of this kernel's code and with call sites in the outer iteration, the line search and
+    // the final cost it was inlined three times (77 KB of SASS).  `mode` says what the evaluation about to run is for.
+    enum { kEvalOuter, kEvalProbe, kEvalFinal };
     T f = T(0);
-    int iters = 0, fevals = 0, reason = DAVO_REASON_CAP;
-    bool have_fg = false, have_f = false;
+    int iters = 0, fevals = 0, reason = DAVO_REASON_CAP, k = 0;
+    bool widening = false, zooming = false;                                    // wolfe_conditions.py:77-114
+    T lo = T(0), hi = T(0), cand = T(1), lo_f = T(0), hi_f = T(0), cand_f = T(0), f0 = T(0), g0 = T(0),
+      neg_c2_g0 = T(0);
+    int ls_i = 0;
+    int mode = (p.max_iters > 0) ? kEvalOuter : kEvalFinal;
 
-    for (int k = 0; k < p.max_iters; ++k) {  // :118
-        if (!have_fg) f = obj.eval(x, g);    // :128-135
-        ++fevals;
-        have_f = true;
-        if (!(f > p.thr)) {                  // :143
-            reason = (f <= p.thr) ? DAVO_REASON_THRESHOLD : DAVO_REASON_NAN;
-            break;
+    for (;;) {
+        const T* pt = x;
+        T* gdst = (mode == kEvalOuter) ? g : gt;
+        if (mode == kEvalProbe) {
+            __syncwarp();
+            if (lane < n) ws.xt[lane] = add_rn(x[lane], mul_rn(cand, d[lane]));  // wolfe_conditions.py:139
+            if (lane + 32 < n) ws.xt[lane + 32] = add_rn(x[lane + 32], mul_rn(cand, d[lane + 32]));
+            pt = ws.xt;
         }
         __syncwarp();
-        if (k == 0) {
-            if (lane < n) d[lane] = mul_rn(T(-1), g[lane]);                 // :152-155
-            if (lane + 32 < n) d[lane + 32] = mul_rn(T(-1), g[lane + 32]);
+        const T fe = obj.eval(pt, gdst);
+        if (mode == kEvalFinal) {                                              // networks/calibration_network.py:71
+            f = fe;
+            break;
+        }
+        bool start_iteration = false;
+        if (mode == kEvalOuter) {                                              // bfgs_solver.py:128-135
+            f = fe;
+            start_iteration = true;
         } else {
-            if (lane < n) y[lane] = sub_rn(g[lane], gprev[lane]);              // :157
-            if (lane + 32 < n) y[lane + 32] = sub_rn(g[lane + 32], gprev[lane + 32]);
-            __syncwarp();
-            const T sy = wide_dot(s, y, n, lane);
-            if (k == 1) {                                                      // :159-167, :217-233
-                T den = wide_dot(y, y, n, lane);
-                den = (den < T(1e-5)) ? T(1e-5) : den;
-                T sc = div_rn(sy, den);
-                sc = (sc < T(1e-4)) ? T(1e-4) : sc;
-                for (int i = 0; i < n; ++i)
-                    for (int j = lane; j < n; j += 32) H[i * ld + j] = mul_rn(sc, H[i * ld + j]);
-                __syncwarp();
+            // ---- one line-search probe has been evaluated: wolfe_conditions.py:143-237 ----
+            cand_f = fe;
+            ++fevals;
+            const T dphi = wide_dot(d, gt, n, lane);                            // :141
+            bool D = cand_f > add_rn(f0, mul_rn(mul_rn(p.c1, cand), g0));       // :146-150
+            if (zooming) D = D || (cand_f >= lo_f);                             // :151-153
+            if (widening && ls_i > 0) D = D || (cand_f >= hi_f);                // :154-157
+            const bool C = p.strong ? (fabs(dphi) <= neg_c2_g0) : (mul_rn(T(-1), dphi) <= neg_c2_g0);  // :160-169
+            const bool G = widening ? (dphi >= T(0)) : (mul_rn(dphi, sub_rn(hi, lo)) >= T(0));         // :174-180
+            if (zooming) {                                                      // :187-207
+                if (D) { hi = cand; hi_f = cand_f; }
+                else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; zooming = false; }
+                else { if (G) { hi = lo; hi_f = lo_f; } lo = cand; lo_f = cand_f; }
+            } else {                                                            // :216-237
+                if (D) { lo = hi; lo_f = hi_f; hi = cand; hi_f = cand_f; widening = false; zooming = true; }
+                else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; widening = false; }
+                else if (G) { lo = cand; lo_f = cand_f; widening = false; zooming = true; }
             }
-            T rho = div_rn(T(1), sy);                                          // func_inverse_curvature.py:8-11
-            if (sy <= T(0)) rho = T(0);
-#if DAVO_WIDE_FAITHFUL
-            // Literal restatement: every product rounded before the next operation, one element at a time.
-            for (int c = lane; c < n; c += 32) {
-                T a = T(0), bsum = T(0);
-                for (int i = 0; i < n; ++i) {
-                    a = add_rn(a, mul_rn(y[i], H[i * ld + c]));                // (y^T H)_c, :268-270
-                    bsum = add_rn(bsum, mul_rn(H[c * ld + i], y[i]));          // (H y)_c,   :293-295
-                }
-                yH[c] = a;
-                Hy[c] = bsum;
+            if (zooming && !(lo != hi)) zooming = false;                        // :236
+            ++ls_i;
+            if ((widening || zooming) && ls_i < p.max_ls) {                     // :116-121: another probe
+                if (widening) { hi = cand; hi_f = cand_f; cand = mul_rn(T(2), cand); }  // :125-127
+                if (zooming) cand = mul_rn(T(0.5), add_rn(lo, hi));                      // :128-131
+                continue;
             }
-            __syncwarp();
-            T qp = T(0);                                                       // :271-274
-            for (int c = lane; c < n; c += 32) qp = add_rn(qp, mul_rn(yH[c], mul_rn(y[c], rho)));
-            const T onepq = add_rn(T(1), warp_allreduce(qp));
-            for (int i = 0; i < n; ++i) {                                      // :278-303
-                const T sri = mul_rn(s[i], rho), Hyi = Hy[i];
-                for (int j = lane; j < n; j += 32) {
-                    const T sop = mul_rn(mul_rn(sri, s[j]), onepq);
-                    const T sgp = mul_rn(sri, yH[j]);
-                    const T gsp = mul_rn(Hyi, mul_rn(s[j], rho));
-                    H[i * ld + j] = sub_rn(sub_rn(add_rn(H[i * ld + j], sop), sgp), gsp);
-                }
-            }
-            __syncwarp();
-            for (int c = lane; c < n; c += 32) {                               // :173-176
-                T a = T(0);
-                for (int j = 0; j < n; ++j) a = fma_t(H[c * ld + j], g[j], a);
-                d[c] = mul_rn(T(-1), a);
-            }
-#else
-            // H' = H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the right (:263-303),
-            // same operands as the literal form, products allowed to fuse.  Lane L owns columns/rows L and L+32.
-            // Sweep 1 walks H once and forms, per owned index c, (y^T H)_c from COLUMN c (never replaced by
-            // (H y)^T: H is symmetric only up to rounding, see solver_warp.cuh), (H y)_c and (H g)_c from ROW c:
-            // six independent FMA chains per lane, no cross-lane traffic.  ld is odd, so both walks are bank
-            // conflict free.  The new direction -H' g (:173-176) follows from
-            //   H' g = H g + (s rho) [ (1+q) s.g - (y^T H).g ] - (H y) rho s.g
-            // without reading H' back.  Sweep 2 rewrites the owned columns.
-            const int c0 = lane, c1 = lane + 32;
-            const bool in0 = c0 < n, in1 = c1 < n;
-            const int k0 = in0 ? c0 : 0, k1 = in1 ? c1 : 0;    // safe indices for lanes beyond n (results discarded)
-            T yH0 = T(0), yH1 = T(0), Hy0 = T(0), Hy1 = T(0), Hg0 = T(0), Hg1 = T(0);
-            {
-                const T* col0 = H + k0;
-                const T* col1 = H + k1;
-                const T* row0 = H + k0 * ld;
-                const T* row1 = H + k1 * ld;
-#pragma unroll 9
-                for (int i = 0; i < n; ++i) {
-                    const T yi = y[i], gi = g[i];
-                    const T hc0 = *col0, hc1 = *col1, hr0 = row0[i], hr1 = row1[i];
-                    col0 += ld;
-                    col1 += ld;
-                    yH0 = fma_t(yi, hc0, yH0); yH1 = fma_t(yi, hc1, yH1);
-                    Hy0 = fma_t(hr0, yi, Hy0); Hy1 = fma_t(hr1, yi, Hy1);
-                    Hg0 = fma_t(hr0, gi, Hg0); Hg1 = fma_t(hr1, gi, Hg1);
-                }
-            }
-            const T y0 = in0 ? y[k0] : T(0), y1 = in1 ? y[k1] : T(0);
-            const T s0 = in0 ? s[k0] : T(0), s1 = in1 ? s[k1] : T(0);
-            const T gg0 = in0 ? g[k0] : T(0), gg1 = in1 ? g[k1] : T(0);
-            if (!in0) { yH0 = T(0); Hy0 = T(0); Hg0 = T(0); }
-            if (!in1) { yH1 = T(0); Hy1 = T(0); Hg1 = T(0); }
-            const T q = mul_rn(warp_allreduce(fma_t(yH0, y0, yH1 * y1)), rho);  // y^T H y / (y^T s), :271-274
-            const T sg = warp_allreduce(fma_t(s0, gg0, s1 * gg1));
-            const T yhg = warp_allreduce(fma_t(yH0, gg0, yH1 * gg1));
-            const T onepq = add_rn(T(1), q);
-            const T dir = fma_t(onepq, sg, -yhg);
-            __syncwarp();  // sweep 1's reads of y are done before it is overwritten with the row constants
-            if (in0) {
-                d[c0] = mul_rn(T(-1), fma_t(-Hy0 * rho, sg, fma_t(s0 * rho, dir, Hg0)));
-                y[c0] = mul_rn(s0, rho);        // row constants of sweep 2: s_i rho ...
-                Hy[c0] = -mul_rn(Hy0, rho);     // ... and -(H y)_i rho
-            }
-            if (in1) {
-                d[c1] = mul_rn(T(-1), fma_t(-Hy1 * rho, sg, fma_t(s1 * rho, dir, Hg1)));
-                y[c1] = mul_rn(s1, rho);
-                Hy[c1] = -mul_rn(Hy1, rho);
-            }
-            __syncwarp();
-            {
-                const T inner0 = fma_t(s0, onepq, -yH0), inner1 = fma_t(s1, onepq, -yH1);  // s_j (1+q) - (y^T H)_j
-                T* col0 = H + k0;
-                T* col1 = H + k1;
-                if (!in1) col1 = ws.xt + lane;  // a lane without a second column updates a scratch word instead of predicating
-                const int st0 = in0 ? ld : 0, st1 = in1 ? ld : 0;
-                if (!in0) col0 = ws.xt + 32 + lane;
-#pragma unroll 9
-                for (int i = 0; i < n; ++i) {
-                    const T sri = y[i], nhr = Hy[i];
-                    *col0 = fma_t(nhr, s0, fma_t(sri, inner0, *col0));
-                    *col1 = fma_t(nhr, s1, fma_t(sri, inner1, *col1));
-                    col0 += st0;
-                    col1 += st1;
-                }
-            }
-#endif
-        }
-        __syncwarp();
-        const LineSearchResult<T> ls = line_search_wide(obj, p, x, d, f, g, ws.xt, gt, lane);  // :181-190
-        fevals += ls.probes;
-        ++iters;
-        T nrm2 = T(0);
+            // ---- line search finished, alpha = upper_alpha (:239): take the step, bfgs_solver.py:191-207 ----
+            ++iters;
+            T nrm2 = T(0);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {                                          // :191-199
-            const int c = lane + 32 * h;
-            if (c < n) {
-                const T sc = mul_rn(ls.alpha, d[c]);
-                s[c] = sc;
-                x[c] = add_rn(x[c], sc);
-                nrm2 = add_rn(nrm2, mul_rn(sc, sc));
+            for (int h = 0; h < 2; ++h) {                                       // :191-199
+                const int c = lane + 32 * h;
+                if (c < n) {
+                    const T sc = mul_rn(hi, d[c]);
+                    s[c] = sc;
+                    x[c] = add_rn(x[c], sc);
+                    nrm2 = add_rn(nrm2, mul_rn(sc, sc));
+                }
             }
+            const T nrm = sqrt_rn(warp_allreduce(nrm2));
+            // the accepted point is bitwise the last probe whenever the search returns the probe it just made:
+            // that probe's (f, grad) are the next outer iteration's evaluation
+            const bool reuse = same_bits(hi, cand);
+            {   // rotate gradient buffers: gprev <- g, and g <- gt when the accepted point is the last probe
+                T* old = gprev;
+                gprev = g;
+                if (reuse) { g = gt; gt = old; }
+                else { g = old; }
+            }
+            ++k;
+            __syncwarp();
+            const bool stop_step = !(nrm > p.min_step);                         // :203-207 (strict >)
+            if (stop_step || k >= p.max_iters) {                                // :118
+                reason = stop_step ? DAVO_REASON_STEP : DAVO_REASON_CAP;
+                if (reuse) {
+                    f = cand_f;
+                    break;
+                }
+                mode = kEvalFinal;
+                continue;
+            }
+            if (!reuse) {
+                mode = kEvalOuter;
+                continue;
+            }
+            f = cand_f;
+            start_iteration = true;
         }
-        const T nrm = sqrt_rn(warp_allreduce(nrm2));
-        have_fg = same_bits(ls.alpha, ls.last_cand);
-        have_f = have_fg;
-        {   // rotate gradient buffers: gprev <- g, and g <- gt when the accepted point is the last probe
-            T* old = gprev;
-            gprev = g;
-            if (have_fg) { g = gt; gt = old; f = ls.last_f; }
-            else { g = old; }
-        }
-        __syncwarp();
-        if (!(nrm > p.min_step)) {                                             // :203-207
-            reason = DAVO_REASON_STEP;
-            break;
+        if (start_iteration) {
+            // ---- top of an outer iteration with (f, g) at x: bfgs_solver.py:136-190 ----
+            ++fevals;  // the reference evaluates here even when the probe is reused
+            if (!(f > p.thr)) {                                                 // :143 (strict >; NaN retires)
+                reason = (f <= p.thr) ? DAVO_REASON_THRESHOLD : DAVO_REASON_NAN;
+                break;
+            }
+            __syncwarp();
+            if (k == 0) {
+                if (lane < n) d[lane] = mul_rn(T(-1), g[lane]);                 // :152-155
+                if (lane + 32 < n) d[lane + 32] = mul_rn(T(-1), g[lane + 32]);
+            } else {
+                if (lane < n) y[lane] = sub_rn(g[lane], gprev[lane]);              // :157
+                if (lane + 32 < n) y[lane + 32] = sub_rn(g[lane + 32], gprev[lane + 32]);
+                __syncwarp();
+                const T sy = wide_dot(s, y, n, lane);
+                if (k == 1) {                                                      // :159-167, :217-233
+                    T den = wide_dot(y, y, n, lane);
+                    den = (den < T(1e-5)) ? T(1e-5) : den;
+                    T sc = div_rn(sy, den);
+                    sc = (sc < T(1e-4)) ? T(1e-4) : sc;
+                    for (int i = 0; i < n; ++i)
+                        for (int j = lane; j < n; j += 32) H[i * ld + j] = mul_rn(sc, H[i * ld + j]);
+                    __syncwarp();
+                }
+                T rho = div_rn(T(1), sy);                                          // func_inverse_curvature.py:8-11
+                if (sy <= T(0)) rho = T(0);
+    #if DAVO_WIDE_FAITHFUL
+                // Literal restatement: every product rounded before the next operation, one element at a time.
+                for (int c = lane; c < n; c += 32) {
+                    T a = T(0), bsum = T(0);
+                    for (int i = 0; i < n; ++i) {
+                        a = add_rn(a, mul_rn(y[i], H[i * ld + c]));                // (y^T H)_c, :268-270
+                        bsum = add_rn(bsum, mul_rn(H[c * ld + i], y[i]));          // (H y)_c,   :293-295
+                    }
+                    yH[c] = a;
+                    Hy[c] = bsum;
+                }
+                __syncwarp();
+                T qp = T(0);                                                       // :271-274
+                for (int c = lane; c < n; c += 32) qp = add_rn(qp, mul_rn(yH[c], mul_rn(y[c], rho)));
+                const T onepq = add_rn(T(1), warp_allreduce(qp));
+                for (int i = 0; i < n; ++i) {                                      // :278-303
+                    const T sri = mul_rn(s[i], rho), Hyi = Hy[i];
+                    for (int j = lane; j < n; j += 32) {
+                        const T sop = mul_rn(mul_rn(sri, s[j]), onepq);
+                        const T sgp = mul_rn(sri, yH[j]);
+                        const T gsp = mul_rn(Hyi, mul_rn(s[j], rho));
+                        H[i * ld + j] = sub_rn(sub_rn(add_rn(H[i * ld + j], sop), sgp), gsp);
+                    }
+                }
+                __syncwarp();
+                for (int c = lane; c < n; c += 32) {                               // :173-176
+                    T a = T(0);
+                    for (int j = 0; j < n; ++j) a = fma_t(H[c * ld + j], g[j], a);
+                    d[c] = mul_rn(T(-1), a);
+                }
+    #else
+                // H' = H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the right (:263-303),
+                // same operands as the literal form, products allowed to fuse.  Lane L owns columns/rows L and L+32.
+                // Sweep 1 walks H once and forms, per owned index c, (y^T H)_c from COLUMN c (never replaced by
+                // (H y)^T: H is symmetric only up to rounding, see solver_warp.cuh), (H y)_c and (H g)_c from ROW c:
+                // six independent FMA chains per lane, no cross-lane traffic.  ld is odd, so both walks are bank
+                // conflict free.  The new direction -H' g (:173-176) follows from
+                //   H' g = H g + (s rho) [ (1+q) s.g - (y^T H).g ] - (H y) rho s.g
+                // without reading H' back.  Sweep 2 rewrites the owned columns.
+                const int c0 = lane, c1 = lane + 32;
+                const bool in0 = c0 < n, in1 = c1 < n;
+                const int k0 = in0 ? c0 : 0, k1 = in1 ? c1 : 0;    // safe indices for lanes beyond n (results discarded)
+                T yH0 = T(0), yH1 = T(0), Hy0 = T(0), Hy1 = T(0), Hg0 = T(0), Hg1 = T(0);
+                {
+                    const T* col0 = H + k0;
+                    const T* col1 = H + k1;
+                    const T* row0 = H + k0 * ld;
+                    const T* row1 = H + k1 * ld;
+    #pragma unroll 9
+                    for (int i = 0; i < n; ++i) {
+                        const T yi = y[i], gi = g[i];
+                        const T hc0 = *col0, hc1 = *col1, hr0 = row0[i], hr1 = row1[i];
+                        col0 += ld;
+                        col1 += ld;
+                        yH0 = fma_t(yi, hc0, yH0); yH1 = fma_t(yi, hc1, yH1);
+                        Hy0 = fma_t(hr0, yi, Hy0); Hy1 = fma_t(hr1, yi, Hy1);
+                        Hg0 = fma_t(hr0, gi, Hg0); Hg1 = fma_t(hr1, gi, Hg1);
+                    }
+                }
+                const T y0 = in0 ? y[k0] : T(0), y1 = in1 ? y[k1] : T(0);
+                const T s0 = in0 ? s[k0] : T(0), s1 = in1 ? s[k1] : T(0);
+                const T gg0 = in0 ? g[k0] : T(0), gg1 = in1 ? g[k1] : T(0);
+                if (!in0) { yH0 = T(0); Hy0 = T(0); Hg0 = T(0); }
+                if (!in1) { yH1 = T(0); Hy1 = T(0); Hg1 = T(0); }
+                const T q = mul_rn(warp_allreduce(fma_t(yH0, y0, yH1 * y1)), rho);  // y^T H y / (y^T s), :271-274
+                const T sg = warp_allreduce(fma_t(s0, gg0, s1 * gg1));
+                const T yhg = warp_allreduce(fma_t(yH0, gg0, yH1 * gg1));
+                const T onepq = add_rn(T(1), q);
+                const T dir = fma_t(onepq, sg, -yhg);
+                __syncwarp();  // sweep 1's reads of y are done before it is overwritten with the row constants
+                if (in0) {
+                    d[c0] = mul_rn(T(-1), fma_t(-Hy0 * rho, sg, fma_t(s0 * rho, dir, Hg0)));
+                    y[c0] = mul_rn(s0, rho);        // row constants of sweep 2: s_i rho ...
+                    Hy[c0] = -mul_rn(Hy0, rho);     // ... and -(H y)_i rho
+                }
+                if (in1) {
+                    d[c1] = mul_rn(T(-1), fma_t(-Hy1 * rho, sg, fma_t(s1 * rho, dir, Hg1)));
+                    y[c1] = mul_rn(s1, rho);
+                    Hy[c1] = -mul_rn(Hy1, rho);
+                }
+                __syncwarp();
+                {
+                    const T inner0 = fma_t(s0, onepq, -yH0), inner1 = fma_t(s1, onepq, -yH1);  // s_j (1+q) - (y^T H)_j
+                    T* col0 = H + k0;
+                    T* col1 = H + k1;
+                    if (!in1) col1 = ws.xt + lane;  // a lane without a second column updates a scratch word instead of predicating
+                    const int st0 = in0 ? ld : 0, st1 = in1 ? ld : 0;
+                    if (!in0) col0 = ws.xt + 32 + lane;
+    #pragma unroll 9
+                    for (int i = 0; i < n; ++i) {
+                        const T sri = y[i], nhr = Hy[i];
+                        *col0 = fma_t(nhr, s0, fma_t(sri, inner0, *col0));
+                        *col1 = fma_t(nhr, s1, fma_t(sri, inner1, *col1));
+                        col0 += st0;
+                        col1 += st1;
+                    }
+                }
+    #endif
+            }
+            __syncwarp();
+            // ---- line-search set-up, wolfe_conditions.py:77-114 ----
+            f0 = f;
+            g0 = wide_dot(d, g, n, lane);                                       // :77
+            neg_c2_g0 = mul_rn(T(-1) * p.c2, g0);
+            widening = true; zooming = false;                                   // :80-82
+            lo = T(0); hi = T(0); cand = T(1);                                  // :97-108
+            lo_f = f0; hi_f = f0; cand_f = f0;                                  // :109-111
+            ls_i = 0;
+            mode = kEvalProbe;
         }
     }
-    if (!have_f) f = obj.eval(x, gt);  // cost at the returned parameters (networks/calibration_network.py:71)
     __syncwarp();
     for (int c = lane; c < n; c += 32) p.x_out[(size_t)b * n + c] = x[c];
     if (lane == 0) {

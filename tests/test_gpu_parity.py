@@ -582,6 +582,29 @@ def test_angle_ba_solve_matches_reference_golden(name):
         assert mo["steps_equal"] >= 0.98
 
 
+def test_angle_ba_large_batch_properties():
+    """16K bundle-adjustment problems (4 views x 8 points, the entry script's shape, float32): every row is written,
+    permuting the problems permutes the outputs bit for bit, the error never increases, and the float32 population
+    looks like the float64 one."""
+    B = 16384
+    b = davo_b200.synthetic.make_angle_ba(B, 8, 4, seed=0xB207, dtype=np.float32)
+    obs, vis, x0 = (torch.from_numpy(a).cuda() for a in (b.obs, b.weights, b.x0))
+    solver = davo_b200.BFGSSolver(error_threshold=1e-4, iterations=200).eval()
+    obj = davo_b200.AngleDistanceObjective(obs, vis)
+    info = solver(x0, obj, return_info=True)
+    start, _ = obj.evaluate(x0, want_grad=False)
+    assert bool(torch.isfinite(info.parameters).all()) and int(info.iterations.min()) >= 1
+    assert bool((info.cost <= start * (1 + 1e-5)).all())
+    assert float(info.cost.median()) < 0.05 * float(start.median())
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(3)).cuda()
+    pinfo = solver(x0[perm], davo_b200.AngleDistanceObjective(obs[perm], vis[perm]), return_info=True)
+    assert torch.equal(pinfo.parameters, info.parameters[perm])
+    assert torch.equal(pinfo.iterations, info.iterations[perm]) and torch.equal(pinfo.cost, info.cost[perm])
+    sub = slice(0, 2048)
+    i64 = solver(x0[sub].double(), davo_b200.AngleDistanceObjective(obs[sub].double(), vis[sub].double()), return_info=True)
+    assert abs(float(i64.cost.median()) - float(info.cost[sub].median())) <= 0.2 * float(i64.cost.median())
+
+
 def test_angle_ba_rejects_bad_shapes():
     obs = torch.zeros(3, 4, 8, 2)
     obj = davo_b200.AngleDistanceObjective(obs)
