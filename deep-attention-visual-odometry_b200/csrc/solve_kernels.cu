@@ -156,7 +156,9 @@ template <typename T>
 static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
     SolveParams<T> p = p_in;
     p.eval_cap = p.reason_out ? DAVO_EVAL_CAP : 0;  // the hand-off flag lives in reason_out
-    auto kernel = (p.N % 32 == 0) ? half_problem_kernel<T, false> : half_problem_kernel<T, true>;
+    auto kernel = (p.N == 256)     ? half_problem_kernel<T, false, 256>   // BASELINE configs 2, 4, 5
+                  : (p.N % 32 == 0) ? half_problem_kernel<T, false>
+                                    : half_problem_kernel<T, true>;
     const size_t smem = half_stride<T>(p.N) * 2 * kWarpsPerCta;
     int dev = 0, sms = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;

@@ -84,7 +84,9 @@ __device__ __forceinline__ void half_gather2(unsigned mask, T own_a, T own_b, T*
     }
 }
 
-template <typename T, bool kRagged>
+// kN > 0 fixes the number of matches per problem at compile time (256 in BASELINE configs 2, 4, 5: shared-memory
+// offsets become immediates, the match loop has a constant trip count); 0 = run time.
+template <typename T, bool kRagged, int kN = 0>
 __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2) half_problem_kernel(const SolveParams<T> p) {
     using V4 = typename Vec4<T>::type;
     using V2 = typename Vec2<T>::type;
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = lane & 15, half = lane >> 4;
     const unsigned hmask = 0xffffu << (half * 16);
-    const int N = p.N, n = p.n;
+    const int N = kN > 0 ? kN : p.N, n = p.n;
     unsigned char* mine = smem + (size_t)(warp * 2 + half) * half_stride<T>(N);
     V4* matches = reinterpret_cast<V4*>(mine);
     T* xt_line = reinterpret_cast<T*>(mine + half_slab_bytes<T>(N));
