@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
 #pragma unroll
             for (int q = 0; q < kPairAcc; ++q) acc2[q] = pk(T(0));
             P gu, gv;
-            DAVO_PRAGMA_UNROLL(DAVO_HALF_UNROLL)
+            // compile-time N: the whole loop is unrolled (8 pairs per lane at N = 256: 3.87 ms against 4.05 ms
+            // unrolled by 2 for 64K x 256)
+            constexpr int kUnroll = kN > 0 ? (kN + 31) / 32 : DAVO_HALF_UNROLL;
+#pragma unroll kUnroll
             for (int i = l; i < N; i += 32) {
                 const V4 ab = matches[i];
                 const V4 ob = matches[i + 16];
