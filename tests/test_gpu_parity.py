@@ -486,6 +486,26 @@ def test_solve_full_size_properties():
     assert float(rel.median()) <= 1e-4
 
 
+@pytest.mark.parametrize("dt,N", [(np.float64, 50), (np.float64, 33), (np.float32, 50), (np.float64, 96)])
+def test_two_per_warp_kernel_ragged_and_generic_match_counts(dt, N):
+    """Batches large enough for the two-problems-per-warp kernel with N not a multiple of 32 (a lane's pair may
+    lack its second match) and with a run-time N (only N = 256 has a compile-time instantiation), against the oracle."""
+    B = 16384
+    batch = davo_b200.synthetic.make_distort10(B, N, seed=300 + N, dtype=dt)
+    kw = dict(error_threshold=1e-12 if dt == np.float64 else 1e-5, iterations=80)
+    obj = davo_b200.DistortionObjective(torch.from_numpy(batch.points_3d).cuda(), torch.from_numpy(batch.obs).cuda())
+    info = davo_b200.BFGSSolver(**kw).eval()(torch.from_numpy(batch.x0).cuda(), obj, return_info=True)
+    got = dict(x=info.parameters.cpu().numpy(), cost=info.cost.cpu().numpy(), iters=info.iterations.cpu().numpy(),
+               fevals=info.evaluations.cpu().numpy(), reason=info.reason.cpu().numpy())
+    ref = c_oracle.solve_batch(batch, **kw)
+    m = compare_solves(got, ref, kw["error_threshold"])
+    print(dt.__name__, N, summary(m))
+    if dt == np.float64:
+        assert m["steps_equal"] >= 0.99 and m["reason_equal"] >= 0.99 and m["dtheta_p99"] <= 1e-6
+    else:
+        assert m["steps_equal"] >= 0.9 and m["reason_equal"] >= 0.97 and m["dtheta_median"] <= 1e-4
+
+
 def test_stragglers_are_handed_off_and_solved():
     """Config 4 (ill-conditioned) at full size: problems that pass the evaluation cap of the two-per-warp launch are
     re-solved by the second launch; every row is written, no hand-off flag survives, and the population agrees with
