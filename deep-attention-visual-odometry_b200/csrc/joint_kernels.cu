@@ -26,10 +26,10 @@ __host__ __device__ inline size_t joint_cta_smem(int N, int V, int n, bool has_w
 #define DAVO_JOINT_MIN_BLOCKS 5  // 96 registers, 20 warps per SM: 31.7 ms vs 33.4 at 4, 32.3 at 6 (config 3)
 #endif
 
-template <typename T, int W, bool kWeighted>
+template <typename T, int W, bool kWeighted, int kV = 0, int kN = 0>
 __global__ void __launch_bounds__(32 * W, (W == 4 && sizeof(T) == 4) ? DAVO_JOINT_MIN_BLOCKS : 1) joint_cta_kernel(const SolveParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    using Obj = JointCtaObjective<T, W, kWeighted>;
+    using Obj = JointCtaObjective<T, W, kWeighted, kV, kN>;
     const size_t data = Obj::data_bytes(p.N, p.V, p.has_w != 0);
     CtaWorkspace<T> ws;
     ws.carve(smem + data, p.n, W);
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(32 * W, (W == 4 && sizeof(T) == 4) ? DAVO_JOIN
 template <typename T, int W>
 static int launch_joint_cta(const SolveParams<T>& p, cudaStream_t stream) {
     auto kernel = p.has_w ? joint_cta_kernel<T, W, true> : joint_cta_kernel<T, W, false>;
+    if (W == 4 && !p.has_w && p.V == 4 && p.N == 256) kernel = joint_cta_kernel<T, W, false, 4, 256>;  // BASELINE config 3
     const size_t smem = joint_cta_smem<T, W>(p.N, p.V, p.n, p.has_w != 0);
     int dev = 0, sms = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;

@@ -48,8 +48,11 @@ struct CtaWorkspace {
 
 // The JOINT objective evaluated by a whole CTA.  th and gout are shared-memory vectors; the caller has
 // made th visible to the CTA (barrier) before the call; on return gout is visible to the CTA.
-template <typename T, int W, bool kWeighted>
+// kV, kN > 0 fix views / points per view at compile time (config 3: 4 x 256, n = 34): loop bounds, the row
+// stride of H and every shared-memory offset of the solver become constants.  0 = run time.
+template <typename T, int W, bool kWeighted, int kV = 0, int kN = 0>
 struct JointCtaObjective {
+    static constexpr int kParams = kV > 0 ? 10 + 6 * kV : 0;  // compile-time n (0: run time)
     const SolveParams<T>& p;
     T* world;  // [N,3]
     T* obs;    // [V,N,2]
@@ -113,7 +116,7 @@ struct JointCtaObjective {
 
     __device__ __forceinline__ T eval(const T* th, T* gout) {
         using V2 = typename Vec2<T>::type;
-        const int N = p.N, V = p.V;
+        const int N = kN > 0 ? kN : p.N, V = kV > 0 ? kV : p.V;
         Intrinsics<T> I;
         I.load(th);
 #if DAVO_JOINT_PACKED
@@ -259,6 +262,7 @@ struct JointCtaObjective {
 // reduced inside each warp (reduce-scatter) and across warps through `red` with one barrier.
 template <typename T, int W>
 struct Distort10CtaObjective {
+    static constexpr int kParams = 10;
     using V4 = typename Vec4<T>::type;
     using P = typename Vec2<T>::type;
     const SolveParams<T>& p;
@@ -395,7 +399,7 @@ __device__ __forceinline__ void cta_matvec3(const T* H, int ld, const T* a, cons
 template <typename T, int W, typename Obj>
 __device__ __forceinline__ LineSearchResult<T> line_search_cta(Obj& obj, const SolveParams<T>& p, const T* x,
                                                                const T* d, T f0, const T* g, T* xt, T* gt) {
-    const int n = p.n, tid = threadIdx.x, lane = tid & 31;
+    const int n = Obj::kParams > 0 ? Obj::kParams : p.n, tid = threadIdx.x, lane = tid & 31;
     const T g0 = wide_dot(d, g, n, lane);       // :77 (each warp, same order: identical in every thread)
     bool widening = true, zooming = false;      // :80-82
     T lo = T(0), hi = T(0), cand = T(1);        // :97-108
@@ -437,7 +441,8 @@ __device__ __forceinline__ LineSearchResult<T> line_search_cta(Obj& obj, const S
 // bfgs_solver.py:80-215 for one problem, executed by the whole CTA.
 template <typename T, int W, typename Obj>
 __device__ __forceinline__ void solve_one_cta(Obj& obj, const SolveParams<T>& p, int b, CtaWorkspace<T>& ws) {
-    const int n = p.n, ld = ws.ld, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = Obj::kParams > 0 ? Obj::kParams : p.n, ld = Obj::kParams > 0 ? Obj::kParams + 1 : ws.ld;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kThreads = 32 * W;
     T *x = ws.x, *g = ws.g, *gprev = ws.gprev, *gt = ws.gt;
     T *d = ws.d, *s = ws.s, *y = ws.y, *yH = ws.yH, *Hy = ws.Hy, *H = ws.H;
