@@ -43,9 +43,15 @@ SOLVER_KW = {"cfg2": dict(error_threshold=1e-7, iterations=1000),
              "ba": dict(error_threshold=1e-7, iterations=1000)}
 
 
-def make_batch(config: str, B: int, seed: int):
+def make_batch(config: str, B: int, seed: int, dtype=np.float32):
     import davo_b200
     syn = davo_b200.synthetic
+    if dtype != np.float32:  # --dtype f64: the entry script's own precision (float_precision="64"), side runs only
+        gen = {"cfg2": lambda: syn.make_distort10(B, 256, seed=seed, dtype=dtype),
+               "cfg4": lambda: syn.make_distort10(B, 256, seed=seed, dtype=dtype, ill_conditioned=True, pathological=0.02),
+               "cfg3": lambda: syn.make_joint(B, 256, 4, seed=seed, dtype=dtype),
+               "ba": lambda: syn.make_angle_ba(B, 8, 4, seed=seed, dtype=dtype)}
+        return gen[config]()
     if config == "cfg2":
         return syn.make_distort10(B, 256, seed=seed, dtype=np.float32)
     if config == "cfg5":  # 1M problems: generated with torch on the GPU when there is one (numpy needs minutes)
@@ -208,6 +214,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5", "ba"])
     ap.add_argument("--batch", type=int, default=0, help="problems per GPU (default: the BASELINE size)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"],
+                    help="arithmetic type (BASELINE asks for f32; the entry script itself trains in f64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -233,7 +241,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch or default_B(args.config, world)
-    batch = make_batch(args.config, B, 0xB200 + rank)
+    np_dt = np.float64 if args.dtype == "f64" else np.float32
+    t_dt = torch.float64 if args.dtype == "f64" else torch.float32
+    esz = 8 if args.dtype == "f64" else 4
+    batch = make_batch(args.config, B, 0xB200 + rank, np_dt)
     kw = SOLVER_KW[args.config]
     solver = davo_b200.BFGSSolver(**kw).eval()
     steps, warm = args.steps, max(args.warmup, 3)
@@ -245,10 +256,10 @@ def main():
     h_obs = torch.from_numpy(batch.obs).pin_memory()
     h_x0 = torch.from_numpy(batch.x0).pin_memory()
     d_pts, d_obs, d_x0 = h_pts.to(dev), h_obs.to(dev), h_x0.to(dev)
-    input_bytes = (h_pts.numel() + h_obs.numel() + h_x0.numel()) * 4
+    input_bytes = (h_pts.numel() + h_obs.numel() + h_x0.numel()) * esz
     # timing rule: inputs larger than L2, or flush L2 between timed iterations (outside the per-step events)
     flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev) if input_bytes <= L2_BYTES else None
-    slab = ResultSlab(B * world, batch.n, torch.float32, world, dev)
+    slab = ResultSlab(B * world, batch.n, t_dt, world, dev)
     out = slab.buffers(rank)
 
     def make_objective(pts, obs):
@@ -361,10 +372,11 @@ def main():
         pass
     props = torch.cuda.get_device_properties(dev)
     sm_max_mhz = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
-    fp32_peak = props.multi_processor_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12   # TFLOP/s
+    lanes = 128 if args.dtype == "f32" else 64   # FP32 / FP64 CUDA-core lanes per SM on B200
+    fp32_peak = props.multi_processor_count * lanes * 2 * sm_max_mhz * 1e6 / 1e12   # TFLOP/s
     flops = algorithmic_flops(batch, fevals, iters)                                # this rank's launch
     achieved = flops / (solve_kernel_ms * 1e-3) / 1e12
-    stage_bytes = batch.N * B * (20 + 16) if batch.model == "distort10" else 0     # read 20 B, write 16 B per match
+    stage_bytes = batch.N * B * (20 + 16) * (esz // 4) if batch.model == "distort10" else 0  # read 20 B, write 16 B per match (f32)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     stage_gbs = stage_bytes / (stage_kernel_ms * 1e-3) / 1e9 if stage_bytes else None
 
@@ -382,7 +394,7 @@ def main():
         "fevals_per_sec": float(stats[1].item()) / (ms_per_step * 1e-3),
         "converged_frac": float(stats[2].item()) / total_B,
         "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None, "dtype": "f32",
+        "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic",
         "config": {"workload": workload_name(args.config, B), "problems_per_gpu": B, "solver": kw,
                    "l2": (f"inputs larger than L2 ({input_bytes / 1e6:.0f} MB of raw inputs per GPU)" if flush is None
@@ -392,12 +404,12 @@ def main():
                    if world > 1 else "none (single GPU)"},
         "kernel_ms": {"solve": solve_kernel_ms, "stage": stage_kernel_ms},
         "mean_iters": float(iters.mean()), "mean_fevals": float(fevals.mean()), "reasons_rank0": reasons,
-        "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "fp32" if args.dtype == "f32" else "fp64", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                      "frac": achieved / fp32_peak, "traffic": traffic,
                      "traffic_note": "DRAM bytes per launch (ncu); the kernel is FP32-pipe bound, its per-problem inputs "
                                      "are read from HBM once and kept in shared memory",
                      "executed_frac": achieved / fp32_peak * float((fevals - iters).sum()) / float(fevals.sum()),
-                     "peak_source": f"{props.multi_processor_count} SMs x 128 lanes x 2 x {sm_max_mhz:.0f} MHz "
+                     "peak_source": f"{props.multi_processor_count} SMs x {lanes} lanes x 2 x {sm_max_mhz:.0f} MHz "
                                     "(no FP32 figure in MEASURED_PEAKS.json; sm_max_mhz taken from it)",
                      "flops_counted": "SURVEY.md 8(d): reference-equivalent fevals x matches x "
                                       f"{FLOP_PER_MATCH_EVAL[batch.model]:.0f} + iters x (12n^2+10n)"},
