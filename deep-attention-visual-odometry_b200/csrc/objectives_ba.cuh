@@ -192,10 +192,11 @@ struct AngleBAObjective {
         gcy = warp_allreduce(gcy);
         __syncwarp();
         // gather: the lane that owns parameter c (c = lane, lane + 32) adds the rows that touch c
-        T own[2];
+        constexpr int kOwn = kParams > 0 ? (kParams + 31) / 32 : kWideMax / 32;  // components per lane
+        T own[kOwn];
         T dsig = T(0);  // sum d/dXs . Xs + sum d/dts . ts  (-> d/d sigma)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kOwn; ++h) {
             const int c = lane + 32 * h;
             T a = T(0);
             if (c < 3) {
@@ -216,7 +217,7 @@ struct AngleBAObjective {
         }
         const T gsig = -warp_allreduce(dsig) * isig;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < kOwn; ++h) {
             const int c = lane + 32 * h;
             if (c < n) {
                 T a = own[h];

@@ -13,7 +13,11 @@
 
 namespace davo {
 
-constexpr int kWideMax = 64;
+constexpr int kWideMax = 128;  // lane L works on components L, L + 32, ... (kCols = 2 for n <= 64, 4 for n <= 128)
+
+__host__ __device__ constexpr int wide_cols(int n) { return n <= 64 ? 2 : 4; }
+// length of one n-vector in the per-warp workspace (>= 64: the sweeps park unused lanes on scratch words of xt)
+__host__ __device__ constexpr int wide_vec(int n) { return n <= 64 ? 64 : 128; }
 
 #ifndef DAVO_WIDE_FAITHFUL
 #define DAVO_WIDE_FAITHFUL 0  // 1: op-by-op rounding of the BFGS update (A/B builds)
@@ -35,34 +39,37 @@ struct WideWorkspace {
     T *x, *g, *gprev, *d, *s, *y, *yH, *Hy, *xt, *gt, *H;
     int ld;  // row stride of H
     __host__ __device__ static size_t bytes(int n) {
-        return sizeof(T) * (10 * (size_t)kWideMax + (size_t)n * (n + 1));
+        return sizeof(T) * (10 * (size_t)wide_vec(n) + (size_t)n * (n + 1));
     }
     __device__ void carve(unsigned char* base, int n) {
         T* p = reinterpret_cast<T*>(base);
-        x = p; g = x + kWideMax; gprev = g + kWideMax; d = gprev + kWideMax; s = d + kWideMax;
-        y = s + kWideMax; yH = y + kWideMax; Hy = yH + kWideMax; xt = Hy + kWideMax; gt = xt + kWideMax;
-        H = gt + kWideMax;
+        const int v = wide_vec(n);
+        x = p; g = x + v; gprev = g + v; d = gprev + v; s = d + v;
+        y = s + v; yH = y + v; Hy = yH + v; xt = Hy + v; gt = xt + v;
+        H = gt + v;
         ld = n | 1;  // odd row stride: a lane walking its row and 32 lanes reading one column are both conflict free
     }
 };
 
 // a . b over the n <= 64 components: lane L contributes components L and L + 32 (no loop: the kernel is bound
 // by instruction issue, and a loop with a run-time trip count costs more than the two guarded products).
-template <typename T>
+template <int kCols = 2, typename T>
 __device__ __forceinline__ T wide_dot(const T* a, const T* b, int n, int lane) {
     T acc = (lane < n) ? mul_rn(a[lane], b[lane]) : T(0);
-    if (lane + 32 < n) acc = add_rn(acc, mul_rn(a[lane + 32], b[lane + 32]));
+#pragma unroll
+    for (int h = 1; h < kCols; ++h)
+        if (lane + 32 * h < n) acc = add_rn(acc, mul_rn(a[lane + 32 * h], b[lane + 32 * h]));
     return warp_allreduce(acc);
 }
 
 // wolfe_conditions.py:23-239.  x, d, g live in shared memory; probes are evaluated at ws.xt with the
 // gradient written to ws.gt.
-template <typename T, typename Obj>
+template <int kCols = 2, typename T, typename Obj>
 __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const SolveParams<T>& p, const T* x,
                                                                 const T* d, T f0, const T* g, T* xt, T* gt,
                                                                 int lane) {
     const int n = Obj::kParams > 0 ? Obj::kParams : p.n;
-    const T g0 = wide_dot(d, g, n, lane);       // :77
+    const T g0 = wide_dot<kCols>(d, g, n, lane);       // :77
     bool widening = true, zooming = false;      // :80-82
     T lo = T(0), hi = T(0), cand = T(1);        // :97-108
     T lo_f = f0, hi_f = f0, cand_f = f0;        // :109-111
@@ -75,11 +82,12 @@ __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const 
             if (zooming) cand = mul_rn(T(0.5), add_rn(lo, hi));                      // :128-131
         }
         __syncwarp();
-        if (lane < n) xt[lane] = add_rn(x[lane], mul_rn(cand, d[lane]));             // :139
-        if (lane + 32 < n) xt[lane + 32] = add_rn(x[lane + 32], mul_rn(cand, d[lane + 32]));
+#pragma unroll
+        for (int h = 0; h < kCols; ++h)                                              // :139
+            if (lane + 32 * h < n) xt[lane + 32 * h] = add_rn(x[lane + 32 * h], mul_rn(cand, d[lane + 32 * h]));
         __syncwarp();
         cand_f = obj.eval(xt, gt);
-        const T dphi = wide_dot(d, gt, n, lane);                                    // :141
+        const T dphi = wide_dot<kCols>(d, gt, n, lane);                                    // :141
         ++probes;
         bool D = cand_f > add_rn(f0, mul_rn(mul_rn(p.c1, cand), g0));               // :146-150
         if (zooming) D = D || (cand_f >= lo_f);                                     // :151-153
@@ -103,7 +111,7 @@ __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const 
 }
 
 // bfgs_solver.py:80-215 for one problem.
-template <typename T, typename Obj>
+template <int kCols = 2, typename T, typename Obj>
 __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p, int b, WideWorkspace<T>& ws,
                                                int lane) {
     // an objective with a compile-time parameter count (Obj::kParams > 0) turns n and the row stride into
@@ -137,8 +145,9 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
         T* gdst = (mode == kEvalOuter) ? g : gt;
         if (mode == kEvalProbe) {
             __syncwarp();
-            if (lane < n) ws.xt[lane] = add_rn(x[lane], mul_rn(cand, d[lane]));  // wolfe_conditions.py:139
-            if (lane + 32 < n) ws.xt[lane + 32] = add_rn(x[lane + 32], mul_rn(cand, d[lane + 32]));
+#pragma unroll
+            for (int h = 0; h < kCols; ++h)                                      // wolfe_conditions.py:139
+                if (lane + 32 * h < n) ws.xt[lane + 32 * h] = add_rn(x[lane + 32 * h], mul_rn(cand, d[lane + 32 * h]));
             pt = ws.xt;
         }
         __syncwarp();
@@ -155,7 +164,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             // ---- one line-search probe has been evaluated: wolfe_conditions.py:143-237 ----
             cand_f = fe;
             ++fevals;
-            const T dphi = wide_dot(d, gt, n, lane);                            // :141
+            const T dphi = wide_dot<kCols>(d, gt, n, lane);                            // :141
             bool D = cand_f > add_rn(f0, mul_rn(mul_rn(p.c1, cand), g0));       // :146-150
             if (zooming) D = D || (cand_f >= lo_f);                             // :151-153
             if (widening && ls_i > 0) D = D || (cand_f >= hi_f);                // :154-157
@@ -181,7 +190,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             ++iters;
             T nrm2 = T(0);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {                                       // :191-199
+            for (int h = 0; h < kCols; ++h) {                                   // :191-199
                 const int c = lane + 32 * h;
                 if (c < n) {
                     const T sc = mul_rn(hi, d[c]);
@@ -228,15 +237,17 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             }
             __syncwarp();
             if (k == 0) {
-                if (lane < n) d[lane] = mul_rn(T(-1), g[lane]);                 // :152-155
-                if (lane + 32 < n) d[lane + 32] = mul_rn(T(-1), g[lane + 32]);
+#pragma unroll
+                for (int h = 0; h < kCols; ++h)                                  // :152-155
+                    if (lane + 32 * h < n) d[lane + 32 * h] = mul_rn(T(-1), g[lane + 32 * h]);
             } else {
-                if (lane < n) y[lane] = sub_rn(g[lane], gprev[lane]);              // :157
-                if (lane + 32 < n) y[lane + 32] = sub_rn(g[lane + 32], gprev[lane + 32]);
+#pragma unroll
+                for (int h = 0; h < kCols; ++h)                                     // :157
+                    if (lane + 32 * h < n) y[lane + 32 * h] = sub_rn(g[lane + 32 * h], gprev[lane + 32 * h]);
                 __syncwarp();
-                const T sy = wide_dot(s, y, n, lane);
+                const T sy = wide_dot<kCols>(s, y, n, lane);
                 if (k == 1) {                                                      // :159-167, :217-233
-                    T den = wide_dot(y, y, n, lane);
+                    T den = wide_dot<kCols>(y, y, n, lane);
                     den = (den < T(1e-5)) ? T(1e-5) : den;
                     T sc = div_rn(sy, den);
                     sc = (sc < T(1e-4)) ? T(1e-4) : sc;
@@ -285,62 +296,81 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
                 // conflict free.  The new direction -H' g (:173-176) follows from
                 //   H' g = H g + (s rho) [ (1+q) s.g - (y^T H).g ] - (H y) rho s.g
                 // without reading H' back.  Sweep 2 rewrites the owned columns.
-                const int c0 = lane, c1 = lane + 32;
-                const bool in0 = c0 < n, in1 = c1 < n;
-                const int k0 = in0 ? c0 : 0, k1 = in1 ? c1 : 0;    // safe indices for lanes beyond n (results discarded)
-                T yH0 = T(0), yH1 = T(0), Hy0 = T(0), Hy1 = T(0), Hg0 = T(0), Hg1 = T(0);
+                T yHc[kCols], Hyc[kCols], Hgc[kCols], yc[kCols], sc_[kCols], gc[kCols];
+                int kc[kCols];
+                bool inc[kCols];
+#pragma unroll
+                for (int h = 0; h < kCols; ++h) {
+                    inc[h] = lane + 32 * h < n;
+                    kc[h] = inc[h] ? lane + 32 * h : 0;   // safe index for lanes beyond n (results discarded)
+                    yHc[h] = Hyc[h] = Hgc[h] = T(0);
+                }
                 {
-                    const T* col0 = H + k0;
-                    const T* col1 = H + k1;
-                    const T* row0 = H + k0 * ld;
-                    const T* row1 = H + k1 * ld;
-    #pragma unroll 9
+                    const T* col[kCols];
+                    const T* row[kCols];
+#pragma unroll
+                    for (int h = 0; h < kCols; ++h) {
+                        col[h] = H + kc[h];
+                        row[h] = H + kc[h] * ld;
+                    }
+#pragma unroll 9
                     for (int i = 0; i < n; ++i) {
                         const T yi = y[i], gi = g[i];
-                        const T hc0 = *col0, hc1 = *col1, hr0 = row0[i], hr1 = row1[i];
-                        col0 += ld;
-                        col1 += ld;
-                        yH0 = fma_t(yi, hc0, yH0); yH1 = fma_t(yi, hc1, yH1);
-                        Hy0 = fma_t(hr0, yi, Hy0); Hy1 = fma_t(hr1, yi, Hy1);
-                        Hg0 = fma_t(hr0, gi, Hg0); Hg1 = fma_t(hr1, gi, Hg1);
+#pragma unroll
+                        for (int h = 0; h < kCols; ++h) {
+                            const T hc = *col[h], hr = row[h][i];
+                            col[h] += ld;
+                            yHc[h] = fma_t(yi, hc, yHc[h]);
+                            Hyc[h] = fma_t(hr, yi, Hyc[h]);
+                            Hgc[h] = fma_t(hr, gi, Hgc[h]);
+                        }
                     }
                 }
-                const T y0 = in0 ? y[k0] : T(0), y1 = in1 ? y[k1] : T(0);
-                const T s0 = in0 ? s[k0] : T(0), s1 = in1 ? s[k1] : T(0);
-                const T gg0 = in0 ? g[k0] : T(0), gg1 = in1 ? g[k1] : T(0);
-                if (!in0) { yH0 = T(0); Hy0 = T(0); Hg0 = T(0); }
-                if (!in1) { yH1 = T(0); Hy1 = T(0); Hg1 = T(0); }
-                const T q = mul_rn(warp_allreduce(fma_t(yH0, y0, yH1 * y1)), rho);  // y^T H y / (y^T s), :271-274
-                const T sg = warp_allreduce(fma_t(s0, gg0, s1 * gg1));
-                const T yhg = warp_allreduce(fma_t(yH0, gg0, yH1 * gg1));
+                T a0 = T(0), a1 = T(0), a2 = T(0);
+#pragma unroll
+                for (int h = 0; h < kCols; ++h) {
+                    yc[h] = inc[h] ? y[kc[h]] : T(0);
+                    sc_[h] = inc[h] ? s[kc[h]] : T(0);
+                    gc[h] = inc[h] ? g[kc[h]] : T(0);
+                    if (!inc[h]) { yHc[h] = T(0); Hyc[h] = T(0); Hgc[h] = T(0); }
+                    a0 = fma_t(yHc[h], yc[h], a0);
+                    a1 = fma_t(sc_[h], gc[h], a1);
+                    a2 = fma_t(yHc[h], gc[h], a2);
+                }
+                const T q = mul_rn(warp_allreduce(a0), rho);                       // y^T H y / (y^T s), :271-274
+                const T sg = warp_allreduce(a1);
+                const T yhg = warp_allreduce(a2);
                 const T onepq = add_rn(T(1), q);
                 const T dir = fma_t(onepq, sg, -yhg);
                 __syncwarp();  // sweep 1's reads of y are done before it is overwritten with the row constants
-                if (in0) {
-                    d[c0] = mul_rn(T(-1), fma_t(-Hy0 * rho, sg, fma_t(s0 * rho, dir, Hg0)));
-                    y[c0] = mul_rn(s0, rho);        // row constants of sweep 2: s_i rho ...
-                    Hy[c0] = -mul_rn(Hy0, rho);     // ... and -(H y)_i rho
-                }
-                if (in1) {
-                    d[c1] = mul_rn(T(-1), fma_t(-Hy1 * rho, sg, fma_t(s1 * rho, dir, Hg1)));
-                    y[c1] = mul_rn(s1, rho);
-                    Hy[c1] = -mul_rn(Hy1, rho);
-                }
+#pragma unroll
+                for (int h = 0; h < kCols; ++h)
+                    if (inc[h]) {
+                        const int c = lane + 32 * h;
+                        d[c] = mul_rn(T(-1), fma_t(-Hyc[h] * rho, sg, fma_t(sc_[h] * rho, dir, Hgc[h])));
+                        y[c] = mul_rn(sc_[h], rho);       // row constants of sweep 2: s_i rho ...
+                        Hy[c] = -mul_rn(Hyc[h], rho);     // ... and -(H y)_i rho
+                    }
                 __syncwarp();
                 {
-                    const T inner0 = fma_t(s0, onepq, -yH0), inner1 = fma_t(s1, onepq, -yH1);  // s_j (1+q) - (y^T H)_j
-                    T* col0 = H + k0;
-                    T* col1 = H + k1;
-                    if (!in1) col1 = ws.xt + lane;  // a lane without a second column updates a scratch word instead of predicating
-                    const int st0 = in0 ? ld : 0, st1 = in1 ? ld : 0;
-                    if (!in0) col0 = ws.xt + 32 + lane;
-    #pragma unroll 9
+                    T inner[kCols];
+                    T* col[kCols];
+                    int st[kCols];
+#pragma unroll
+                    for (int h = 0; h < kCols; ++h) {
+                        inner[h] = fma_t(sc_[h], onepq, -yHc[h]);                  // s_j (1+q) - (y^T H)_j
+                        // a lane without column h updates a scratch word of xt instead of predicating every store
+                        col[h] = inc[h] ? H + kc[h] : ws.xt + (32 * h + lane) % wide_vec(n);
+                        st[h] = inc[h] ? ld : 0;
+                    }
+#pragma unroll 9
                     for (int i = 0; i < n; ++i) {
                         const T sri = y[i], nhr = Hy[i];
-                        *col0 = fma_t(nhr, s0, fma_t(sri, inner0, *col0));
-                        *col1 = fma_t(nhr, s1, fma_t(sri, inner1, *col1));
-                        col0 += st0;
-                        col1 += st1;
+#pragma unroll
+                        for (int h = 0; h < kCols; ++h) {
+                            *col[h] = fma_t(nhr, sc_[h], fma_t(sri, inner[h], *col[h]));
+                            col[h] += st[h];
+                        }
                     }
                 }
     #endif
@@ -348,7 +378,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             __syncwarp();
             // ---- line-search set-up, wolfe_conditions.py:77-114 ----
             f0 = f;
-            g0 = wide_dot(d, g, n, lane);                                       // :77
+            g0 = wide_dot<kCols>(d, g, n, lane);                                       // :77
             neg_c2_g0 = mul_rn(T(-1) * p.c2, g0);
             widening = true; zooming = false;                                   // :80-82
             lo = T(0); hi = T(0); cand = T(1);                                  // :97-108

@@ -21,7 +21,8 @@ __host__ __device__ inline size_t wide_warp_stride(int N, int V, int n, bool has
     return (b + 127) & ~size_t(127);
 }
 
-template <typename T, typename Obj, WMode kMode>
+// kCols: components per lane (2 for n <= 64, 4 for n <= 128)
+template <typename T, typename Obj, WMode kMode, int kCols = 2>
 __global__ void __launch_bounds__(kWideWarpsPerCta * 32) wide_problem_kernel(const SolveParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -31,8 +32,9 @@ __global__ void __launch_bounds__(kWideWarpsPerCta * 32) wide_problem_kernel(con
     WideWorkspace<T> ws;
     ws.carve(mine + Obj::slab_bytes(p.N, p.V, p.has_w != 0), p.n);
     const int n = p.n;
-    const unsigned total_warps = gridDim.x * kWideWarpsPerCta;
-    unsigned b_static = blockIdx.x * kWideWarpsPerCta + warp;
+    const unsigned warps_per_cta = blockDim.x >> 5;  // 2, or 1 when two slabs do not fit in shared memory
+    const unsigned total_warps = gridDim.x * warps_per_cta;
+    unsigned b_static = blockIdx.x * warps_per_cta + warp;
     for (;;) {
         unsigned b = 0;
         if (kMode == WMode::kSolve) {
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(kWideWarpsPerCta * 32) wide_problem_kernel(con
         if (b >= (unsigned)p.B) break;
         obj.bind((int)b);
         if (kMode == WMode::kSolve) {
-            solve_one_wide<T>(obj, p, (int)b, ws, lane);
+            solve_one_wide<kCols>(obj, p, (int)b, ws, lane);
         } else {
             for (int c = lane; c < n; c += 32) ws.x[c] = p.x0[(size_t)b * n + c];
             __syncwarp();
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(kWideWarpsPerCta * 32) wide_problem_kernel(con
                 }
                 __syncwarp();
                 const LineSearchResult<T> r =
-                    line_search_wide(obj, p, ws.x, ws.d, p.base_cost[b], ws.g, ws.xt, ws.gt, lane);
+                    line_search_wide<kCols>(obj, p, ws.x, ws.d, p.base_cost[b], ws.g, ws.xt, ws.gt, lane);
                 if (lane == 0) {
                     p.alpha_out[b] = r.alpha;
                     if (p.fevals_out) p.fevals_out[b] = r.probes;
@@ -72,30 +74,32 @@ __global__ void __launch_bounds__(kWideWarpsPerCta * 32) wide_problem_kernel(con
     }
 }
 
-template <typename T, typename Obj, WMode kMode>
+template <typename T, typename Obj, WMode kMode, int kCols = 2>
 static int launch_wide(const SolveParams<T>& p, cudaStream_t stream) {
-    if (p.n > kWideMax) return DAVO_ERR_UNSUPPORTED;
-    auto kernel = wide_problem_kernel<T, Obj, kMode>;
-    const size_t smem = wide_warp_stride<T, Obj>(p.N, p.V, p.n, p.has_w != 0) * kWideWarpsPerCta;
+    if (p.n > 32 * kCols || p.n > kWideMax) return DAVO_ERR_UNSUPPORTED;
+    auto kernel = wide_problem_kernel<T, Obj, kMode, kCols>;
     int dev = 0, sms = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t stride = wide_warp_stride<T, Obj>(p.N, p.V, p.n, p.has_w != 0);
+    int warps = kWideWarpsPerCta;
+    if (stride * warps > (size_t)max_optin) warps = 1;  // e.g. n = 111 in float64: one 120 KB slab per CTA
+    const size_t smem = stride * warps;
     if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return DAVO_ERR_CUDA;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWideWarpsPerCta * 32, smem) != cudaSuccess ||
-        per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem) != cudaSuccess || per_sm < 1)
         return DAVO_ERR_CUDA;
     long long grid = (long long)per_sm * sms;
-    const long long need = ((long long)p.B + kWideWarpsPerCta - 1) / kWideWarpsPerCta;
+    const long long need = ((long long)p.B + warps - 1) / warps;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (kMode == WMode::kSolve && cudaMemsetAsync(p.queue, 0, sizeof(unsigned), stream) != cudaSuccess)
         return DAVO_ERR_CUDA;
-    kernel<<<(unsigned)grid, kWideWarpsPerCta * 32, smem, stream>>>(p);
+    kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(p);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
 }

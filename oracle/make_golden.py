@@ -67,6 +67,11 @@ SOLVE_CASES = {
                      dict(error_threshold=1e-4, iterations=1000)),
     "solve_ba_small_f64": ("make_angle_ba", dict(B=32, N=5, V=2, seed=0xB206), "float64",
                            dict(error_threshold=1e-7, iterations=40)),
+    # more than 64 parameters (3 views x 20 points: n = 75; 4 views x 30 points: n = 111): four components per lane
+    "solve_ba_n75_f64": ("make_angle_ba", dict(B=32, N=20, V=3, seed=0xB208), "float64",
+                         dict(error_threshold=1e-7, iterations=30)),
+    "solve_ba_n111_f64": ("make_angle_ba", dict(B=16, N=30, V=4, seed=0xB209), "float64",
+                          dict(error_threshold=1e-7, iterations=25)),
 }
 
 
@@ -146,7 +151,7 @@ def gen_angle_ba():
     the Taylor branches of sin(x)/x and (1-cos x)/x^2, the negative-f branch of elu and a zero rotation."""
     rng = np.random.default_rng(15)
     out = {}
-    for tag, (V, N) in (("a", (4, 8)), ("b", (2, 5)), ("c", (3, 11)), ("d", (6, 7))):
+    for tag, (V, N) in (("a", (4, 8)), ("b", (2, 5)), ("c", (3, 11)), ("d", (6, 7)), ("e", (3, 20)), ("f", (4, 30))):
         b = syn.make_angle_ba(12, N, V, seed=40 + V, dtype=np.float64)
         x = b.x0.copy()
         x[1, -3 * (V - 1):] *= 0.1

@@ -115,7 +115,7 @@ def test_analytic_solves(name):
     assert (r32["iters"] == g[f"{name}_float32_iters"]).mean() >= 0.6  # fp32 trajectories are chaotic near the floor
 
 
-BA_SHAPES = {"a": (4, 8), "b": (2, 5), "c": (3, 11), "d": (6, 7)}
+BA_SHAPES = {"a": (4, 8), "b": (2, 5), "c": (3, 11), "d": (6, 7), "e": (3, 20), "f": (4, 30)}
 
 
 @pytest.mark.parametrize("tag", sorted(BA_SHAPES))
@@ -139,7 +139,8 @@ def test_angle_ba_cost_gradient_line_search_match_reference(tag):
 
 
 F64_CASES = ["solve_cfg2_f64", "solve_cfg2_pose_f64", "solve_cfg3_small_f64", "solve_cfg3_f64", "solve_cfg4_f64",
-             "solve_cfg2_noisy_f64", "solve_ba_f64_30steps", "solve_ba_small_f64", "solve_ba_f64"]
+             "solve_cfg2_noisy_f64", "solve_ba_f64_30steps", "solve_ba_small_f64", "solve_ba_f64", "solve_ba_n75_f64",
+             "solve_ba_n111_f64"]
 F32_CASES = ["solve_cfg2_f32", "solve_cfg2_f32_thr1e-7", "solve_cfg3_f32", "solve_cfg4_f32", "solve_ba_f32_30steps",
              "solve_ba_f32"]
 
@@ -159,7 +160,7 @@ def test_solve_matches_reference_within_its_own_band(name):
     print(name, "reference vs itself", summary(band))
     assert_within_band(m, band)
     if name in ("solve_cfg2_f64", "solve_cfg2_pose_f64", "solve_cfg3_small_f64", "solve_ba_f64_30steps",
-                "solve_ba_small_f64"):
+                "solve_ba_small_f64", "solve_ba_n75_f64", "solve_ba_n111_f64"):
         assert m["steps_equal"] == 1.0 and m["fevals_equal"] == 1.0 and m["reason_equal"] == 1.0
         # the 2-view, 5-point bundle adjustment has nearly flat directions: the reference reproduces itself to
         # 9e-6 there under a permutation of the points; the north_star tolerance is 1e-4
