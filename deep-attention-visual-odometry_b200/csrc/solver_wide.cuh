@@ -257,7 +257,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
                 }
                 T rho = div_rn(T(1), sy);                                          // func_inverse_curvature.py:8-11
                 if (sy <= T(0)) rho = T(0);
-    #if DAVO_WIDE_FAITHFUL
+#if DAVO_WIDE_FAITHFUL
                 // Literal restatement: every product rounded before the next operation, one element at a time.
                 for (int c = lane; c < n; c += 32) {
                     T a = T(0), bsum = T(0);
@@ -287,7 +287,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
                     for (int j = 0; j < n; ++j) a = fma_t(H[c * ld + j], g[j], a);
                     d[c] = mul_rn(T(-1), a);
                 }
-    #else
+#else
                 // H' = H + (s rho) s^T (1+q) - (s rho)(y^T H) - (H y)(s rho)^T with the old H on the right (:263-303),
                 // same operands as the literal form, products allowed to fuse.  Lane L owns columns/rows L and L+32.
                 // Sweep 1 walks H once and forms, per owned index c, (y^T H)_c from COLUMN c (never replaced by
@@ -373,7 +373,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
                         }
                     }
                 }
-    #endif
+#endif
             }
             __syncwarp();
             // ---- line-search set-up, wolfe_conditions.py:77-114 ----
