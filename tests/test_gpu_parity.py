@@ -506,6 +506,28 @@ def test_two_per_warp_kernel_ragged_and_generic_match_counts(dt, N):
         assert m["steps_equal"] >= 0.9 and m["reason_equal"] >= 0.97 and m["dtheta_median"] <= 1e-4
 
 
+@pytest.mark.parametrize("B", [14209, 20001, 65535])
+def test_two_per_warp_kernel_odd_batch_sizes(B):
+    """Batch sizes that leave a half-warp without a partner problem at the end of the queue: every row is written
+    exactly once (outputs pre-filled with a sentinel), and the first rows agree with a small batch of the same
+    problems (solved one warp per problem) within the float32 band."""
+    batch = davo_b200.synthetic.make_distort10(B, 64, seed=77, dtype=np.float32)
+    obj = davo_b200.DistortionObjective(torch.from_numpy(batch.points_3d).cuda(), torch.from_numpy(batch.obs).cuda())
+    solver = davo_b200.BFGSSolver(error_threshold=1e-5).eval()
+    from davo_b200.solvers import SolveBuffers
+    buf = SolveBuffers.allocate(B, 10, torch.float32, obj.device)
+    buf.x.fill_(float("nan")); buf.cost.fill_(float("nan")); buf.iterations.fill_(-7); buf.reason.fill_(-7)
+    x0 = torch.from_numpy(batch.x0).cuda()
+    solver.solve_into(x0, obj, out=buf)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(buf.x).all()) and bool(torch.isfinite(buf.cost).all())
+    assert int(buf.iterations.min()) >= 1 and int(buf.reason.min()) >= 0 and int(buf.reason.max()) <= 3
+    assert float(buf.converged.float().mean()) > 0.99
+    small = davo_b200.DistortionObjective.from_staged(obj.data0[:2048])
+    sinfo = solver(x0[:2048], small, return_info=True)
+    assert float((sinfo.iterations == buf.iterations[:2048]).float().mean()) >= 0.97
+
+
 def test_stragglers_are_handed_off_and_solved():
     """Config 4 (ill-conditioned) at full size: problems that pass the evaluation cap of the two-per-warp launch are
     re-solved by the second launch; every row is written, no hand-off flag survives, and the population agrees with
