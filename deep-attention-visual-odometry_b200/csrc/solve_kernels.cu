@@ -157,7 +157,11 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
     SolveParams<T> p = p_in;
     // The hand-off flag lives in reason_out.  The cap grows with the iteration limit (a problem may legitimately use
     // ~2.5 evaluations per outer iteration): only line-search stragglers pass 4 per iteration on average.
+#ifdef DAVO_EVAL_CAP_EXACT  // test builds (tools/resolve_check.py): hand nearly every problem to the second launch
+    const long long cap = DAVO_EVAL_CAP;
+#else
     const long long cap = 4LL * p.max_iters > DAVO_EVAL_CAP ? 4LL * p.max_iters : DAVO_EVAL_CAP;
+#endif
     p.eval_cap = p.reason_out ? (int)(cap > 0x7fffffffLL ? 0x7fffffffLL : cap) : 0;
     auto kernel = (p.N == 256)     ? half_problem_kernel<T, false, 256>   // BASELINE configs 2, 4, 5
                   : (p.N % 32 == 0) ? half_problem_kernel<T, false>
