@@ -202,7 +202,10 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
 }
 
 // ---- second launch of a DISTORT10 solve: one CTA (4 warps) per handed-off problem ------------------------------
-constexpr int kResolveWarps = 4;
+#ifndef DAVO_RESOLVE_WARPS
+#define DAVO_RESOLVE_WARPS 4
+#endif
+constexpr int kResolveWarps = DAVO_RESOLVE_WARPS;
 
 template <typename T>
 __global__ void __launch_bounds__(32 * kResolveWarps) resolve_cta_kernel(const SolveParams<T> p) {
