@@ -23,11 +23,14 @@ __host__ __device__ inline size_t joint_cta_smem(int N, int V, int n, bool has_w
 }
 
 #ifndef DAVO_JOINT_MIN_BLOCKS
-#define DAVO_JOINT_MIN_BLOCKS 5  // 96 registers, 20 warps per SM: 31.7 ms vs 33.4 at 4, 32.3 at 6 (config 3)
+#define DAVO_JOINT_MIN_BLOCKS 8  // CTAs of 2 warps per SM (128 registers, no spills): 25.1 ms for config 3; 10: 25.7, 12: 29.2
+#endif
+#ifndef DAVO_JOINT_WARPS
+#define DAVO_JOINT_WARPS 2       // warps per problem for V >= 2: 25.1 ms vs 27.3 ms with 4 (fewer barriers; still ~11 problems per CTA)
 #endif
 
 template <typename T, int W, bool kWeighted, int kV = 0, int kN = 0>
-__global__ void __launch_bounds__(32 * W, (W == 4 && sizeof(T) == 4) ? DAVO_JOINT_MIN_BLOCKS : 1) joint_cta_kernel(const SolveParams<T> p) {
+__global__ void __launch_bounds__(32 * W, (sizeof(T) == 4 && W > 1) ? (DAVO_JOINT_MIN_BLOCKS * 2) / W : 1) joint_cta_kernel(const SolveParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem[];
     using Obj = JointCtaObjective<T, W, kWeighted, kV, kN>;
     const size_t data = Obj::data_bytes(p.N, p.V, p.has_w != 0);
@@ -51,7 +54,8 @@ __global__ void __launch_bounds__(32 * W, (W == 4 && sizeof(T) == 4) ? DAVO_JOIN
 template <typename T, int W>
 static int launch_joint_cta(const SolveParams<T>& p, cudaStream_t stream) {
     auto kernel = p.has_w ? joint_cta_kernel<T, W, true> : joint_cta_kernel<T, W, false>;
-    if (W == 4 && !p.has_w && p.V == 4 && p.N == 256) kernel = joint_cta_kernel<T, W, false, 4, 256>;  // BASELINE config 3
+    if (W == DAVO_JOINT_WARPS && !p.has_w && p.V == 4 && p.N == 256)
+        kernel = joint_cta_kernel<T, W, false, 4, 256>;  // BASELINE config 3
     const size_t smem = joint_cta_smem<T, W>(p.N, p.V, p.n, p.has_w != 0);
     int dev = 0, sms = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;
@@ -73,11 +77,11 @@ static int launch_joint_cta(const SolveParams<T>& p, cudaStream_t stream) {
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
 }
 
-// W = the largest power of two <= min(V, 4): warp w evaluates views w, w+W, ...
+// Warp w of a problem's CTA evaluates views w, w+W, ...
 template <typename T>
 static int launch_joint_solve(const SolveParams<T>& p, cudaStream_t s) {
-    if (p.V < 1 || p.V > kMaxViews || p.n > kWideMax) return DAVO_ERR_UNSUPPORTED;
-    if (p.V >= 4) return launch_joint_cta<T, 4>(p, s);
+    if (p.V < 1 || p.V > kMaxViews || p.n > 64) return DAVO_ERR_UNSUPPORTED;
+    if (p.V >= DAVO_JOINT_WARPS) return launch_joint_cta<T, DAVO_JOINT_WARPS>(p, s);
     if (p.V >= 2) return launch_joint_cta<T, 2>(p, s);
     return launch_joint_cta<T, 1>(p, s);
 }
