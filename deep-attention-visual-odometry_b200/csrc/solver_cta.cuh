@@ -20,9 +20,9 @@
 #include "solver_wide.cuh"  // warp_allreduce, wide_dot, kWideMax
 
 #ifndef DAVO_JOINT_PACKED
-// 1: evaluate the JOINT matches two per instruction (FFMA2).  Measured slower on config 3 (16K x 1024): 32.3 ms at 4
-// CTAs/SM (128 registers, spills), 35.7 ms at 5 CTAs/SM (96 registers, heavy spills) against 30.2 ms for the scalar
-// loop at 5 CTAs/SM: the 12 pose sums double the accumulator registers.  Kept for A/B builds.
+// 1: evaluate the JOINT matches two per instruction (FFMA2).  Measured on config 3 (16K x 1024) with every
+// occupancy that fits: never faster than the scalar loop (W = 2: 25.4-26.5 ms against 25.0 ms; W = 4: 28.7-35.7 ms
+// against 27.3 ms): the 12 pose sums double the accumulator registers.  Kept for A/B builds.
 #define DAVO_JOINT_PACKED 0
 #endif
 
