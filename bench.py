@@ -394,8 +394,10 @@ def main():
     traffic = stage_traffic = None
     try:  # DRAM bytes per launch of the solve kernel from the committed ncu --set full capture of this workload
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if B == default_B(args.config, world) and args.config in ("cfg2", "cfg3"):
+        if B == default_B(args.config, world) and args.config in ("cfg2", "cfg3", "cfg4") and args.dtype == "f32":
             traffic = tj["solve_" + args.config]["bytes"]
+        if args.config == "ba" and args.dtype == "f32":   # captured at 32K problems: scale to this launch
+            traffic = int(tj["solve_ba"]["bytes"] * B / tj["solve_ba"]["problems"])
         stage_traffic = tj["stage_cfg2"]["bytes"] if (args.config == "cfg2" and B == default_B("cfg2")) else None
     except (OSError, KeyError):
         pass
