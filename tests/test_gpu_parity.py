@@ -678,3 +678,18 @@ def test_calibration_network_forward_refines_its_initial_guess():
     net.train()
     with pytest.raises(NotImplementedError):
         net(obs, vis)
+
+
+def test_randomised_sweep_against_oracle():
+    """tools/fuzz_parity.py for 20 s: random batch sizes on both sides of the two-per-warp threshold, ragged and tiny
+    match counts, weights, both precisions, all four objectives, iteration caps 0..200 — no case may leave the band
+    (float64: >= 90 % identical step counts and median |dtheta| <= 1e-6 per batch)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "20", "7"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "SUSPECT" not in r.stdout, r.stdout[-3000:]
+    assert " runs in " in r.stdout
