@@ -59,7 +59,7 @@ typedef enum davo_status {
 #define DAVO_MODEL_JOINT 1
 /* ANGLE_BA:  the entry script's bundle-adjustment objective (networks/calibration_network.py:58-67):
  *            parameters (f, cx, cy | N world points | V-1 translations | V-1 axis-angle rotations),
- *            n = 3 + 3N + 6(V-1), V >= 2; error = sum over views and points of
+ *            n = 3 + 3N + 6(V-1) <= 128, V >= 2; error = sum over views and points of
  *            visibility * angle(pixel ray, camera-relative point), with
  *            unpack_calibration_parameters / get_camera_relative_points
  *            (camera_model/calibration_pinhole_camera_model.py:33-117), rotate_vector_axis_angle
@@ -141,7 +141,12 @@ const char* davo_strerror(int status);
  *   iters_out [B]     accepted steps (= line searches the problem took part in)
  *   fevals_out[B]     objective evaluations the reference would have made
  *   reason_out[B]     DAVO_REASON_* (may be NULL)
- * Output pointers are written for all B rows. */
+ * Output pointers are written for all B rows.
+ * DISTORT10 without weights, large batches: two launches on `stream` — two problems per warp, then one CTA per
+ * straggler (a problem past max(4096, 4 * max_iters) evaluations is abandoned by the first launch and solved again
+ * from x0 by the second).  reason_out carries the hand-off flag between them (an internal value that never
+ * survives the call); with reason_out == NULL the first launch solves every problem to the end.  `workspace`
+ * holds one work-queue counter per launch. */
 int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, const void* data1,
                            const void* weights, const void* x0, void* x_out, void* cost_out,
                            uint8_t* converged_out, int32_t* iters_out, int32_t* fevals_out,
