@@ -27,8 +27,31 @@ def _prepare(points_3d: torch.Tensor, parameters: torch.Tensor):
     return device, dt, pts, th
 
 
+class _ProjectWithGrad(torch.autograd.Function):
+    """(u', v') = forward model, differentiable with respect to the 16 parameters: the backward pass contracts the
+    incoming gradients with the Jacobian the forward pass computed (davo_project_jacobian)."""
+
+    @staticmethod
+    def forward(ctx, points_3d, parameters):
+        J, u, v = compute_distorted_camera_model_and_jacobian(points_3d, parameters)
+        ctx.save_for_backward(J)
+        return u, v
+
+    @staticmethod
+    def backward(ctx, grad_u, grad_v):
+        (J,) = ctx.saved_tensors
+        N = J.shape[1] // 2
+        zero = lambda g: torch.zeros(J.shape[0], N, dtype=J.dtype, device=J.device) if g is None else g.to(J.dtype)
+        g = torch.cat([zero(grad_u), zero(grad_v)], dim=1)           # [B, 2N]
+        return None, torch.bmm(g.unsqueeze(1), J).squeeze(1)         # d/d points_3d is not provided
+
+
 def compute_distorted_camera_model(points_3d: torch.Tensor, parameters: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """points_3d [B,N,3], parameters [B,16] -> (u'[B,N], v'[B,N])."""
+    """points_3d [B,N,3], parameters [B,16] -> (u'[B,N], v'[B,N]).  Differentiable with respect to `parameters`
+    (the reference's TorchScript function is differentiated by autograd; here the analytic Jacobian is used);
+    `points_3d` is treated as data."""
+    if parameters.requires_grad and torch.is_grad_enabled():
+        return _ProjectWithGrad.apply(points_3d, parameters)
     device, dt, pts, th = _prepare(points_3d, parameters)
     B, N = pts.shape[0], pts.shape[1]
     with torch.cuda.device(device):

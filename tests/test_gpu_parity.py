@@ -550,6 +550,20 @@ def test_stragglers_are_handed_off_and_solved():
     assert abs(dev.iterations.float().mean().item() - host.iterations.float().mean().item()) <= 0.03 * dev.iterations.float().mean().item()
 
 
+def test_forward_model_is_differentiable_in_the_parameters():
+    """compute_distorted_camera_model(points, theta) back-propagates to theta through the analytic Jacobian; the
+    fixture holds autograd's Jacobian of the reference forward model."""
+    g = load_golden("camera_model")
+    pts = torch.from_numpy(g["points_3d"][1:])
+    th = torch.from_numpy(g["params16"][1:]).clone().requires_grad_(True)
+    u, v = davo_b200.compute_distorted_camera_model(pts, th)
+    rng = np.random.default_rng(3)
+    a, b = torch.from_numpy(rng.standard_normal(u.shape)), torch.from_numpy(rng.standard_normal(v.shape))
+    ((u * a).sum() + (v * b).sum()).backward()
+    expect = np.einsum("bi,bij->bj", np.concatenate([a.numpy(), b.numpy()], axis=1), g["J_autograd"])
+    assert np.allclose(th.grad.numpy(), expect, rtol=1e-9, atol=1e-10)
+
+
 # ---- SURVEY.md 8(f) row 1: the entry script's bundle-adjustment objective ---------------------------------
 
 BA_SHAPES = {"a": (4, 8), "b": (2, 5), "c": (3, 11), "d": (6, 7), "e": (3, 20), "f": (4, 30)}  # e, f: n = 75, 111 > 64
