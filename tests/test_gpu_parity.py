@@ -506,6 +506,39 @@ def test_two_per_warp_kernel_ragged_and_generic_match_counts(dt, N):
         assert m["steps_equal"] >= 0.9 and m["reason_equal"] >= 0.97 and m["dtheta_median"] <= 1e-4
 
 
+@pytest.mark.parametrize("name", ["solve_cfg2_f64", "solve_cfg2_f32", "solve_cfg4_f32"])
+def test_two_per_warp_kernel_matches_reference_golden(name):
+    """The golden problems of configs 2 and 4 tiled to >= 15K problems (the two-problems-per-warp route + the
+    straggler launch): every copy of a problem gives bit-identical outputs whatever half-warp, partner problem and queue
+    position it meets, and copy 0 is held to the same gate against the REFERENCE's results as the small batch."""
+    g = load_golden(name)
+    batch = golden_batch(g["meta"])
+    kw = g["meta"]["solver_kwargs"]
+    B0 = batch.B
+    reps = -(-15360 // B0)
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (reps,) + (1,) * (a.ndim - 1)))
+    big = davo_b200.synthetic.CalibrationBatch(batch.model, tile(batch.points_3d), tile(batch.obs), tile(batch.pose),
+                                               tile(batch.x0), tile(batch.truth), 1)
+    dt = TDT[big.x0.dtype]
+    obj = davo_b200.DistortionObjective(torch.from_numpy(big.points_3d).cuda(), torch.from_numpy(big.obs).cuda(),
+                                        torch.from_numpy(big.pose).cuda(), dtype=dt)
+    info = davo_b200.BFGSSolver(**kw).eval()(torch.from_numpy(big.x0).cuda(), obj, return_info=True)
+    x = info.parameters.cpu().numpy().reshape(reps, B0, -1)
+    it = info.iterations.cpu().numpy().reshape(reps, B0)
+    co = info.cost.cpu().numpy().reshape(reps, B0)
+    for r in range(1, reps):
+        assert np.array_equal(x[r], x[0], equal_nan=True) and np.array_equal(it[r], it[0])
+        assert np.array_equal(co[r], co[0], equal_nan=True)
+    got = dict(x=x[0], cost=co[0], iters=it[0], fevals=info.evaluations.cpu().numpy()[:B0],
+               reason=info.reason.cpu().numpy()[:B0])
+    m = compare_solves(got, g, kw["error_threshold"])
+    band = reference_band(g, kw["error_threshold"])
+    print(name, "two-per-warp kernel vs reference", summary(m))
+    assert_within_band(m, band)
+    if name == "solve_cfg2_f64":
+        assert m["steps_equal"] >= 0.995 and m["dtheta_max"] <= 1e-6
+
+
 @pytest.mark.parametrize("B", [14209, 20001, 65535])
 def test_two_per_warp_kernel_odd_batch_sizes(B):
     """Batch sizes that leave a half-warp without a partner problem at the end of the queue: every row is written
