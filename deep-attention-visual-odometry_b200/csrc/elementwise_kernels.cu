@@ -157,80 +157,115 @@ template int launch_stage<float>(int, int, const float*, const float*, const flo
 template int launch_stage<double>(int, int, const double*, const double*, const double*, double*, cudaStream_t);
 
 // ---- 16-parameter forward model and Jacobian ------------------------------------------------------
+// A CTA takes kProjGroup problems per trip: kProjGroup threads load the 16 parameters and build R (and dR/dr for
+// the Jacobian) of one problem each, in parallel, then all threads stream the group's matches flat, kProjUnroll
+// per thread with the point loads issued before the first use (one thread doing the trigonometry for a whole
+// CTA, one match per thread, kept this kernel at a third of the HBM rate).
+// (The Jacobian variant writes 136 B per match and does ~10x the arithmetic: there one problem per trip with two
+// matches per thread is faster — 81 us against 103 us for 8K x 256 — so it keeps a group of 1.)
+template <bool kJac>
+struct ProjGroup { static constexpr int value = kJac ? 1 : 8; };
+
 template <typename T, bool kJac>
 __global__ void __launch_bounds__(128) project_kernel(int B, int N, const T* __restrict__ pts,
                                                       const T* __restrict__ th16, T* __restrict__ u_out,
                                                       T* __restrict__ v_out, T* __restrict__ J) {
-    __shared__ T th[16];
-    __shared__ T Rm[9], dR[3][9];
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    constexpr int kProjUnroll = kJac ? 1 : 4;
+    constexpr int kProjGroup = ProjGroup<kJac>::value;
+    __shared__ T ths[kProjGroup][16];
+    __shared__ T Rms[kProjGroup][9], dRs[kProjGroup][3][9];
+    for (long long g0 = (long long)blockIdx.x * kProjGroup; g0 < B; g0 += (long long)gridDim.x * kProjGroup) {
+        const int nb = (int)((B - g0) < kProjGroup ? (B - g0) : kProjGroup);
         __syncthreads();
-        if (threadIdx.x < 16) th[threadIdx.x] = th16[16 * (size_t)b + threadIdx.x];
+        if ((int)threadIdx.x < 16 * nb) ths[threadIdx.x >> 4][threadIdx.x & 15] = th16[16 * (size_t)g0 + threadIdx.x];
         __syncthreads();
-        if (threadIdx.x == 0)
-            euler_matrices<T>(th[DAVO_RX], th[DAVO_RY], th[DAVO_RZ], Rm, kJac ? dR[0] : nullptr, dR[1], dR[2]);
+        if ((int)threadIdx.x < nb) {
+            const int q = threadIdx.x;
+            euler_matrices<T>(ths[q][DAVO_RX], ths[q][DAVO_RY], ths[q][DAVO_RZ], Rms[q], kJac ? dRs[q][0] : nullptr,
+                              dRs[q][1], dRs[q][2]);
+        }
         __syncthreads();
-        const T cx = th[0], cy = th[1], k1 = th[2], k2 = th[3], k3 = th[4], p1 = th[5], p2 = th[6], fx = th[7],
-                sk = th[8], fy = th[9];
-        for (int m = threadIdx.x; m < N; m += blockDim.x) {
-            const T* X = pts + 3 * ((size_t)b * N + m);
-            const T X0 = X[0], X1 = X[1], X2 = X[2];
-            T xp, yp, zp;
-            transform_point<T>(Rm, th + DAVO_TX, X0, X1, X2, xp, yp, zp);
-            // un-fused, in the reference's order, so the float32 forward agrees to the last bit or two
-            const T a = div_rn(xp, zp), bb = div_rn(yp, zp);
-            const T u = add_rn(mul_rn(fx, a), mul_rn(sk, bb));                   // :59-61
-            const T v = mul_rn(fy, bb);                                          // :62
-            const T r2 = add_rn(mul_rn(u, u), mul_rn(v, v));                     // :64
-            const T uv = mul_rn(u, v);                                           // :65
-            const T rad = add_rn(add_rn(add_rn(T(1), mul_rn(k1, r2)), mul_rn(mul_rn(k2, r2), r2)),
-                                 mul_rn(mul_rn(mul_rn(k3, r2), r2), r2));        // :66-74
-            const T A = add_rn(r2, mul_rn(mul_rn(T(2), u), u));
-            const T Bv = add_rn(r2, mul_rn(mul_rn(T(2), v), v));
-            const T up = add_rn(add_rn(add_rn(mul_rn(u, rad), mul_rn(mul_rn(T(2), p1), uv)), mul_rn(p2, A)), cx);
-            const T vp = add_rn(add_rn(add_rn(mul_rn(v, rad), mul_rn(mul_rn(T(2), p2), uv)), mul_rn(p1, Bv)), cy);
-            u_out[(size_t)b * N + m] = up;
-            v_out[(size_t)b * N + m] = vp;
-            if (kJac) {
-                const T r4 = r2 * r2, r6 = r4 * r2;
-                const T radp = k1 + T(2) * k2 * r2 + T(3) * k3 * r4;
-                const T Duu = rad + T(2) * u * u * radp + T(2) * p1 * v + T(6) * p2 * u;
-                const T Dvv = rad + T(2) * v * v * radp + T(6) * p1 * v + T(2) * p2 * u;
-                const T Duv = T(2) * uv * radp + T(2) * p1 * u + T(2) * p2 * v;
-                const T iz = T(1) / zp;
-                T ju[16], jv[16];
-                ju[0] = 1; jv[0] = 0;
-                ju[1] = 0; jv[1] = 1;
-                ju[2] = u * r2; jv[2] = v * r2;
-                ju[3] = u * r4; jv[3] = v * r4;
-                ju[4] = u * r6; jv[4] = v * r6;
-                ju[5] = T(2) * uv; jv[5] = Bv;
-                ju[6] = A; jv[6] = T(2) * uv;
-                ju[7] = Duu * a;  jv[7] = Duv * a;
-                ju[8] = Duu * bb; jv[8] = Duv * bb;
-                ju[9] = Duv * bb; jv[9] = Dvv * bb;
-                const T ux = Duu * fx * iz, uy = (Duu * sk + Duv * fy) * iz, uz = -(Duu * u + Duv * v) * iz;
-                const T vx = Duv * fx * iz, vy = (Duv * sk + Dvv * fy) * iz, vz = -(Duv * u + Dvv * v) * iz;
+        const long long first = g0 * N;
+        const int total = nb * N;
+        for (int base = threadIdx.x; base < total; base += 128 * kProjUnroll) {
+            T Xs[kProjUnroll][3];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const T dX = dR[k][0] * X0 + dR[k][1] * X1 + dR[k][2] * X2;
-                    const T dY = dR[k][3] * X0 + dR[k][4] * X1 + dR[k][5] * X2;
-                    const T dZ = dR[k][6] * X0 + dR[k][7] * X1 + dR[k][8] * X2;
-                    ju[10 + k] = ux * dX + uy * dY + uz * dZ;
-                    jv[10 + k] = vx * dX + vy * dY + vz * dZ;
+            for (int k = 0; k < kProjUnroll; ++k) {
+                const int i = base + 128 * k;
+                if (i < total) {
+                    const T* X = pts + 3 * (first + i);
+                    Xs[k][0] = __ldg(X); Xs[k][1] = __ldg(X + 1); Xs[k][2] = __ldg(X + 2);
                 }
-                ju[13] = ux; ju[14] = uy; ju[15] = uz;
-                jv[13] = vx; jv[14] = vy; jv[15] = vz;
-                using V4 = typename Vec4<T>::type;
-                V4* Ju = reinterpret_cast<V4*>(J + 16 * ((size_t)b * 2 * N + m));          // rows 0..N-1: u'
-                V4* Jv = reinterpret_cast<V4*>(J + 16 * ((size_t)b * 2 * N + N + m));      // rows N..2N-1: v'
+            }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    V4 a4, b4;
-                    a4.x = ju[4 * q]; a4.y = ju[4 * q + 1]; a4.z = ju[4 * q + 2]; a4.w = ju[4 * q + 3];
-                    b4.x = jv[4 * q]; b4.y = jv[4 * q + 1]; b4.z = jv[4 * q + 2]; b4.w = jv[4 * q + 3];
-                    Ju[q] = a4;
-                    Jv[q] = b4;
+            for (int k = 0; k < kProjUnroll; ++k) {
+                const int i = base + 128 * k;
+                if (i >= total) continue;
+                const int q = i / N, m = i - q * N;
+                const long long b = g0 + q, mi = first + i;
+                const T* th = ths[q];
+                const T* Rm = Rms[q];
+                const T (*dR)[9] = dRs[q];
+                const T cx = th[0], cy = th[1], k1 = th[2], k2 = th[3], k3 = th[4], p1 = th[5], p2 = th[6], fx = th[7],
+                        sk = th[8], fy = th[9];
+                const T X0 = Xs[k][0], X1 = Xs[k][1], X2 = Xs[k][2];
+                T xp, yp, zp;
+                transform_point<T>(Rm, th + DAVO_TX, X0, X1, X2, xp, yp, zp);
+                // un-fused, in the reference's order, so the float32 forward agrees to the last bit or two
+                const T a = div_rn(xp, zp), bb = div_rn(yp, zp);
+                const T u = add_rn(mul_rn(fx, a), mul_rn(sk, bb));                   // :59-61
+                const T v = mul_rn(fy, bb);                                          // :62
+                const T r2 = add_rn(mul_rn(u, u), mul_rn(v, v));                     // :64
+                const T uv = mul_rn(u, v);                                           // :65
+                const T rad = add_rn(add_rn(add_rn(T(1), mul_rn(k1, r2)), mul_rn(mul_rn(k2, r2), r2)),
+                                     mul_rn(mul_rn(mul_rn(k3, r2), r2), r2));        // :66-74
+                const T A = add_rn(r2, mul_rn(mul_rn(T(2), u), u));
+                const T Bv = add_rn(r2, mul_rn(mul_rn(T(2), v), v));
+                const T up = add_rn(add_rn(add_rn(mul_rn(u, rad), mul_rn(mul_rn(T(2), p1), uv)), mul_rn(p2, A)), cx);
+                const T vp = add_rn(add_rn(add_rn(mul_rn(v, rad), mul_rn(mul_rn(T(2), p2), uv)), mul_rn(p1, Bv)), cy);
+                u_out[mi] = up;
+                v_out[mi] = vp;
+                if (kJac) {
+                    const T r4 = r2 * r2, r6 = r4 * r2;
+                    const T radp = k1 + T(2) * k2 * r2 + T(3) * k3 * r4;
+                    const T Duu = rad + T(2) * u * u * radp + T(2) * p1 * v + T(6) * p2 * u;
+                    const T Dvv = rad + T(2) * v * v * radp + T(6) * p1 * v + T(2) * p2 * u;
+                    const T Duv = T(2) * uv * radp + T(2) * p1 * u + T(2) * p2 * v;
+                    const T iz = T(1) / zp;
+                    T ju[16], jv[16];
+                    ju[0] = 1; jv[0] = 0;
+                    ju[1] = 0; jv[1] = 1;
+                    ju[2] = u * r2; jv[2] = v * r2;
+                    ju[3] = u * r4; jv[3] = v * r4;
+                    ju[4] = u * r6; jv[4] = v * r6;
+                    ju[5] = T(2) * uv; jv[5] = Bv;
+                    ju[6] = A; jv[6] = T(2) * uv;
+                    ju[7] = Duu * a;  jv[7] = Duv * a;
+                    ju[8] = Duu * bb; jv[8] = Duv * bb;
+                    ju[9] = Duv * bb; jv[9] = Dvv * bb;
+                    const T ux = Duu * fx * iz, uy = (Duu * sk + Duv * fy) * iz, uz = -(Duu * u + Duv * v) * iz;
+                    const T vx = Duv * fx * iz, vy = (Duv * sk + Dvv * fy) * iz, vz = -(Duv * u + Dvv * v) * iz;
+    #pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const T dX = dR[k][0] * X0 + dR[k][1] * X1 + dR[k][2] * X2;
+                        const T dY = dR[k][3] * X0 + dR[k][4] * X1 + dR[k][5] * X2;
+                        const T dZ = dR[k][6] * X0 + dR[k][7] * X1 + dR[k][8] * X2;
+                        ju[10 + k] = ux * dX + uy * dY + uz * dZ;
+                        jv[10 + k] = vx * dX + vy * dY + vz * dZ;
+                    }
+                    ju[13] = ux; ju[14] = uy; ju[15] = uz;
+                    jv[13] = vx; jv[14] = vy; jv[15] = vz;
+                    using V4 = typename Vec4<T>::type;
+                    V4* Ju = reinterpret_cast<V4*>(J + 16 * ((size_t)b * 2 * N + m));          // rows 0..N-1: u'
+                    V4* Jv = reinterpret_cast<V4*>(J + 16 * ((size_t)b * 2 * N + N + m));      // rows N..2N-1: v'
+    #pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        V4 a4, b4;
+                        a4.x = ju[4 * q]; a4.y = ju[4 * q + 1]; a4.z = ju[4 * q + 2]; a4.w = ju[4 * q + 3];
+                        b4.x = jv[4 * q]; b4.y = jv[4 * q + 1]; b4.z = jv[4 * q + 2]; b4.w = jv[4 * q + 3];
+                        Ju[q] = a4;
+                        Jv[q] = b4;
+                    }
                 }
             }
         }
@@ -240,7 +275,9 @@ __global__ void __launch_bounds__(128) project_kernel(int B, int N, const T* __r
 template <typename T>
 int launch_project(int B, int N, const T* pts, const T* th16, T* u, T* v, T* J, cudaStream_t s) {
     if (B == 0 || N == 0) return DAVO_OK;
-    const int grid = B < 148 * 64 ? B : 148 * 64;
+    const int group = J ? ProjGroup<true>::value : ProjGroup<false>::value;
+    const long long groups = ((long long)B + group - 1) / group;
+    const int grid = (int)(groups < 148LL * 64 ? groups : 148LL * 64);
     if (J) project_kernel<T, true><<<grid, 128, 0, s>>>(B, N, pts, th16, u, v, J);
     else   project_kernel<T, false><<<grid, 128, 0, s>>>(B, N, pts, th16, u, v, nullptr);
     count_launch();
@@ -250,55 +287,64 @@ template int launch_project<float>(int, int, const float*, const float*, float*,
 template int launch_project<double>(int, int, const double*, const double*, double*, double*, double*, cudaStream_t);
 
 // ---- explicit least squares: error[B] = sum w r^2, gradient[B,P] = sum 2 w r J --------------------
+// One WARP per problem (8 per CTA, grid-stride): lanes stride over the R residuals with several loads in flight,
+// per-lane partial sums, one butterfly per output.  (A 256-thread CTA per problem with an 8-stage block reduction
+// ran at a fifth of the HBM rate at R = 512.)
 constexpr int kLsqThreads = 256;
+constexpr int kLsqCols = 16;  // gradient columns accumulated per pass over the residuals
+
+template <typename T>
+__device__ __forceinline__ T lsq_warp_sum(T v) {
+    v += shfl_xor(v, 16); v += shfl_xor(v, 8); v += shfl_xor(v, 4); v += shfl_xor(v, 2); v += shfl_xor(v, 1);
+    return v;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kLsqThreads) least_squares_kernel(int B, int R, int P, const T* __restrict__ res,
                                                                     const T* __restrict__ jac,
                                                                     const T* __restrict__ w, T* __restrict__ err,
                                                                     T* __restrict__ grad) {
-    __shared__ T red[kLsqThreads];
-    const int t = threadIdx.x;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = kLsqThreads / 32;
+    for (long long b = (long long)blockIdx.x * warps + warp; b < B; b += (long long)gridDim.x * warps) {
         const T* r = res + (size_t)b * R;
         const T* ww = w ? w + (size_t)b * R : nullptr;
         if (err) {
-            T e = T(0);
-            for (int i = t; i < R; i += kLsqThreads) {
-                const T sq = r[i] * r[i];
-                e += ww ? ww[i] * sq : sq;                      // least_squares_utils.py:24-28
+            T e0 = T(0), e1 = T(0), e2 = T(0), e3 = T(0);
+            int i = lane;
+            for (; i + 96 < R; i += 128) {                      // four independent loads per trip
+                const T r0 = r[i], r1 = r[i + 32], r2 = r[i + 64], r3 = r[i + 96];
+                if (ww) {
+                    e0 = fma_t(ww[i] * r0, r0, e0); e1 = fma_t(ww[i + 32] * r1, r1, e1);
+                    e2 = fma_t(ww[i + 64] * r2, r2, e2); e3 = fma_t(ww[i + 96] * r3, r3, e3);
+                } else {
+                    e0 = fma_t(r0, r0, e0); e1 = fma_t(r1, r1, e1); e2 = fma_t(r2, r2, e2); e3 = fma_t(r3, r3, e3);
+                }
             }
-            __syncthreads();
-            red[t] = e;
-            __syncthreads();
-            for (int s = kLsqThreads / 2; s > 0; s >>= 1) {
-                if (t < s) red[t] += red[t + s];
-                __syncthreads();
+            for (; i < R; i += 32) {
+                const T r0 = r[i];
+                e0 = ww ? fma_t(ww[i] * r0, r0, e0) : fma_t(r0, r0, e0);   // least_squares_utils.py:24-28
             }
-            if (t == 0) err[b] = red[0];
+            const T e = lsq_warp_sum((e0 + e1) + (e2 + e3));
+            if (lane == 0) err[b] = e;
         }
         if (grad && jac) {
-            // a thread keeps one parameter column: the stride over the flat [R,P] index is a multiple of P
-            for (int p0 = 0; p0 < P; p0 += kLsqThreads) {
-                const int Pc = (P - p0) < kLsqThreads ? (P - p0) : kLsqThreads;  // columns in this chunk
-                const int groups = kLsqThreads / Pc;
-                const int gi = t / Pc, pc = t % Pc;
-                T acc = T(0);
-                if (gi < groups) {
-                    const T* Jb = jac + (size_t)b * R * P + p0 + pc;
-                    for (int i = gi; i < R; i += groups) {
-                        T gr = T(2) * r[i];                     // :43
-                        if (ww) gr = ww[i] * gr;                // :44-45
-                        acc = fma_t(gr, Jb[(size_t)i * P], acc);
-                    }
+            const T* Jb = jac + (size_t)b * R * P;
+            for (int p0 = 0; p0 < P; p0 += kLsqCols) {
+                T acc[kLsqCols];
+#pragma unroll
+                for (int k = 0; k < kLsqCols; ++k) acc[k] = T(0);
+                for (int i = lane; i < R; i += 32) {
+                    T gr = T(2) * r[i];                         // :43
+                    if (ww) gr = ww[i] * gr;                    // :44-45
+                    const T* row = Jb + (size_t)i * P + p0;
+#pragma unroll
+                    for (int k = 0; k < kLsqCols; ++k)
+                        if (p0 + k < P) acc[k] = fma_t(gr, row[k], acc[k]);
                 }
-                __syncthreads();
-                red[t] = acc;
-                __syncthreads();
-                if (t < Pc) {
-                    T sum = T(0);
-                    for (int g2 = 0; g2 < groups; ++g2) sum += red[g2 * Pc + t];
-                    grad[(size_t)b * P + p0 + t] = sum;
+#pragma unroll
+                for (int k = 0; k < kLsqCols; ++k) {
+                    const T sum = lsq_warp_sum(acc[k]);
+                    if (lane == 0 && p0 + k < P) grad[(size_t)b * P + p0 + k] = sum;
                 }
             }
         }
@@ -309,7 +355,8 @@ template <typename T>
 int launch_least_squares(int B, int R, int P, const T* res, const T* jac, const T* w, T* err, T* grad,
                          cudaStream_t s) {
     if (B == 0) return DAVO_OK;
-    const int grid = B < 148 * 16 ? B : 148 * 16;
+    const long long ctas = ((long long)B + kLsqThreads / 32 - 1) / (kLsqThreads / 32);
+    const int grid = (int)(ctas < 148LL * 8 ? ctas : 148LL * 8);
     least_squares_kernel<T><<<grid, kLsqThreads, 0, s>>>(B, R, P, res, jac, w, err, grad);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
@@ -369,10 +416,119 @@ __global__ void __launch_bounds__(128) bfgs_update_kernel(int K, int n, T* __res
     }
 }
 
+// n <= 16 (the calibration fits: n = 10): a GROUP of n lanes per problem, 32 / n problems per warp.  Lane i of a
+// group keeps row i of H in registers; columns are reached through a padded shared-memory copy.  Every sum runs in
+// the same order with the same separately rounded operations as the kernel above and the oracle (bit-identical
+// results), but all lanes stream memory: the one-warp-per-problem kernel reached 5 % of the HBM rate at n = 10.
+constexpr int kSmallN = 16;
+
+__host__ __device__ inline int bfgs_small_group_words(int n) { return ((n * (n + 1) + 3) & ~3) + 4 * kSmallN; }
+
+// read a 16-entry, 16-byte aligned shared vector into registers with vector loads
+template <typename T>
+__device__ __forceinline__ void load16(const T* v, int n, T (&out)[kSmallN]) {
+    using V4 = typename Vec4<T>::type;
+    const V4* v4 = reinterpret_cast<const V4*>(v);
+#pragma unroll
+    for (int k = 0; k < kSmallN / 4; ++k)
+        if (4 * k < n) {
+            const V4 t = v4[k];
+            out[4 * k] = t.x; out[4 * k + 1] = t.y; out[4 * k + 2] = t.z; out[4 * k + 3] = t.w;
+        }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) bfgs_update_small_kernel(int K, int n, T* __restrict__ H,
+                                                                const T* __restrict__ s_, const T* __restrict__ y_) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int G = 32 / n;                       // problems per warp
+    const int q = lane / n, i = lane - q * n;   // group, row
+    const bool member = q < G;
+    const int ld = n + 1;
+    T* base = reinterpret_cast<T*>(raw) + ((size_t)warp * G + (member ? q : 0)) * bfgs_small_group_words(n);
+    T* Hs = base;
+    T* ss = Hs + ((n * ld + 3) & ~3);           // four 16-entry vectors, 16-byte aligned
+    T* ys = ss + kSmallN;
+    T* yHs = ys + kSmallN;
+    T* srs = yHs + kSmallN;
+    const long long groups = (long long)gridDim.x * warps * G;
+    for (long long b0 = ((long long)blockIdx.x * warps + warp) * G; b0 < K; b0 += groups) {
+        const long long b = b0 + q;
+        const bool on = member && b < K;
+        T row[kSmallN];
+        T si = T(0);
+        T* Hg = H + (size_t)(on ? b : 0) * n * n + (size_t)i * n;
+        __syncwarp();
+        if (on) {
+#pragma unroll
+            for (int j = 0; j < kSmallN; ++j)
+                if (j < n) {
+                    row[j] = Hg[j];
+                    Hs[i * ld + j] = row[j];
+                }
+            si = s_[(size_t)b * n + i];
+            ss[i] = si;
+            ys[i] = y_[(size_t)b * n + i];
+        }
+        __syncwarp();
+        T rho = T(0), Hy = T(0), sr = T(0);
+        T sv[kSmallN], yv[kSmallN];
+        if (on) {
+            load16(ss, n, sv);
+            load16(ys, n, yv);
+            T c = T(0);                                       // func_inverse_curvature.py:8-11
+#pragma unroll
+            for (int j = 0; j < kSmallN; ++j)
+                if (j < n) c = add_rn(c, mul_rn(sv[j], yv[j]));
+            rho = div_rn(T(1), c);
+            if (c <= T(0)) rho = T(0);
+            T a = T(0);                                       // (y^T H)_i from column i, bfgs_solver.py:268-270
+#pragma unroll
+            for (int k = 0; k < kSmallN; ++k)
+                if (k < n) a = add_rn(a, mul_rn(yv[k], Hs[k * ld + i]));
+            yHs[i] = a;
+#pragma unroll
+            for (int j = 0; j < kSmallN; ++j)                 // (H y)_i from row i, :293-295
+                if (j < n) Hy = add_rn(Hy, mul_rn(row[j], yv[j]));
+            sr = mul_rn(si, rho);                             // :277
+            srs[i] = sr;
+        }
+        __syncwarp();
+        if (on) {
+            T yHv[kSmallN], srv[kSmallN];
+            load16(yHs, n, yHv);
+            load16(srs, n, srv);
+            T qq = T(0);                                      // :271-274
+#pragma unroll
+            for (int j = 0; j < kSmallN; ++j)
+                if (j < n) qq = add_rn(qq, mul_rn(yHv[j], mul_rn(yv[j], rho)));
+            const T onepq = add_rn(T(1), qq);
+#pragma unroll
+            for (int j = 0; j < kSmallN; ++j)                 // :278-303
+                if (j < n) {
+                    const T sop = mul_rn(mul_rn(sr, sv[j]), onepq);
+                    const T sgp = mul_rn(sr, yHv[j]);
+                    const T gsp = mul_rn(Hy, srv[j]);
+                    Hg[j] = sub_rn(sub_rn(add_rn(row[j], sop), sgp), gsp);
+                }
+        }
+    }
+}
+
 template <typename T>
 int launch_bfgs_update(int k, int n, T* H, const T* s_, const T* y, cudaStream_t s) {
     if (k == 0) return DAVO_OK;
     if (n < 1 || n > 96) return DAVO_ERR_UNSUPPORTED;
+    if (n <= kSmallN) {
+        const int G = 32 / n, warps = 4;
+        const size_t smem = (size_t)warps * G * bfgs_small_group_words(n) * sizeof(T);
+        long long grid = ((long long)k + warps * G - 1) / (warps * G);
+        if (grid > 148LL * 16) grid = 148LL * 16;
+        bfgs_update_small_kernel<T><<<(unsigned)grid, warps * 32, smem, s>>>(k, n, H, s_, y);
+        count_launch();
+        return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+    }
     const size_t per_warp = ((size_t)n * (n + 1) + 5 * (size_t)n) * sizeof(T);
     const int warps = (4 * per_warp <= 160 * 1024) ? 4 : 1;
     const size_t smem = warps * per_warp;
