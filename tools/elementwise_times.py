@@ -7,7 +7,7 @@ hd = rows[h]; ki = hd.index("Kernel Name"); mi = hd.index("Metric Name"); vi = h
 d = collections.defaultdict(lambda: collections.defaultdict(list))
 scale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 for r in rows[h + 2:]:
-    if len(r) > vi and "davo" in r[ki]:
+    if len(r) > vi and ("davo" in r[ki] or "_kernel<" in r[ki]) and "at::" not in r[ki]:
         d[r[ki][:64]][r[mi]].append(float(r[vi].replace(",", "")) * scale.get(r[ui], 1.0))
 med = lambda L: sorted(L)[len(L) // 2]
 for k, m in d.items():
