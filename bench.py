@@ -82,6 +82,11 @@ def workload_name(config: str, B: int) -> str:
                   f"4 views x 8 points, n=45"}[config]
 
 
+def bench_config(config: str, B: int, solver_kw: dict) -> dict:
+    """The `config` object of the JSON line: identical on the GPU arm and on `--impl reference`."""
+    return {"workload": workload_name(config, B), "problems_per_gpu": B, "solver": solver_kw, "seed": "0xB200 + rank"}
+
+
 def algorithmic_flops(batch, fevals: np.ndarray, iters: np.ndarray) -> float:
     """sum fevals * matches * F_fg + sum iters * (12 n^2 + 10 n), with the reference-equivalent
     evaluation count (what the reference's algorithm evaluates, not what the kernel skipped by reuse)."""
@@ -173,7 +178,7 @@ def run_reference_arm(args):
             "bfgs_iters_per_sec": float(np.mean([r["iters_per_s"] for r in res])),
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.config, B), "sample_per_step": res[-1]["sample"]},
+            "config": bench_config(args.config, B, SOLVER_KW[args.config]),
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": res[-1]["cores"], "kind": "port",
                              "sample": res[-1]["sample"]},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -218,6 +223,9 @@ def main():
                     help="arithmetic type (BASELINE asks for f32; the entry script itself trains in f64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-side-configs", action="store_true",
+                    help="skip the 'configs' object (cfg3, cfg4, bundle adjustment, cfg5 strong scaling)")
+    ap.add_argument("--side-steps", type=int, default=5, help="timed steps per side configuration")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -251,51 +259,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B = args.batch or default_B(args.config, world)
-    np_dt = np.float64 if args.dtype == "f64" else np.float32
-    t_dt = torch.float64 if args.dtype == "f64" else torch.float32
-    esz = 8 if args.dtype == "f64" else 4
-    batch = make_batch(args.config, B, 0xB200 + rank, np_dt)
-    kw = SOLVER_KW[args.config]
-    solver = davo_b200.BFGSSolver(**kw).eval()
-    steps, warm = args.steps, max(args.warmup, 3)
-
-    # ---- raw inputs resident in HBM (value) and in pinned host memory (e2e) ------------------------------
-    # (angle_ba has no 3-D points: its second input is the visibility mask)
-    second = batch.weights if batch.model == "angle_ba" else batch.points_3d
-    h_pts = torch.from_numpy(second).pin_memory()
-    h_obs = torch.from_numpy(batch.obs).pin_memory()
-    h_x0 = torch.from_numpy(batch.x0).pin_memory()
-    d_pts, d_obs, d_x0 = h_pts.to(dev), h_obs.to(dev), h_x0.to(dev)
-    input_bytes = (h_pts.numel() + h_obs.numel() + h_x0.numel()) * esz
-    # timing rule: inputs larger than L2, or flush L2 between timed iterations (outside the per-step events)
-    flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev) if input_bytes <= L2_BYTES else None
-    slab = ResultSlab(B * world, batch.n, t_dt, world, dev)
-    out = slab.buffers(rank)
-
-    def make_objective(pts, obs):
-        if batch.model == "distort10":
-            return davo_b200.DistortionObjective(pts, obs)  # runs davo_stage_matches
-        if batch.model == "angle_ba":
-            return davo_b200.AngleDistanceObjective(obs, pts)
-        return davo_b200.JointPoseObjective(pts, obs)
-
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-
-    def step(record=False):
-        if flush is not None:
-            flush.zero_()
-        if record:
-            ev[0].record()
-        obj = make_objective(d_pts, d_obs)
-        if record:
-            ev[1].record()
-        solver.solve_into(d_x0, obj, out=out)
-        if record:
-            ev[2].record()
-        slab.all_gather(rank)
-        if record:
-            ev[3].record()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    props = torch.cuda.get_device_properties(dev)
+    try:
+        traffic_json = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except OSError:
+        traffic_json = {}
 
     def barrier():
         torch.cuda.synchronize()
@@ -303,134 +276,210 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(warm):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = _lib.launch_count()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    solve_ms, stage_ms, step_ms = [], [], []
-    barrier()
-    t_start.record()
-    for _ in range(steps):
-        step(record=True)
-        # per-kernel events are read after the loop; recording them does not synchronise
-        solve_ms.append((ev[1], ev[2]))
-        stage_ms.append((ev[0], ev[1]))
-        step_ms.append((ev[0], ev[3]))
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    t_end.record()
-    barrier()
-    launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    # with an L2 flush between the steps the timed region is the sum of the per-step event pairs (flush excluded)
-    total_ms = (t_start.elapsed_time(t_end) if flush is None
-                else float(sum(a.elapsed_time(b) for a, b in step_ms)))
-    solve_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in solve_ms]))
-    stage_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in stage_ms]))
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / steps
+    def measure(config: str, B: int, dtype: str, steps: int, warm: int, solver_kw: dict, with_e2e: bool,
+                with_clocks: bool):
+        """One workload: W warm-up steps, K timed steps (stage + solve (+ all-gather)), device-timed, max over ranks.
+        Returns the fields of the JSON line that describe this workload."""
+        np_dt = np.float64 if dtype == "f64" else np.float32
+        t_dt = torch.float64 if dtype == "f64" else torch.float32
+        esz = 8 if dtype == "f64" else 4
+        batch = make_batch(config, B, 0xB200 + rank, np_dt)
+        solver = davo_b200.BFGSSolver(**solver_kw).eval()
 
-    iters = out.iterations.cpu().numpy()
-    fevals = out.evaluations.cpu().numpy()
-    converged = float(out.converged.float().mean().item())
-    reasons = np.bincount(out.reason.cpu().numpy(), minlength=4).tolist()
-    stats = torch.tensor([float(iters.sum()), float(fevals.sum()), converged * B], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(stats)
-    total_B = B * world
-    value = total_B / (ms_per_step * 1e-3)
+        # ---- raw inputs resident in HBM (value) and in pinned host memory (e2e) ------------------------------
+        # (angle_ba has no 3-D points: its second input is the visibility mask)
+        second = batch.weights if batch.model == "angle_ba" else batch.points_3d
+        h_pts, h_obs, h_x0 = (torch.from_numpy(a) for a in (second, batch.obs, batch.x0))
+        if with_e2e:
+            h_pts, h_obs, h_x0 = h_pts.pin_memory(), h_obs.pin_memory(), h_x0.pin_memory()
+        d_pts, d_obs, d_x0 = h_pts.to(dev), h_obs.to(dev), h_x0.to(dev)
+        input_bytes = (h_pts.numel() + h_obs.numel() + h_x0.numel()) * esz
+        # timing rule: inputs larger than L2, or flush L2 between timed iterations (outside the per-step events)
+        flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev) if input_bytes <= L2_BYTES else None
+        slab = ResultSlab(B * world, batch.n, t_dt, world, dev)
+        out = slab.buffers(rank)
 
-    # ---- e2e: the public call with host buffers, H2D + D2H inside the timed region -------------------------
-    e2e = None
-    if not args.no_e2e:
-        def e2e_step():
-            obj = make_objective(h_pts, h_obs)                       # H2D of points + observations, staging
-            info = solver(h_x0, obj, return_info=True)               # H2D of x0, solve, D2H of every output
-            return info
-        for _ in range(2):
-            e2e_step()
+        def make_objective(pts, obs):
+            if batch.model == "distort10":
+                return davo_b200.DistortionObjective(pts, obs)  # runs davo_stage_matches
+            if batch.model == "angle_ba":
+                return davo_b200.AngleDistanceObjective(obs, pts)
+            return davo_b200.JointPoseObjective(pts, obs)
+
+        def step(ev=None):
+            if flush is not None:
+                flush.zero_()
+            if ev:
+                ev[0].record()
+            obj = make_objective(d_pts, d_obs)
+            if ev:
+                ev[1].record()
+            solver.solve_into(d_x0, obj, out=out)
+            if ev:
+                ev[2].record()
+            slab.all_gather(rank)
+            if ev:
+                ev[3].record()
+
+        for _ in range(warm):
+            step()
         barrier()
-        t0 = time.perf_counter()
+        sampler = ClockSampler(local)
+        if rank == 0 and with_clocks:
+            sampler.start()
+        launches0 = _lib.launch_count()
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        events = []
+        barrier()
+        t_start.record()
         for _ in range(steps):
-            info = e2e_step()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            step(ev)  # per-kernel events are read after the loop; recording them does not synchronise
+            events.append(ev)
+        t_end.record()
         barrier()
-        e2e_s = (time.perf_counter() - t0) / steps
+        launches = _lib.launch_count() - launches0
+        clocks = sampler.stop() if (rank == 0 and with_clocks) else None
+        # with an L2 flush between the steps the timed region is the sum of the per-step event pairs (flush excluded)
+        total_ms = (t_start.elapsed_time(t_end) if flush is None
+                    else float(sum(e[0].elapsed_time(e[3]) for e in events)))
+        solve_kernel_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
+        stage_kernel_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
         if world > 1:
-            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        h2d = input_bytes
-        d2h = sum(t.numel() * t.element_size() for t in info)
-        e2e = {"value": total_B / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3}
+            total_ms = float(t.item())
+        ms_per_step = total_ms / steps
+
+        iters = out.iterations.cpu().numpy()
+        fevals = out.evaluations.cpu().numpy()
+        converged = float(out.converged.float().mean().item())
+        reasons = np.bincount(out.reason.cpu().numpy(), minlength=4).tolist()
+        stats = torch.tensor([float(iters.sum()), float(fevals.sum()), converged * B], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(stats)
+        total_B = B * world
+        value = total_B / (ms_per_step * 1e-3)
+
+        # ---- e2e: the public call with host buffers, H2D + D2H inside the timed region -----------------------
+        e2e = None
+        if with_e2e:
+            def e2e_step():
+                obj = make_objective(h_pts, h_obs)                       # H2D of points + observations, staging
+                return solver(h_x0, obj, return_info=True)               # H2D of x0, solve, D2H of every output
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                info = e2e_step()
+            barrier()
+            e2e_s = (time.perf_counter() - t0) / steps
+            if world > 1:
+                t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t.item())
+            d2h = sum(t.numel() * t.element_size() for t in info)
+            e2e = {"value": total_B / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(input_bytes),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                   "h2d_gbs_per_gpu": input_bytes / e2e_s / 1e9,
+                   "note": "bound by the host-to-device copy of the raw inputs (tools/h2d_probe.py measures the "
+                           "plain-copy ceiling of the same bytes; DESIGN.md section 6)"}
+
+        # ---- roofline of the dominant kernel (the solve kernel): FP32 / FP64 CUDA-core pipe ------------------
+        sm_max_mhz = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+        lanes = 128 if dtype == "f32" else 64   # FP32 / FP64 CUDA-core lanes per SM on B200
+        pipe_peak = props.multi_processor_count * lanes * 2 * sm_max_mhz * 1e6 / 1e12   # TFLOP/s
+        flops = algorithmic_flops(batch, fevals, iters)                                 # this rank's launch
+        achieved = flops / (solve_kernel_ms * 1e-3) / 1e12
+        stage_bytes = batch.N * B * (20 + 16) * (esz // 4) if batch.model == "distort10" else 0
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        stage_gbs = stage_bytes / (stage_kernel_ms * 1e-3) / 1e9 if stage_bytes else None
+        traffic = stage_traffic = None
+        try:  # DRAM bytes per launch of the solve kernel from the committed ncu --set full capture of this workload
+            if B == default_B(config, world) and config in ("cfg2", "cfg3", "cfg4") and dtype == "f32":
+                traffic = traffic_json["solve_" + config]["bytes"]
+            if config == "ba" and dtype == "f32":   # captured at 32K problems: scale to this launch
+                traffic = int(traffic_json["solve_ba"]["bytes"] * B / traffic_json["solve_ba"]["problems"])
+            stage_traffic = traffic_json["stage_cfg2"]["bytes"] if (config == "cfg2" and B == default_B("cfg2")) else None
+        except KeyError:
+            pass
+        res = {
+            "value": value, "unit": "solves/s",
+            "bfgs_iters_per_sec": float(stats[0].item()) / (ms_per_step * 1e-3),
+            "fevals_per_sec": float(stats[1].item()) / (ms_per_step * 1e-3),
+            "converged_frac": float(stats[2].item()) / total_B,
+            "steps": steps, "warmup": warm, "ms_per_step": ms_per_step, "dtype": dtype,
+            "config": bench_config(config, B, solver_kw),
+            "timing": {"l2": (f"inputs larger than L2 ({input_bytes / 1e6:.0f} MB of raw inputs per GPU)" if flush is None
+                              else f"L2 flushed between timed steps (a {2 * L2_BYTES >> 20} MiB buffer is rewritten, "
+                                   f"outside the per-step events; inputs are {input_bytes / 1e6:.0f} MB per GPU)"),
+                       "collective": "one all_gather_into_tensor of the solved records"
+                       if world > 1 else "none (single GPU)"},
+            "kernel_ms": {"solve": solve_kernel_ms, "stage": stage_kernel_ms},
+            "mean_iters": float(iters.mean()), "mean_fevals": float(fevals.mean()), "reasons_rank0": reasons,
+            "roofline": {"bound": "fp32" if dtype == "f32" else "fp64", "achieved": achieved, "peak": pipe_peak,
+                         "unit": "TFLOP/s", "frac": achieved / pipe_peak, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per launch (ncu); the kernel is FP32-pipe bound, its per-problem "
+                                         "inputs are read from HBM once and kept in shared memory",
+                         # evaluations the kernel really ran = reference-equivalent evaluations - reused probes
+                         "executed_frac": achieved / pipe_peak * float((fevals - iters).sum()) / max(float(fevals.sum()), 1.0),
+                         "peak_source": f"{props.multi_processor_count} SMs x {lanes} lanes x 2 x {sm_max_mhz:.0f} MHz "
+                                        "(no FP32 figure in MEASURED_PEAKS.json; sm_max_mhz taken from it)",
+                         "flops_counted": "SURVEY.md 8(d): reference-equivalent fevals x matches x "
+                                          f"{FLOP_PER_MATCH_EVAL[batch.model]:.0f} + iters x (12n^2+10n)"},
+            "roofline_staging": None if stage_gbs is None else {
+                "bound": "hbm", "achieved": stage_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,
+                "traffic": stage_traffic, "bytes_counted": "20 B read + 16 B written per match"},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+        }
+        del d_pts, d_obs, d_x0, slab, out, flush
+        torch.cuda.empty_cache()
+        return res
+
+    B = args.batch or default_B(args.config, world)
+    kw = SOLVER_KW[args.config]
+    steps, warm = args.steps, max(args.warmup, 3)
+    head = measure(args.config, B, args.dtype, steps, warm, kw, with_e2e=not args.no_e2e, with_clocks=True)
+
+    # ---- the other BASELINE configurations, on the record beside the headline (fewer steps each) ---------------
+    side = {}
+    if not args.no_side_configs and args.config == "cfg2" and not args.batch:
+        side_steps = max(3, min(steps, args.side_steps))
+        plan = [("cfg5_strong", "cfg5", "f32", SOLVER_KW["cfg5"])]
+        if world == 1:
+            plan = [("cfg3", "cfg3", "f32", SOLVER_KW["cfg3"]), ("cfg4", "cfg4", "f32", SOLVER_KW["cfg4"]),
+                    ("ba_f32_thr1e-4", "ba", "f32", dict(error_threshold=1e-4, iterations=1000)),
+                    ("ba_f64_thr1e-7", "ba", "f64", SOLVER_KW["ba"])] + plan
+        for label, cfg, dt, skw in plan:
+            r = measure(cfg, default_B(cfg, world), dt, side_steps, 3, skw, with_e2e=False, with_clocks=False)
+            side[label] = {"workload": r["config"]["workload"], "solver": skw, "dtype": dt, "value": r["value"],
+                           "unit": "solves/s", "ms_per_step": r["ms_per_step"], "steps": side_steps,
+                           "kernel_ms": r["kernel_ms"]["solve"], "bfgs_iters_per_sec": r["bfgs_iters_per_sec"],
+                           "mean_iters": r["mean_iters"], "mean_fevals": r["mean_fevals"],
+                           "converged_frac": r["converged_frac"], "reasons_rank0": r["reasons_rank0"],
+                           "roofline": {"frac": r["roofline"]["frac"], "executed_frac": r["roofline"]["executed_frac"],
+                                        "achieved": r["roofline"]["achieved"], "peak": r["roofline"]["peak"],
+                                        "unit": "TFLOP/s", "bound": r["roofline"]["bound"]},
+                           "scaling": "strong" if cfg == "cfg5" else "weak", "n_gpus": world,
+                           "l2": r["timing"]["l2"]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (the solve kernel): FP32 CUDA-core pipe ----------------------------
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    props = torch.cuda.get_device_properties(dev)
-    sm_max_mhz = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
-    lanes = 128 if args.dtype == "f32" else 64   # FP32 / FP64 CUDA-core lanes per SM on B200
-    fp32_peak = props.multi_processor_count * lanes * 2 * sm_max_mhz * 1e6 / 1e12   # TFLOP/s
-    flops = algorithmic_flops(batch, fevals, iters)                                # this rank's launch
-    achieved = flops / (solve_kernel_ms * 1e-3) / 1e12
-    stage_bytes = batch.N * B * (20 + 16) * (esz // 4) if batch.model == "distort10" else 0  # read 20 B, write 16 B per match (f32)
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    stage_gbs = stage_bytes / (stage_kernel_ms * 1e-3) / 1e9 if stage_bytes else None
-
-    traffic = stage_traffic = None
-    try:  # DRAM bytes per launch of the solve kernel from the committed ncu --set full capture of this workload
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if B == default_B(args.config, world) and args.config in ("cfg2", "cfg3", "cfg4") and args.dtype == "f32":
-            traffic = tj["solve_" + args.config]["bytes"]
-        if args.config == "ba" and args.dtype == "f32":   # captured at 32K problems: scale to this launch
-            traffic = int(tj["solve_ba"]["bytes"] * B / tj["solve_ba"]["problems"])
-        stage_traffic = tj["stage_cfg2"]["bytes"] if (args.config == "cfg2" and B == default_B("cfg2")) else None
-    except (OSError, KeyError):
-        pass
-    line = {
-        "metric": "calibration_solves_per_sec", "value": value, "unit": "solves/s",
-        "bfgs_iters_per_sec": float(stats[0].item()) / (ms_per_step * 1e-3),
-        "fevals_per_sec": float(stats[1].item()) / (ms_per_step * 1e-3),
-        "converged_frac": float(stats[2].item()) / total_B,
-        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None, "dtype": args.dtype,
-        "data": "synthetic",
-        "config": {"workload": workload_name(args.config, B), "problems_per_gpu": B, "solver": kw,
-                   "l2": (f"inputs larger than L2 ({input_bytes / 1e6:.0f} MB of raw inputs per GPU)" if flush is None
-                          else f"L2 flushed between timed steps (a {2 * L2_BYTES >> 20} MiB buffer is rewritten, outside "
-                               f"the per-step events; inputs are {input_bytes / 1e6:.0f} MB per GPU)"),
-                   "seed": "0xB200 + rank", "collective": "one all_gather_into_tensor of the solved records"
-                   if world > 1 else "none (single GPU)"},
-        "kernel_ms": {"solve": solve_kernel_ms, "stage": stage_kernel_ms},
-        "mean_iters": float(iters.mean()), "mean_fevals": float(fevals.mean()), "reasons_rank0": reasons,
-        "roofline": {"bound": "fp32" if args.dtype == "f32" else "fp64", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": achieved / fp32_peak, "traffic": traffic,
-                     "traffic_note": "DRAM bytes per launch (ncu); the kernel is FP32-pipe bound, its per-problem inputs "
-                                     "are read from HBM once and kept in shared memory",
-                     "executed_frac": achieved / fp32_peak * float((fevals - iters).sum()) / float(fevals.sum()),
-                     "peak_source": f"{props.multi_processor_count} SMs x {lanes} lanes x 2 x {sm_max_mhz:.0f} MHz "
-                                    "(no FP32 figure in MEASURED_PEAKS.json; sm_max_mhz taken from it)",
-                     "flops_counted": "SURVEY.md 8(d): reference-equivalent fevals x matches x "
-                                      f"{FLOP_PER_MATCH_EVAL[batch.model]:.0f} + iters x (12n^2+10n)"},
-        "roofline_staging": None if stage_gbs is None else {
-            "bound": "hbm", "achieved": stage_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak,
-            "traffic": stage_traffic, "bytes_counted": "20 B read + 16 B written per match"},
-        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-    }
+    line = {"metric": "calibration_solves_per_sec", "value": head["value"], "unit": "solves/s",
+            "bfgs_iters_per_sec": head["bfgs_iters_per_sec"], "fevals_per_sec": head["fevals_per_sec"],
+            "converged_frac": head["converged_frac"], "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic"}
+    for k in ("config", "timing", "kernel_ms", "mean_iters", "mean_fevals", "reasons_rank0", "roofline", "roofline_staging",
+              "clocks", "gpu_launches", "e2e"):
+        line[k] = head[k]
+    if side:
+        line["configs"] = side
     if not args.no_cpu_baseline and world == 1:
         c = cpu_arm(args.config, B, 15.0)
         line["cpu_baseline"] = {"value": c["value"], "unit": "solves/s", "cores": c["cores"], "kind": "port",

@@ -28,7 +28,8 @@ REASON_NAMES = {0: "threshold", 1: "step", 2: "cap", 3: "nan"}
 # every symbol include/davo_b200.h declares (tests check the library exports all of them)
 EXPORTED = ("davo_abi_version", "davo_strerror", "davo_launch_count", "davo_solve_calibration",
             "davo_eval_cost_grad", "davo_line_search", "davo_stage_matches", "davo_project",
-            "davo_project_jacobian", "davo_least_squares", "davo_bfgs_update", "davo_bfgs_initial_scale")
+            "davo_project_jacobian", "davo_least_squares", "davo_bfgs_update", "davo_bfgs_initial_scale",
+            "davo_generate_distort10", "davo_generate_joint", "davo_generate_views_and_points")
 
 
 class ProblemDesc(ctypes.Structure):
@@ -37,6 +38,14 @@ class ProblemDesc(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in
                 ("B", "N", "V", "n", "model", "dtype", "max_iters", "max_ls_iters", "strong", "has_weights")] + \
                [(k, ctypes.c_double) for k in ("sufficient_decrease", "curvature", "error_threshold", "minimum_step")]
+
+
+class GeneratorDesc(ctypes.Structure):
+    """davo_generator_desc (include/davo_b200.h)."""
+
+    _fields_ = [(k, ctypes.c_int32) for k in ("B", "N", "V", "dtype", "ill_conditioned", "random_pose")] + \
+               [("seed", ctypes.c_uint64), ("first_problem", ctypes.c_uint64)] + \
+               [(k, ctypes.c_double) for k in ("fov", "noise", "pathological", "start_noise", "min_camera_distance")]
 
 
 class DavoError(RuntimeError):
@@ -80,6 +89,10 @@ def lib() -> ctypes.CDLL:
         L.davo_least_squares.argtypes = [i32] * 4 + [vp] * 6
         L.davo_bfgs_update.argtypes = [i32] * 3 + [vp] * 4
         L.davo_bfgs_initial_scale.argtypes = [i32] * 3 + [vp] * 4
+        gp = ctypes.POINTER(GeneratorDesc)
+        L.davo_generate_distort10.argtypes = [gp] + [vp] * 6
+        L.davo_generate_joint.argtypes = [gp] + [vp] * 5
+        L.davo_generate_views_and_points.argtypes = [gp] + [vp] * 9
         for name in EXPORTED[3:]:
             getattr(L, name).restype = ctypes.c_int
         if L.davo_abi_version() != ABI_VERSION:

@@ -50,6 +50,9 @@ def compute_distorted_camera_model(points_3d: torch.Tensor, parameters: torch.Te
     """points_3d [B,N,3], parameters [B,16] -> (u'[B,N], v'[B,N]).  Differentiable with respect to `parameters`
     (the reference's TorchScript function is differentiated by autograd; here the analytic Jacobian is used);
     `points_3d` is treated as data."""
+    if points_3d.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("compute_distorted_camera_model is differentiable with respect to `parameters` "
+                                  "only; points_3d is treated as data (detach it)")
     if parameters.requires_grad and torch.is_grad_enabled():
         return _ProjectWithGrad.apply(points_3d, parameters)
     device, dt, pts, th = _prepare(points_3d, parameters)

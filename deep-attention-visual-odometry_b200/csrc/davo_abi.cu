@@ -2,6 +2,9 @@
 // descriptor -> typed device parameters, dispatch to the kernel launchers.  No torch types, no
 // allocation, no host synchronisation.
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "davo_common.cuh"
 #include "launch.h"
@@ -9,6 +12,21 @@
 namespace davo {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool ensure_dynamic_smem(const void* kernel, size_t smem) {
+    if (smem <= 48 * 1024) return true;
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;  // (device, kernel) -> bytes opted in so far
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = granted[{dev, kernel}];
+    if (smem <= have) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return false;
+    have = smem;
+    return true;
+}
 
 #if DAVO_TRACE
 static void* g_trace = nullptr;
@@ -269,6 +287,63 @@ int davo_bfgs_initial_scale(int32_t dtype, int32_t k, int32_t n, const void* s_,
         return launch_bfgs_initial_scale<double>(k, n, static_cast<const double*>(s_),
                                                  static_cast<const double*>(y), static_cast<double*>(scale), s);
     return DAVO_ERR_UNSUPPORTED;
+}
+
+static int check_gen(const davo_generator_desc* d, int min_views) {
+    if (!d) return DAVO_ERR_NULL_POINTER;
+    if (d->B < 0 || d->N < 1 || d->V < min_views) return DAVO_ERR_BAD_SHAPE;
+    if (d->dtype != DAVO_F32 && d->dtype != DAVO_F64) return DAVO_ERR_UNSUPPORTED;
+    if (!(d->fov > 0.0) || d->noise < 0.0 || d->pathological < 0.0 || d->pathological > 1.0) return DAVO_ERR_BAD_ARGUMENT;
+    return DAVO_OK;
+}
+
+int davo_generate_distort10(const davo_generator_desc* desc, void* points_3d, void* obs, void* pose, void* x0,
+                            void* truth, void* stream) {
+    int st = check_gen(desc, 1);
+    if (st) return st;
+    if (desc->B == 0) return DAVO_OK;
+    if (!points_3d || !obs || !x0) return DAVO_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (desc->dtype == DAVO_F32)
+        return launch_generate_distort10<float>(desc, static_cast<float*>(points_3d), static_cast<float*>(obs),
+                                                static_cast<float*>(pose), static_cast<float*>(x0),
+                                                static_cast<float*>(truth), s);
+    return launch_generate_distort10<double>(desc, static_cast<double*>(points_3d), static_cast<double*>(obs),
+                                             static_cast<double*>(pose), static_cast<double*>(x0),
+                                             static_cast<double*>(truth), s);
+}
+
+int davo_generate_joint(const davo_generator_desc* desc, void* points_3d, void* obs, void* x0, void* truth,
+                        void* stream) {
+    int st = check_gen(desc, 1);
+    if (st) return st;
+    if (desc->B == 0) return DAVO_OK;
+    if (!points_3d || !obs || !x0) return DAVO_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (desc->dtype == DAVO_F32)
+        return launch_generate_joint<float>(desc, static_cast<float*>(points_3d), static_cast<float*>(obs),
+                                            static_cast<float*>(x0), static_cast<float*>(truth), s);
+    return launch_generate_joint<double>(desc, static_cast<double*>(points_3d), static_cast<double*>(obs),
+                                         static_cast<double*>(x0), static_cast<double*>(truth), s);
+}
+
+int davo_generate_views_and_points(const davo_generator_desc* desc, void* projected_points, void* visibility_mask,
+                                   void* camera_intrinsics, void* camera_orientations, void* camera_translations,
+                                   void* world_points, void* x0, void* truth, void* stream) {
+    int st = check_gen(desc, 2);
+    if (st) return st;
+    if (desc->B == 0) return DAVO_OK;
+    if (!projected_points || !visibility_mask || !camera_intrinsics || !camera_orientations || !camera_translations ||
+        !world_points)
+        return DAVO_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define DAVO_GEN_VIEWS(T)                                                                                         \
+    launch_generate_views<T>(desc, static_cast<T*>(projected_points), static_cast<T*>(visibility_mask),           \
+                             static_cast<T*>(camera_intrinsics), static_cast<T*>(camera_orientations),            \
+                             static_cast<T*>(camera_translations), static_cast<T*>(world_points),                 \
+                             static_cast<T*>(x0), static_cast<T*>(truth), s)
+    return desc->dtype == DAVO_F32 ? DAVO_GEN_VIEWS(float) : DAVO_GEN_VIEWS(double);
+#undef DAVO_GEN_VIEWS
 }
 
 }  // extern "C"

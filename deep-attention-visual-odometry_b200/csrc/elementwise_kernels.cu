@@ -33,7 +33,12 @@ __device__ void euler_matrices(T rx, T ry, T rz, T* Rm, T* dRx, T* dRy, T* dRz) 
     }
 }
 
-// X' = R X + t with the reference's un-fused left-to-right sums; z' == 0 -> += 1e-8 (:38-57).
+// X' = R X + t as un-fused left-to-right sums of separately rounded products; z' == 0 -> += 1e-8 (:38-57).
+// The entries of R are rounded first and then multiplied by the coordinate.  The reference multiplies the
+// coordinate by each trigonometric factor in turn in four places ((X cy) cz, (X cy) sz, (Y sx) cy, (Z cx) cy,
+// :39,:45,:52-53), so a float32 X' can differ from the reference's in the last bit: parity of the staged matches
+// and of the forward model is a TOLERANCE (tests: rtol 3e-6 / 2e-5 in float32, 1e-12 in float64), not bitwise,
+// except for the identity pose, where every product is exact.
 template <typename T>
 __device__ __forceinline__ void transform_point(const T* Rm, const T* t, T X, T Y, T Z, T& xp, T& yp, T& zp) {
     xp = add_rn(add_rn(add_rn(mul_rn(X, Rm[0]), mul_rn(Y, Rm[1])), mul_rn(Z, Rm[2])), t[0]);
@@ -533,8 +538,7 @@ int launch_bfgs_update(int k, int n, T* H, const T* s_, const T* y, cudaStream_t
     const int warps = (4 * per_warp <= 160 * 1024) ? 4 : 1;
     const size_t smem = warps * per_warp;
     auto kernel = bfgs_update_kernel<T>;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (!ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem))
         return DAVO_ERR_CUDA;
     int grid = (k + warps - 1) / warps;
     if (grid > 148 * 8) grid = 148 * 8;

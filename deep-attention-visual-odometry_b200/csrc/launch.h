@@ -7,6 +7,11 @@ namespace davo {
 
 void count_launch();  // increments the process-wide counter behind davo_launch_count()
 
+// Opt a kernel in to `smem` bytes of dynamic shared memory.  The attribute is process-wide per (device, kernel), so
+// it is only ever RAISED, under a mutex: two host threads launching the same kernel with different N cannot lower
+// each other's limit between the set and the launch.  Returns false on a CUDA error.
+bool ensure_dynamic_smem(const void* kernel, size_t smem);
+
 int launch_solve_warp_f32(const SolveParams<float>& p, cudaStream_t s);
 int launch_solve_warp_f64(const SolveParams<double>& p, cudaStream_t s);
 int launch_line_search_warp_f32(const SolveParams<float>& p, cudaStream_t s);
@@ -39,5 +44,13 @@ template <typename T>
 int launch_bfgs_update(int k, int n, T* H, const T* s_, const T* y, cudaStream_t s);
 template <typename T>
 int launch_bfgs_initial_scale(int k, int n, const T* s_, const T* y, T* scale, cudaStream_t s);
+
+template <typename T>
+int launch_generate_distort10(const davo_generator_desc* d, T* pts, T* obs, T* pose, T* x0, T* truth, cudaStream_t s);
+template <typename T>
+int launch_generate_joint(const davo_generator_desc* d, T* pts, T* obs, T* x0, T* truth, cudaStream_t s);
+template <typename T>
+int launch_generate_views(const davo_generator_desc* d, T* projected, T* visibility, T* intrinsics, T* orientations,
+                          T* translations, T* world, T* x0, T* truth, cudaStream_t s);
 
 }  // namespace davo

@@ -117,8 +117,7 @@ static int launch_warp_kernel(const SolveParams<T>& p, cudaStream_t stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;  // N too large for a warp-resident slab
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (!ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem))
         return DAVO_ERR_CUDA;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerCta * 32, smem) != cudaSuccess ||
@@ -172,8 +171,7 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (!ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem))
         return DAVO_ERR_CUDA;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerCta * 32, smem) != cudaSuccess ||
@@ -258,8 +256,7 @@ static int launch_resolve_cta(const SolveParams<T>& p, cudaStream_t stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (!ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem))
         return DAVO_ERR_CUDA;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * kResolveWarps, smem) != cudaSuccess ||

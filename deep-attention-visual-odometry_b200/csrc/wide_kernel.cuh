@@ -87,8 +87,7 @@ static int launch_wide(const SolveParams<T>& p, cudaStream_t stream) {
     if (stride * warps > (size_t)max_optin) warps = 1;  // e.g. n = 111 in float64: one 120 KB slab per CTA
     const size_t smem = stride * warps;
     if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (!ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem))
         return DAVO_ERR_CUDA;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem) != cudaSuccess || per_sm < 1)

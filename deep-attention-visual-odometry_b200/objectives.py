@@ -53,9 +53,12 @@ class CalibrationObjective:
         self.data0 = self.data1 = self.weights = None
 
     # ---- what the solver needs -------------------------------------------------------------------
+    def has_weights(self) -> bool:
+        return self.weights is not None
+
     def desc(self, B=None, **kw) -> _lib.ProblemDesc:
         return _lib.make_desc(self.B if B is None else B, self.N, self.views, self.n, self.model, self.dtype,
-                              has_weights=self.weights is not None, **kw)
+                              has_weights=self.has_weights(), **kw)
 
     def _select(self, index):
         """Rows of the problem set for a subset of problems (the reference's `mask`)."""
@@ -134,6 +137,11 @@ class DistortionObjective(CalibrationObjective):
     @property
     def is_staged(self) -> bool:
         return self._data0 is not None
+
+    def has_weights(self) -> bool:
+        # a lazily staged (host-input) problem set knows it is weighted before its weights are on the device
+        raw = getattr(self, "_raw", None)
+        return self.weights is not None or (raw is not None and raw[3] is not None)
 
     def upload_rows(self, lo: int, hi: int, d_pts: torch.Tensor, d_obs: torch.Tensor, d_pose, weights_out=None) -> None:
         """Host -> device copy of the raw inputs of problems [lo, hi) into rows lo:hi of preallocated device

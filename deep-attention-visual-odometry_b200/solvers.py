@@ -224,11 +224,12 @@ class BFGSSolver(Module):
         iterations = self.iterations if iterations is None else iterations
         with torch.cuda.device(device):
             buf = out if out is not None else SolveBuffers.allocate(B, n, obj.dtype, device)
+            data0 = obj.data0  # stages a lazily staged problem set (and its weights) before the descriptor is built
             desc = obj.desc(iterations=iterations, strong=True, sufficient_decrease=self.sufficient_decrease,
                             curvature=self.curvature, error_threshold=error_threshold,
                             minimum_step=self.minimum_step)
             st = _lib.lib().davo_solve_calibration(
-                ctypes.byref(desc), _lib.ptr(obj.data0), _lib.ptr(obj.data1), _lib.ptr(obj.weights), _lib.ptr(x0),
+                ctypes.byref(desc), _lib.ptr(data0), _lib.ptr(obj.data1), _lib.ptr(obj.weights), _lib.ptr(x0),
                 _lib.ptr(buf.x), _lib.ptr(buf.cost), _lib.ptr(buf.converged), _lib.ptr(buf.iterations),
                 _lib.ptr(buf.evaluations), _lib.ptr(buf.reason), _lib.ptr(buf.workspace), _lib.stream_ptr())
         _lib.check(st, "davo_solve_calibration")
@@ -283,8 +284,9 @@ def line_search_wolfe_conditions(parameters: torch.Tensor, search_direction: tor
         f0 = prep(base_error, (B,))
         alpha = torch.empty(B, dtype=obj.dtype, device=device)
         probes = torch.empty(B, dtype=torch.int32, device=device)
+        data0 = obj.data0  # stages a lazily staged problem set (and its weights) before the descriptor is built
         desc = obj.desc(strong=strong, sufficient_decrease=sufficient_decrease, curvature=curvature)
-        st = _lib.lib().davo_line_search(ctypes.byref(desc), _lib.ptr(obj.data0), _lib.ptr(obj.data1),
+        st = _lib.lib().davo_line_search(ctypes.byref(desc), _lib.ptr(data0), _lib.ptr(obj.data1),
                                          _lib.ptr(obj.weights), _lib.ptr(x), _lib.ptr(d), _lib.ptr(f0), _lib.ptr(g),
                                          _lib.ptr(alpha), _lib.ptr(probes), _lib.stream_ptr())
     _lib.check(st, "davo_line_search")

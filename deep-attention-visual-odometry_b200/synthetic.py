@@ -291,3 +291,121 @@ def make_distort10_torch(B: int, N: int = 256, seed: int = 0xB200, device="cpu",
         x0_out[lo:lo + b, FY] = x0_out[lo:lo + b, FX]
         truth_out[lo:lo + b] = th.float().cpu().numpy()
     return CalibrationBatch("distort10", pts_out, obs_out, np.zeros((B, 6), np.float32), x0_out, truth_out, 1)
+
+
+# ---- on-device generation (csrc/generate_kernels.cu through the C-ABI) ---------------------------------------------
+
+@dataclass
+class DeviceBatch:
+    """A CalibrationBatch whose arrays are torch tensors resident on the GPU that generated them."""
+
+    model: str
+    points_3d: "object"
+    obs: "object"
+    pose: "object"
+    x0: "object"
+    truth: "object"
+    views: int = 1
+    weights: "object" = None
+    sample: "object" = None  # CameraViewsAndPoints for model "angle_ba"
+
+    @property
+    def B(self) -> int:
+        return self.obs.shape[0]
+
+    @property
+    def N(self) -> int:
+        return self.obs.shape[-2]
+
+    @property
+    def n(self) -> int:
+        return self.x0.shape[1]
+
+    def numpy(self) -> CalibrationBatch:
+        h = lambda t: None if t is None else t.cpu().numpy()
+        return CalibrationBatch(self.model, h(self.points_3d), h(self.obs), h(self.pose), h(self.x0), h(self.truth),
+                                self.views, h(self.weights))
+
+
+def _gen_desc(B, N, V, dtype, seed, first, *, fov=0.5, noise=0.0, ill_conditioned=False, pathological=0.0,
+              random_pose=False, start_noise=1.0, min_camera_distance=0.1):
+    from . import _lib
+    return _lib.GeneratorDesc(int(B), int(N), int(V), _lib.dtype_code(dtype), int(bool(ill_conditioned)),
+                              int(bool(random_pose)), int(seed) & (2 ** 64 - 1), int(first), float(fov), float(noise),
+                              float(pathological), float(start_noise), float(min_camera_distance))
+
+
+def generate_distort10(B: int, N: int = 256, seed: int = 0xB200, dtype=None, device=None, first_problem: int = 0,
+                       fov: float = 0.5, noise: float = 0.0, ill_conditioned: bool = False, pathological: float = 0.0,
+                       random_pose: bool = False) -> DeviceBatch:
+    """BASELINE configs 2, 4, 5 generated in HBM (davo_generate_distort10): the distributions of make_distort10
+    (SURVEY.md 8(d)), Philox randomness keyed by (seed, first_problem + row) so that shards are rows of one batch."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+    dtype = dtype or torch.float32
+    device = _lib.require_cuda() if device is None else torch.device(device)
+    if ill_conditioned and fov == 0.5:
+        fov = 1.0
+    with torch.cuda.device(device):
+        new = lambda *shape: torch.empty(*shape, dtype=dtype, device=device)
+        pts, obs, pose, x0, truth = new(B, N, 3), new(B, N, 2), new(B, 6), new(B, 10), new(B, 10)
+        d = _gen_desc(B, N, 1, dtype, seed, first_problem, fov=fov, noise=noise, ill_conditioned=ill_conditioned,
+                      pathological=pathological, random_pose=random_pose)
+        st = _lib.lib().davo_generate_distort10(ctypes.byref(d), _lib.ptr(pts), _lib.ptr(obs), _lib.ptr(pose),
+                                                _lib.ptr(x0), _lib.ptr(truth), _lib.stream_ptr())
+    _lib.check(st, "davo_generate_distort10")
+    return DeviceBatch("distort10", pts, obs, pose, x0, truth, 1)
+
+
+def generate_joint(B: int, N: int = 256, V: int = 4, seed: int = 0xB200, dtype=None, device=None,
+                   first_problem: int = 0, fov: float = 0.5, noise: float = 0.0) -> DeviceBatch:
+    """BASELINE config 3 generated in HBM (davo_generate_joint), distributions of make_joint."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+    dtype = dtype or torch.float32
+    device = _lib.require_cuda() if device is None else torch.device(device)
+    with torch.cuda.device(device):
+        new = lambda *shape: torch.empty(*shape, dtype=dtype, device=device)
+        pts, obs, x0, truth = new(B, N, 3), new(B, V, N, 2), new(B, 10 + 6 * V), new(B, 10 + 6 * V)
+        d = _gen_desc(B, N, V, dtype, seed, first_problem, fov=fov, noise=noise)
+        st = _lib.lib().davo_generate_joint(ctypes.byref(d), _lib.ptr(pts), _lib.ptr(obs), _lib.ptr(x0),
+                                            _lib.ptr(truth), _lib.stream_ptr())
+    _lib.check(st, "davo_generate_joint")
+    return DeviceBatch("joint", pts, obs, None, x0, truth, V)
+
+
+def generate_views_and_points(B: int, num_points: int = 8, num_views: int = 4, seed: int = 0xB200, dtype=None,
+                              device=None, first_problem: int = 0, start_noise: float = 1.0,
+                              min_camera_distance: float = 0.1) -> DeviceBatch:
+    """The entry script's batches generated in HBM (davo_generate_views_and_points): the reference dataset's
+    distributions (data/camera_and_parameters_dataset.py:85-151) in its CameraViewsAndPoints layout (`.sample`),
+    plus the solver's start / truth parameter vectors (the reference starts from an MLP's guess)."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+    from .base_types import CameraViewsAndPoints
+    dtype = dtype or torch.float32
+    device = _lib.require_cuda() if device is None else torch.device(device)
+    M, N = int(num_views), int(num_points)
+    n = 3 + 3 * N + 6 * (M - 1)
+    with torch.cuda.device(device):
+        new = lambda *shape: torch.empty(*shape, dtype=dtype, device=device)
+        proj, vis, intr, orient, trans, world = new(B, M, N, 2), new(B, M, N), new(B, 3), new(B, M - 1, 3), \
+            new(B, M - 1, 3), new(B, N, 3)
+        x0, truth = new(B, n), new(B, n)
+        d = _gen_desc(B, N, M, dtype, seed, first_problem, start_noise=start_noise,
+                      min_camera_distance=min_camera_distance)
+        st = _lib.lib().davo_generate_views_and_points(
+            ctypes.byref(d), _lib.ptr(proj), _lib.ptr(vis), _lib.ptr(intr), _lib.ptr(orient), _lib.ptr(trans),
+            _lib.ptr(world), _lib.ptr(x0), _lib.ptr(truth), _lib.stream_ptr())
+    _lib.check(st, "davo_generate_views_and_points")
+    sample = CameraViewsAndPoints(proj, vis, intr, orient, trans, world)
+    return DeviceBatch("angle_ba", None, proj, None, x0, truth, M, vis, sample)

@@ -16,7 +16,10 @@
  *  - `dtype` in the descriptor selects the arithmetic type of every data pointer
  *    (DAVO_F32 / DAVO_F64); integer outputs are int32_t / uint8_t in both cases.
  *  - return value: DAVO_OK (0) or a negative davo_status; never throws, never aborts.
- *  - thread-safe and re-entrant (no hidden globals).
+ *  - thread-safe and re-entrant: no state is kept between calls except (a) a mutex-guarded, monotone
+ *    record of the dynamic-shared-memory size each kernel has been opted in to (the CUDA attribute is
+ *    process-wide per kernel, so it is only ever raised) and (b) the atomic launch counter behind
+ *    davo_launch_count(), a statistic that no result depends on.
  */
 #ifndef DAVO_B200_H
 #define DAVO_B200_H
@@ -199,6 +202,43 @@ int davo_bfgs_update(int32_t dtype, int32_t k, int32_t n, void* H, const void* s
 /* BFGSSolver.scale_initial_inverse_hessian (bfgs_solver.py:217-233): scale[k]. */
 int davo_bfgs_initial_scale(int32_t dtype, int32_t k, int32_t n, const void* s, const void* y,
                             void* scale, void* stream);
+
+/* ---- synthetic oracle-match generator, on the device -------------------------------------------------
+ * Replaces the reference's host-side dataset (data/camera_and_parameters_dataset.py:48-61,85-151, batch layout
+ * base_types/camera_views_and_points.py:21-33; that file does not parse at HEAD) and this repo's numpy generators
+ * for the BASELINE configurations, so that million-problem batches are produced in HBM and never cross PCIe.
+ * Counter-based randomness (Philox4x32-10): every value is a pure function of (seed, first_problem + row,
+ * element), so shards generated by different ranks are the rows of one global batch. */
+typedef struct davo_generator_desc {
+    int32_t B;               /* rows to generate                                                     */
+    int32_t N;               /* matches (points) per problem per view                                */
+    int32_t V;               /* views (JOINT: poses per problem; views-and-points: M >= 2)           */
+    int32_t dtype;           /* DAVO_F32 | DAVO_F64 (arithmetic is float64, rounded at the end)      */
+    int32_t ill_conditioned; /* 1 = BASELINE config 4: heavy distortion, start focal x U_log(0.3, 3) */
+    int32_t random_pose;     /* DISTORT10: 1 = draw a fixed pose per problem (else identity)         */
+    uint64_t seed;
+    uint64_t first_problem;  /* global index of row 0                                                */
+    double fov;              /* half-width of x,y relative to z (0.5; config 4: 1.0)                 */
+    double noise;            /* sigma of Gaussian noise added to the observations (0 = exact)        */
+    double pathological;     /* config 4: fraction of rows with points at z -> 0+ or an ascent start */
+    double start_noise;      /* views-and-points: scale of the perturbation truth -> x0 (1.0)        */
+    double min_camera_distance; /* views-and-points: 0.1 in the reference                            */
+} davo_generator_desc;
+
+/* BASELINE configs 2, 4, 5: points_3d[B,N,3], obs[B,N,2], pose[B,6] (may be NULL), x0[B,10], truth[B,10] (may be NULL). */
+int davo_generate_distort10(const davo_generator_desc* desc, void* points_3d, void* obs, void* pose, void* x0,
+                            void* truth, void* stream);
+/* BASELINE config 3: points_3d[B,N,3], obs[B,V,N,2], x0[B,10+6V], truth[B,10+6V] (may be NULL). */
+int davo_generate_joint(const davo_generator_desc* desc, void* points_3d, void* obs, void* x0, void* truth,
+                        void* stream);
+/* The entry script's batches, CameraViewsAndPoints layout: projected_points[B,M,N,2], visibility_mask[B,M,N]
+ * (1.0 / 0.0), camera_intrinsics[B,3] = (f', cx, cy), camera_orientations[B,M-1,3] (axis-angle),
+ * camera_translations[B,M-1,3], world_points[B,N,3]; optionally the solver's parameter vectors
+ * x0[B,n] / truth[B,n], n = 3+3N+6(M-1), laid out as unpack_calibration_parameters expects
+ * (camera_model/calibration_pinhole_camera_model.py:33-75).  M = desc->V <= 32. */
+int davo_generate_views_and_points(const davo_generator_desc* desc, void* projected_points, void* visibility_mask,
+                                   void* camera_intrinsics, void* camera_orientations, void* camera_translations,
+                                   void* world_points, void* x0, void* truth, void* stream);
 
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t davo_launch_count(void);

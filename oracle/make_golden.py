@@ -30,10 +30,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 # name -> (generator, generator kwargs, torch dtype, solver kwargs)
 SOLVE_CASES = {
     # gate G64: float64 against the float64 reference
-    "solve_cfg2_f64": ("make_distort10", dict(B=1024, N=256, seed=0xB200), "float64",
+    "solve_cfg2_f64": ("make_distort10", dict(B=4096, N=256, seed=0xB200), "float64",
                        dict(error_threshold=1e-12, iterations=1000)),
     # gate G32: float32 at a threshold every problem reaches before the fp32 noise floor
-    "solve_cfg2_f32": ("make_distort10", dict(B=1024, N=256, seed=0xB200), "float32",
+    "solve_cfg2_f32": ("make_distort10", dict(B=4096, N=256, seed=0xB200), "float32",
                        dict(error_threshold=1e-5, iterations=1000)),
     # the driver's eval threshold (networks/calibration_network.py:44): chaotic in fp32, kept for the record
     "solve_cfg2_f32_thr1e-7": ("make_distort10", dict(B=256, N=256, seed=0xB200), "float32",
@@ -43,9 +43,9 @@ SOLVE_CASES = {
                              dict(error_threshold=1e-12, iterations=300)),
     "solve_cfg2_pose_f64": ("make_distort10", dict(B=128, N=96, seed=0xB202, random_pose=True), "float64",
                             dict(error_threshold=1e-12, iterations=1000)),
-    "solve_cfg3_f64": ("make_joint", dict(B=384, N=256, V=4, seed=0xB200), "float64",
+    "solve_cfg3_f64": ("make_joint", dict(B=4096, N=256, V=4, seed=0xB200), "float64",
                        dict(error_threshold=1e-10, iterations=1000)),
-    "solve_cfg3_f32": ("make_joint", dict(B=384, N=256, V=4, seed=0xB200), "float32",
+    "solve_cfg3_f32": ("make_joint", dict(B=4096, N=256, V=4, seed=0xB200), "float32",
                        dict(error_threshold=1e-5, iterations=1000)),
     "solve_cfg3_small_f64": ("make_joint", dict(B=64, N=40, V=2, seed=0xB203), "float64",
                              dict(error_threshold=1e-10, iterations=1000)),

@@ -1,5 +1,37 @@
 """Shared comparison of two solve results (dicts with x, cost, iters, fevals, reason)."""
+import json
+import os
+
 import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# The achieved parity numbers of every gated fixture are written here by the GPU suite (and mirrored into
+# gpurun_out/, the only directory that travels back from the GPU box); the committed copy is the record.
+PARITY_RECORD = os.environ.get("DAVO_PARITY_RECORD", os.path.join(ROOT, "profiles", "parity_r2.json"))
+_RECORD_KEYS = ("steps_equal", "fevals_equal", "reason_equal", "dtheta_median", "dtheta_p99", "dtheta_max",
+                "dcost_median", "dcost_p99", "dcost_max")
+
+
+def record_parity(fixture, route, **comparisons):
+    """Merge {fixture: {route: {comparison: metrics}}} into the parity record.  `comparisons` maps a label
+    ("kernel_vs_reference", "reference_vs_itself", "kernel_vs_oracle") to a compare_solves() result."""
+    for path in (PARITY_RECORD, os.path.join(ROOT, "gpurun_out", os.path.basename(PARITY_RECORD))):
+        try:
+            with open(path) as fh:
+                data = json.load(fh)
+        except (OSError, ValueError):
+            data = {}
+        entry = data.setdefault(fixture, {}).setdefault(route, {})
+        for label, m in comparisons.items():
+            entry[label] = {k: (float(m[k]) if not isinstance(m[k], (int, str)) else m[k])
+                            for k in m if k in _RECORD_KEYS or k in ("problems", "note")}
+            entry[label]["problems"] = int(len(m["dtheta"])) if "dtheta" in m else m.get("problems")
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "w") as fh:
+                json.dump(data, fh, indent=1, sort_keys=True)
+        except OSError:
+            pass
 
 
 def compare_solves(got, ref, error_threshold):
@@ -35,10 +67,12 @@ def reference_band(golden, error_threshold):
     return compare_solves(perm, golden, error_threshold)
 
 
-def assert_within_band(m, band, steps_slack=0.04, reason_slack=0.03, tol_factor=4.0, theta_floor=1e-4,
+def assert_within_band(m, band, steps_slack=0.0, reason_slack=0.0, tol_factor=2.0, theta_floor=1e-4,
                        cost_floor=1e-5):
     """north_star tolerances (identical steps >= 99 %, dtheta <= 1e-4, dcost <= 1e-5) wherever the reference
-    itself meets them; otherwise at least as tight as the reference's own band (with statistical slack)."""
+    itself meets them; otherwise at least as tight as the reference's own band: the fraction of identical step
+    counts / termination reasons may fall short of the reference's own self-agreement only by the 3-sigma
+    sampling error of a binomial estimate over B problems, medians / p99 by a factor of `tol_factor`."""
     B = len(m["dtheta"])
     for key, slack in (("steps_equal", steps_slack), ("reason_equal", reason_slack)):
         p = band[key]
