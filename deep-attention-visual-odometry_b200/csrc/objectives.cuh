@@ -36,18 +36,16 @@ struct Intrinsics {
     }
 };
 
-// One match: residuals, squared error and the intrinsic-gradient accumulators.
-//   acc[0..9]  += d(cost/2)/d(cx,cy,k1,k2,k3,p1,p2,fx,s,fy)   (acc[5], acc[6] without their 2uv terms)
-//   acc[10]    += cost
-//   acc[11]    += ru * uv,  acc[12] += rv * uv                 (folded into acc[5], acc[6] by fold_uv_terms)
-// (gu, gv) = d(cost/2)/d(u, v) are returned for the pose chain rule of the JOINT model.
-// 53 FP32 instructions; counted as 93 flop by SURVEY.md 8(d).
+// One match in the REFERENCE's association, operation by operation, without FMA: the expressions of
+// camera_model/distorted_camera_model.py:59-86 exactly as written (rad = 1 + k1 r2 + k2 r2 r2 + k3 r2 r2 r2, not
+// Horner), as restated by oracle/calib_oracle_impl.h match_intrinsics.  Used (a) when an evaluation overflows: whether
+// a cost is +inf or NaN decides how the reference's line search continues (inf: "sufficient decrease failed", bisect
+// back; NaN: every comparison false, keep doubling until the probe cap and retire on a NaN cost), and the Horner / FMA
+// form of the fast path turns many of the reference's inf - inf = NaN into +-inf (BASELINE config 4's points at
+// z -> 0+); (b) by DAVO_ORACLE_ARITH=1 debug builds for every evaluation.
 template <typename T, bool kWeighted>
-__device__ __forceinline__ void match_cost_grad(const Intrinsics<T>& I, T a, T b, T us, T vs, T w,
-                                                T (&acc)[kSlots], T& gu, T& gv) {
-#if DAVO_ORACLE_ARITH
-    // Debug variant: the oracle's expressions, operation by operation, without FMA (oracle/calib_oracle_impl.h
-    // match_intrinsics).  Used to separate effects of the evaluator's rounding from effects of the solver.
+__device__ __forceinline__ void match_cost_grad_unfused(const Intrinsics<T>& I, T a, T b, T us, T vs, T w,
+                                                        T (&acc)[kSlots], T& gu, T& gv) {
     const T u = add_rn(mul_rn(I.fx, a), mul_rn(I.s, b));
     const T v = mul_rn(I.fy, b);
     const T r2 = add_rn(mul_rn(u, u), mul_rn(v, v));
@@ -82,6 +80,19 @@ __device__ __forceinline__ void match_cost_grad(const Intrinsics<T>& I, T a, T b
     acc[7] = add_rn(acc[7], mul_rn(gu, a));
     acc[8] = add_rn(acc[8], mul_rn(gu, b));
     acc[9] = add_rn(acc[9], mul_rn(gv, b));
+}
+
+// One match: residuals, squared error and the intrinsic-gradient accumulators.
+//   acc[0..9]  += d(cost/2)/d(cx,cy,k1,k2,k3,p1,p2,fx,s,fy)   (acc[5], acc[6] without their 2uv terms)
+//   acc[10]    += cost
+//   acc[11]    += ru * uv,  acc[12] += rv * uv                 (folded into acc[5], acc[6] by fold_uv_terms)
+// (gu, gv) = d(cost/2)/d(u, v) are returned for the pose chain rule of the JOINT model.
+// 53 FP32 instructions; counted as 93 flop by SURVEY.md 8(d).
+template <typename T, bool kWeighted>
+__device__ __forceinline__ void match_cost_grad(const Intrinsics<T>& I, T a, T b, T us, T vs, T w,
+                                                T (&acc)[kSlots], T& gu, T& gv) {
+#if DAVO_ORACLE_ARITH
+    match_cost_grad_unfused<T, kWeighted>(I, a, b, us, vs, w, acc, gu, gv);
 #else
     const T u = fma_t(I.fx, a, I.s * b);            // distorted_camera_model.py:59-61
     const T v = I.fy * b;                           // :62
@@ -308,6 +319,24 @@ struct Distort10Objective {
         }
     }
 
+    // The match loop again in the reference's association (match_cost_grad_unfused), for an evaluation that
+    // overflowed: rolled, rarely executed.
+    __device__ __noinline__ void accumulate_unfused(const Intrinsics<T>& I, T (&acc)[kSlots]) {
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k) acc[k] = T(0);
+        T gu, gv;
+        const int N = p.N;
+#pragma unroll 1
+        for (int i = lane; i < N; i += 64) {
+            const V4 ab = matches[i];
+            const V4 ob = matches[i + 32];
+            match_cost_grad_unfused<T, kWeighted>(I, ab.x, ab.z, -ob.x, -ob.z, kWeighted ? weights[i] : T(1), acc, gu, gv);
+            if (i + 32 < N)
+                match_cost_grad_unfused<T, kWeighted>(I, ab.y, ab.w, -ob.y, -ob.w, kWeighted ? weights[i + 32] : T(1),
+                                                      acc, gu, gv);
+        }
+    }
+
     // One evaluation.  Inlined at its call site (solve_one_warp has a single one): a __noinline__ version ran
     // 12 % slower (call + stack).
     __device__ __forceinline__ void eval(const T* th, T& f, T& g_own) {
@@ -322,6 +351,9 @@ struct Distort10Objective {
 #pragma unroll
         for (int k = 0; k < kPairAcc; ++k) acc[k] = acc2[k].x + acc2[k].y;
         fold_uv_terms(acc);  // acc[11], acc[12] are folded into acc[5], acc[6]: 11 sums remain
+        // An overflowed evaluation is redone in the reference's association: whether the cost is inf or NaN steers
+        // the reference's line search (see match_cost_grad_unfused).
+        if (__any_sync(kFull, !isfinite(acc[10]))) accumulate_unfused(I, acc);
         // Sum over the 32 lanes as a transpose through shared memory: lane L stores its 11 partial sums as row
         // L, lane pair c adds up column c (lane 2c the even rows, lane 2c+1 the odd rows) and one shuffle joins
         // the two halves, so lanes 2c and 2c+1 both end with total c.  (The caller's eval_at has synchronised

@@ -211,6 +211,27 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
 #pragma unroll
             for (int q = 0; q < kPairAcc; ++q) acc[q] = acc2[q].x + acc2[q].y;
             fold_uv_terms(acc);  // acc[11], acc[12] are folded into acc[5], acc[6]: 11 sums remain
+            // An overflowed evaluation is redone in the reference's association (objectives.cuh
+            // match_cost_grad_unfused): whether the cost is inf or NaN steers the reference's line search.  Rare
+            // (BASELINE config 4's points at z -> 0+); both halves take the branch together, each keeps its own sums.
+            if (__any_sync(kFull, !isfinite(acc[10]))) {
+                const bool mine_bad = __any_sync(hmask, !isfinite(acc[10]));
+                T ref[kSlots];
+#pragma unroll
+                for (int q = 0; q < kSlots; ++q) ref[q] = T(0);
+                T gu1, gv1;
+#pragma unroll 1
+                for (int i = l; i < N; i += 32) {
+                    const V4 ab = matches[i];
+                    const V4 ob = matches[i + 16];
+                    match_cost_grad_unfused<T, false>(I, ab.x, ab.z, -ob.x, -ob.z, T(1), ref, gu1, gv1);
+                    if (i + 16 < N) match_cost_grad_unfused<T, false>(I, ab.y, ab.w, -ob.y, -ob.w, T(1), ref, gu1, gv1);
+                }
+                if (mine_bad) {
+#pragma unroll
+                    for (int q = 0; q < 11; ++q) acc[q] = ref[q];
+                }
+            }
             // Sum over the 16 lanes as a transpose through shared memory: lane l stores its 11 partial sums as row l,
             // lane c adds up column c.
             V4* row = reinterpret_cast<V4*>(scratch + l * kRedPitch);

@@ -36,7 +36,7 @@ SOLVE_CASES = {
     "solve_cfg2_f32": ("make_distort10", dict(B=4096, N=256, seed=0xB200), "float32",
                        dict(error_threshold=1e-5, iterations=1000)),
     # the driver's eval threshold (networks/calibration_network.py:44): chaotic in fp32, kept for the record
-    "solve_cfg2_f32_thr1e-7": ("make_distort10", dict(B=256, N=256, seed=0xB200), "float32",
+    "solve_cfg2_f32_thr1e-7": ("make_distort10", dict(B=4096, N=256, seed=0xB200), "float32",
                                dict(error_threshold=1e-7, iterations=1000)),
     # noisy observations: optimum cost ~ 2 N sigma^2, retire on step size / cap
     "solve_cfg2_noisy_f64": ("make_distort10", dict(B=256, N=256, seed=0xB201, noise=1e-3), "float64",
@@ -257,12 +257,63 @@ def gen_analytic_solves():
     _save("analytic_solves", **out)
 
 
+def gen_training():
+    """The differentiable / training-mode solve: the UNMODIFIED reference BFGSSolver in
+    train() mode, `parameters.requires_grad` (so every gradient evaluation is made with create_graph=True,
+    bfgs_solver.py:85,133-135), drop_path_p = 0 (its random retirement cannot be reproduced bit for bit) and both
+    settings of return_second_last.  Stored: the returned parameters and d(sum(w * x_out))/d x0 for a random w —
+    for the distortion objective also the gradient with respect to the observations."""
+    bfgs_mod, _, _, _ = rh._import_reference()
+    rng = np.random.default_rng(16)
+    out = {}
+    cases = {}
+    for name, x0 in (("rosenbrock", rng.uniform(-1.5, 1.5, (6, 2))), ("log_sphere", rng.normal(0, 2, (6, 3))),
+                     ("sphere", rng.normal(0, 1, (5, 4))), ("cosine", rng.normal(0, 3, (6, 4)))):
+        cases[name] = (rh.ANALYTIC[name], x0, None)
+    b = syn.make_distort10(6, 20, seed=51, dtype=np.float64, random_pose=True)
+    out["d10_points"], out["d10_obs"], out["d10_pose"] = b.points_3d, b.obs, b.pose
+    cases["d10"] = (rh.make_objective(b), b.x0, "obs")
+    j = syn.make_joint(4, 16, 2, seed=52, dtype=np.float64)
+    out["joint_points"], out["joint_obs"] = j.points_3d, j.obs
+    cases["joint"] = (rh.make_objective(j), j.x0, None)
+    a = syn.make_angle_ba(6, 6, 3, seed=53, dtype=np.float64)
+    out["ba_obs"], out["ba_vis"] = a.obs, a.weights
+    cases["ba"] = (rh.make_objective(a), a.x0, None)
+    settings = {"k3": dict(training_iterations=3, training_error_threshold=1e-12),
+                "k8": dict(training_iterations=8, training_error_threshold=1e-12),
+                "k25thr": dict(training_iterations=25, training_error_threshold=1e-3),
+                "k8second": dict(training_iterations=8, training_error_threshold=1e-12, return_second_last=True)}
+    for cname, (obj, x0, data_attr) in cases.items():
+        out[f"{cname}_x0"] = x0
+        w = rng.standard_normal(x0.shape)
+        out[f"{cname}_w"] = w
+        for sname, skw in settings.items():
+            solver = bfgs_mod.BFGSSolver(drop_path_p=0.0, **skw).train()
+            xg = torch.tensor(x0, requires_grad=True)
+            data = None
+            if data_attr is not None:
+                data = getattr(obj, data_attr).clone().requires_grad_(True)
+                setattr(obj, data_attr, data)
+            xo = solver(xg, obj)
+            loss = (xo * torch.tensor(w)).sum()
+            grads = torch.autograd.grad(loss, [xg] + ([data] if data is not None else []), allow_unused=True)
+            out[f"{cname}_{sname}_x"] = xo.detach().numpy()
+            out[f"{cname}_{sname}_grad_x0"] = grads[0].numpy()
+            if data is not None:
+                out[f"{cname}_{sname}_grad_{data_attr}"] = grads[1].numpy()
+                setattr(obj, data_attr, data.detach())
+            print(f"  training {cname}/{sname}: |x - x0| {np.abs(xo.detach().numpy() - x0).max():.3e}, "
+                  f"|grad| {np.abs(grads[0].numpy()).max():.3e}", flush=True)
+    out["meta"] = json.dumps(dict(settings=settings, torch=torch.__version__))
+    _save("training", **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*", default=None)
     args = ap.parse_args()
     small = {"camera_model": gen_camera_model, "bfgs_update": gen_bfgs_update, "line_search": gen_line_search,
-             "analytic_solves": gen_analytic_solves, "angle_ba": gen_angle_ba}
+             "analytic_solves": gen_analytic_solves, "angle_ba": gen_angle_ba, "training": gen_training}
     names = args.only or (list(small) + list(SOLVE_CASES))
     for name in names:
         print(name, flush=True)

@@ -72,11 +72,13 @@ def assert_within_band(m, band, steps_slack=0.0, reason_slack=0.0, tol_factor=2.
     """north_star tolerances (identical steps >= 99 %, dtheta <= 1e-4, dcost <= 1e-5) wherever the reference
     itself meets them; otherwise at least as tight as the reference's own band: the fraction of identical step
     counts / termination reasons may fall short of the reference's own self-agreement only by the 3-sigma
-    sampling error of a binomial estimate over B problems, medians / p99 by a factor of `tol_factor`."""
+    sampling error of the two binomial estimates being compared, medians / p99 by a factor of `tol_factor`."""
     B = len(m["dtheta"])
+    Bb = len(band["dtheta"]) if "dtheta" in band else B
     for key, slack in (("steps_equal", steps_slack), ("reason_equal", reason_slack)):
         p = band[key]
-        slack = max(slack, 3.0 * np.sqrt(max(p * (1.0 - p), 1e-4) / B))  # 3 sigma of a binomial estimate over B problems
+        # 3 sigma of the difference of two binomial estimates: the kernel's over B problems, the band's over Bb
+        slack = max(slack, 3.0 * np.sqrt(max(p * (1.0 - p), 1e-4) * (1.0 / B + 1.0 / Bb)))
         assert m[key] >= min(0.99, p - slack), (key, summary(m), summary(band))
     # Where the reference's own tail is already of order one the trajectories are chaotic (float32 at its
     # noise floor, ill-conditioned config 4): a p99 of a heavy tail is not a stable statistic, compare medians.

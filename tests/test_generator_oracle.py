@@ -70,8 +70,16 @@ def test_sharded_generation_is_a_slice_of_the_global_batch():
 # ---- the CUDA generator against the restatement -------------------------------------------------------------------
 
 def _close(a, b, tol):
+    """|a - b| <= tol * max(1, |b|); values beyond the float32 range (config 4's points at z -> 0+ give
+    observations of order 1e40) must have overflowed to the same infinity."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b)))
+    big = np.abs(b) > 3e38
+    ok = np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b))
+    ok = np.where(big, (a == b) | (np.isinf(a) & (np.sign(a) == np.sign(b))) | ok, ok)
+    if not np.all(ok):
+        i = np.unravel_index(np.argmax(~ok), ok.shape)
+        print("first mismatch at", i, "device", a[i], "restatement", b[i], "mismatches", int((~ok).sum()), "of", ok.size)
+    return bool(np.all(ok))
 
 
 @pytest.mark.gpu
@@ -90,7 +98,7 @@ def test_device_distort10_and_joint_match_restatement(dt, tol):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("M,N", [(4, 8), (2, 5), (6, 40)])
+@pytest.mark.parametrize("M,N", [(4, 8), (2, 5), (6, 12)])
 def test_device_views_and_points_match_restatement(M, N):
     d = davo_b200.synthetic.generate_views_and_points(500, N, M, seed=13, dtype=torch.float64)
     r = gen_oracle.generate_views_and_points(500, N, M, seed=13)

@@ -771,3 +771,59 @@ def test_randomised_sweep_against_oracle():
     assert r.returncode == 0, r.stderr[-2000:]
     assert "SUSPECT" not in r.stdout, r.stdout[-3000:]
     assert " runs in " in r.stdout
+
+
+# ---- regression tests for round-1 review findings ---------------------------------------------------------------
+
+def test_lazily_staged_weighted_objective_keeps_its_weights_in_line_search_and_solve():
+    """A host-input (lazily staged) DistortionObjective with weights: the descriptor must say has_weights before
+    the weights are on the device (line search and solve_into build it before touching data0)."""
+    b = davo_b200.synthetic.make_distort10(48, 64, seed=91, dtype=np.float64)
+    rng = np.random.default_rng(91)
+    w = rng.uniform(0.0, 2.0, size=(48, 64))
+    w[:, ::5] = 0.0
+    pts, obs, x0 = (torch.from_numpy(a) for a in (b.points_3d, b.obs, b.x0))
+    resident = davo_b200.DistortionObjective(pts.cuda(), obs.cuda(), weights=torch.from_numpy(w).cuda())
+    cost, grad = resident.evaluate(x0)
+    d = -1e-2 * grad
+    want_alpha, want_probes = davo_b200.line_search_wolfe_conditions(x0, d, cost, grad, resident, strong=True,
+                                                                     return_probes=True)
+    lazy = davo_b200.DistortionObjective(pts, obs, weights=torch.from_numpy(w))
+    assert not lazy.is_staged and lazy.has_weights()
+    alpha, probes = davo_b200.line_search_wolfe_conditions(x0, d, cost, grad, lazy, strong=True, return_probes=True)
+    assert torch.equal(alpha, want_alpha) and torch.equal(probes, want_probes)
+    unweighted = davo_b200.DistortionObjective(pts.cuda(), obs.cuda())
+    a0, _ = davo_b200.line_search_wolfe_conditions(x0, d, cost, grad, unweighted, strong=True, return_probes=True)
+    assert not torch.equal(a0, want_alpha)  # the weights matter for this input: a dropped flag would show
+    lazy2 = davo_b200.DistortionObjective(pts, obs, weights=torch.from_numpy(w))
+    solver = davo_b200.BFGSSolver(error_threshold=1e-12, iterations=50).eval()
+    got = solver.solve_into(x0.cuda(), lazy2)
+    ref = solver.solve_into(x0.cuda(), resident)
+    assert torch.equal(got.x, ref.x) and torch.equal(got.iterations, ref.iterations)
+
+
+def test_least_squares_wrappers_are_differentiable_like_the_reference():
+    """find_error / find_error_gradient are plain differentiable torch ops in the reference
+    (solvers/least_squares_utils.py:16-48); the kernel-backed versions carry the same gradients."""
+    rng = np.random.default_rng(3)
+    B, F, N, P = 4, 2, 9, 5
+    r = torch.tensor(rng.standard_normal((B, F, N, 2)), requires_grad=True)
+    J = torch.tensor(rng.standard_normal((B, F, N, 2, P)), requires_grad=True)
+    w = torch.tensor(rng.uniform(0.1, 1.0, size=(B, F, N, 1)), requires_grad=True)
+    up = torch.tensor(rng.standard_normal(B))
+    upg = torch.tensor(rng.standard_normal((B, P)))
+    for weights in (None, w):
+        ref_e = (r.square() if weights is None else r.square() * weights).sum(dim=(-3, -2, -1))
+        ref_g = (2.0 * (r if weights is None else r * weights).unsqueeze(-1) * J).sum(dim=(-4, -3, -2))
+        inputs = [r, J] + ([] if weights is None else [w])
+        want_e = torch.autograd.grad((ref_e * up).sum(), [r] + inputs[2:])
+        want_g = torch.autograd.grad((ref_g * upg).sum(), inputs)
+        e = davo_b200.find_error(r, weights)
+        g = davo_b200.find_error_gradient(r, J, weights)
+        assert torch.allclose(e, ref_e.detach(), rtol=1e-12) and torch.allclose(g, ref_g.detach(), rtol=1e-11, atol=1e-12)
+        got_e = torch.autograd.grad((e * up).sum(), [r] + inputs[2:])
+        got_g = torch.autograd.grad((g * upg).sum(), inputs)
+        for a, b_ in zip(got_e + got_g, want_e + want_g):
+            assert torch.allclose(a, b_, rtol=1e-11, atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        davo_b200.compute_distorted_camera_model(torch.zeros(1, 2, 3, requires_grad=True), torch.zeros(1, 16))
