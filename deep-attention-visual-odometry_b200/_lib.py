@@ -23,11 +23,11 @@ F32, F64 = 0, 1
 
 MODEL_IDS = {"distort10": 0, "joint": 1, "angle_ba": 2, "sphere": 16, "sphere_offset": 17, "log_sphere": 18,
              "rosenbrock": 19, "cosine": 20, "x2_sine": 21, "distance": 22}
-REASON_NAMES = {0: "threshold", 1: "step", 2: "cap", 3: "nan"}
+REASON_NAMES = {0: "threshold", 1: "step", 2: "cap", 3: "nan", 5: "dropped"}
 
 # every symbol include/davo_b200.h declares (tests check the library exports all of them)
 EXPORTED = ("davo_abi_version", "davo_strerror", "davo_launch_count", "davo_solve_calibration",
-            "davo_eval_cost_grad", "davo_line_search", "davo_stage_matches", "davo_project",
+            "davo_solve_training", "davo_solve_backward", "davo_eval_cost_grad", "davo_line_search", "davo_stage_matches", "davo_project",
             "davo_project_jacobian", "davo_least_squares", "davo_bfgs_update", "davo_bfgs_initial_scale",
             "davo_generate_distort10", "davo_generate_joint", "davo_generate_views_and_points")
 
@@ -38,6 +38,13 @@ class ProblemDesc(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in
                 ("B", "N", "V", "n", "model", "dtype", "max_iters", "max_ls_iters", "strong", "has_weights")] + \
                [(k, ctypes.c_double) for k in ("sufficient_decrease", "curvature", "error_threshold", "minimum_step")]
+
+
+class TrainingDesc(ctypes.Structure):
+    """davo_training_desc (include/davo_b200.h)."""
+
+    _fields_ = [("capacity", ctypes.c_int32), ("return_second_last", ctypes.c_int32),
+                ("drop_path_p", ctypes.c_double), ("seed", ctypes.c_uint64), ("hvp_rel_step", ctypes.c_double)]
 
 
 class GeneratorDesc(ctypes.Structure):
@@ -81,6 +88,9 @@ def lib() -> ctypes.CDLL:
         L.davo_strerror.argtypes = [ctypes.c_int]
         L.davo_launch_count.restype = i64
         L.davo_solve_calibration.argtypes = [dp] + [vp] * 12
+        tp = ctypes.POINTER(TrainingDesc)
+        L.davo_solve_training.argtypes = [dp, tp] + [vp] * 16
+        L.davo_solve_backward.argtypes = [dp, tp] + [vp] * 14
         L.davo_eval_cost_grad.argtypes = [dp] + [vp] * 7
         L.davo_line_search.argtypes = [dp] + [vp] * 10
         L.davo_stage_matches.argtypes = [dp] + [vp] * 5

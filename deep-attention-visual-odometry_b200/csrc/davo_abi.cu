@@ -151,6 +151,66 @@ int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, con
     return DAVO_DISPATCH(solve, f64, p, s);
 }
 
+int davo_solve_training(const davo_problem_desc* desc, const davo_training_desc* train, const void* data0,
+                        const void* data1, const void* weights, const void* x0, void* x_out, void* cost_out,
+                        uint8_t* converged_out, int32_t* iters_out, int32_t* fevals_out, int32_t* reason_out,
+                        void* traj_x, void* traj_g, void* traj_alpha, int32_t* traj_len, void* workspace,
+                        void* stream) {
+    int st = check_desc(desc);
+    if (st) return st;
+    if (!train) return DAVO_ERR_NULL_POINTER;
+    if (desc->B == 0) return DAVO_OK;
+    if (!x0 || !x_out || !workspace) return DAVO_ERR_NULL_POINTER;
+    if ((st = check_data(desc, data0, data1, weights))) return st;
+    const bool recording = traj_x || traj_g || traj_alpha || traj_len;
+    if (recording && !(traj_x && traj_g && traj_alpha && traj_len)) return DAVO_ERR_NULL_POINTER;
+    if (recording && train->capacity < desc->max_iters) return DAVO_ERR_BAD_ARGUMENT;
+    if (!(train->drop_path_p >= 0.0 && train->drop_path_p <= 1.0)) return DAVO_ERR_BAD_ARGUMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (desc->dtype == DAVO_F32) {
+        SolveParams<float> p = make_params<float>(desc, data0, data1, weights);
+        p.x0 = static_cast<const float*>(x0); p.x_out = static_cast<float*>(x_out);
+        p.cost_out = static_cast<float*>(cost_out); p.converged_out = converged_out;
+        p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
+        p.queue = static_cast<unsigned*>(workspace);
+        TrainRecorder<float> rec{static_cast<float*>(traj_x), static_cast<float*>(traj_g),
+                                 static_cast<float*>(traj_alpha), traj_len, train->capacity,
+                                 static_cast<float>(train->drop_path_p), train->seed, train->return_second_last};
+        return launch_train_forward<float>(p, rec, s);
+    }
+    SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
+    p.x0 = static_cast<const double*>(x0); p.x_out = static_cast<double*>(x_out);
+    p.cost_out = static_cast<double*>(cost_out); p.converged_out = converged_out;
+    p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
+    p.queue = static_cast<unsigned*>(workspace);
+    TrainRecorder<double> rec{static_cast<double*>(traj_x), static_cast<double*>(traj_g),
+                              static_cast<double*>(traj_alpha), traj_len, train->capacity,
+                              static_cast<float>(train->drop_path_p), train->seed, train->return_second_last};
+    return launch_train_forward<double>(p, rec, s);
+}
+
+int davo_solve_backward(const davo_problem_desc* desc, const davo_training_desc* train, const void* data0,
+                        const void* data1, const void* weights, const void* traj_x, const void* traj_g,
+                        const void* traj_alpha, const int32_t* traj_len, const int64_t* traj_offset,
+                        const int64_t* scratch_offset, void* scratch, const void* grad_out, void* grad_x0,
+                        void* workspace, void* stream) {
+    int st = check_desc(desc);
+    if (st) return st;
+    if (!train) return DAVO_ERR_NULL_POINTER;
+    if (desc->dtype != DAVO_F64) return DAVO_ERR_UNSUPPORTED;
+    if (desc->B == 0) return DAVO_OK;
+    if (!traj_x || !traj_g || !traj_alpha || !traj_len || !traj_offset || !scratch_offset || !grad_out || !grad_x0 || !workspace)
+        return DAVO_ERR_NULL_POINTER;  // scratch may be NULL when no problem recorded a step
+    if ((st = check_data(desc, data0, data1, weights))) return st;
+    SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
+    p.queue = static_cast<unsigned*>(workspace);
+    BackwardParams<double> bp{static_cast<const double*>(traj_x), static_cast<const double*>(traj_g),
+                              static_cast<const double*>(traj_alpha), traj_len, traj_offset, scratch_offset,
+                              static_cast<double*>(scratch), static_cast<const double*>(grad_out),
+                              static_cast<double*>(grad_x0), train->hvp_rel_step > 0.0 ? train->hvp_rel_step : 5e-7};
+    return launch_train_backward(p, bp, static_cast<cudaStream_t>(stream));
+}
+
 int davo_eval_cost_grad(const davo_problem_desc* desc, const void* data0, const void* data1,
                         const void* weights, const void* x, void* cost, void* grad, void* stream) {
     int st = check_desc(desc);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "davo_common.cuh"
+#include "train_params.cuh"
 
 namespace davo {
 
@@ -32,6 +33,10 @@ int launch_eval_ba_f32(const SolveParams<float>& p, cudaStream_t s);
 int launch_eval_ba_f64(const SolveParams<double>& p, cudaStream_t s);
 int launch_line_search_ba_f32(const SolveParams<float>& p, cudaStream_t s);
 int launch_line_search_ba_f64(const SolveParams<double>& p, cudaStream_t s);
+
+template <typename T>
+int launch_train_forward(const SolveParams<T>& p, const TrainRecorder<T>& rec, cudaStream_t s);
+int launch_train_backward(const SolveParams<double>& p, const BackwardParams<double>& bp, cudaStream_t s);
 
 template <typename T>
 int launch_stage(int B, int N, const T* pts, const T* obs, const T* pose, T* staged, cudaStream_t s);

@@ -10,6 +10,7 @@
 #pragma once
 #include "davo_common.cuh"
 #include "solver_warp.cuh"  // same_bits
+#include "train_params.cuh"
 
 namespace davo {
 
@@ -111,9 +112,9 @@ __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const 
 }
 
 // bfgs_solver.py:80-215 for one problem.
-template <int kCols = 2, typename T, typename Obj>
+template <int kCols = 2, typename T, typename Obj, typename Rec = NoRecorder>
 __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p, int b, WideWorkspace<T>& ws,
-                                               int lane) {
+                                               int lane, const Rec rec = Rec()) {
     // an objective with a compile-time parameter count (Obj::kParams > 0) turns n and the row stride into
     // constants: the sweeps over H below unroll with immediate offsets
     const int n = Obj::kParams > 0 ? Obj::kParams : p.n, ld = Obj::kParams > 0 ? (Obj::kParams | 1) : ws.ld;
@@ -139,6 +140,10 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
       neg_c2_g0 = T(0);
     int ls_i = 0;
     int mode = (p.max_iters > 0) ? kEvalOuter : kEvalFinal;
+    if (Rec::kActive && mode == kEvalOuter && rec.drop(b, 0)) {  // dropped before its first evaluation (:122-125)
+        reason = DAVO_REASON_DROPPED;
+        mode = kEvalFinal;
+    }
 
     for (;;) {
         const T* pt = x;
@@ -189,17 +194,44 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             // ---- line search finished, alpha = upper_alpha (:239): take the step, bfgs_solver.py:191-207 ----
             ++iters;
             T nrm2 = T(0);
+            if (!Rec::kActive) {
 #pragma unroll
-            for (int h = 0; h < kCols; ++h) {                                   // :191-199
-                const int c = lane + 32 * h;
-                if (c < n) {
-                    const T sc = mul_rn(hi, d[c]);
-                    s[c] = sc;
-                    x[c] = add_rn(x[c], sc);
-                    nrm2 = add_rn(nrm2, mul_rn(sc, sc));
+                for (int h = 0; h < kCols; ++h) {                               // :191-199
+                    const int c = lane + 32 * h;
+                    if (c < n) {
+                        const T sc = mul_rn(hi, d[c]);
+                        s[c] = sc;
+                        x[c] = add_rn(x[c], sc);
+                        nrm2 = add_rn(nrm2, mul_rn(sc, sc));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < kCols; ++h) {
+                    const int c = lane + 32 * h;
+                    if (c < n) {
+                        const T sc = mul_rn(hi, d[c]);
+                        s[c] = sc;
+                        nrm2 = add_rn(nrm2, mul_rn(sc, sc));
+                    }
                 }
             }
             const T nrm = sqrt_rn(warp_allreduce(nrm2));
+            if (Rec::kActive) {
+                // training mode: keep (x_k, g_k, alpha_k) for the backward pass; with return_second_last the step
+                // that retires the problem on its length is not applied (:196-212)
+                const bool withheld = rec.second_last() && !(nrm > p.min_step);
+                __syncwarp();
+                rec.record(b, iters - 1, n, x, g, withheld ? T(0) : hi, lane);
+                if (withheld) {
+                    reason = DAVO_REASON_STEP;
+                    f = f0;  // the cost at the retained iterate x_k
+                    break;
+                }
+#pragma unroll
+                for (int h = 0; h < kCols; ++h)
+                    if (lane + 32 * h < n) x[lane + 32 * h] = add_rn(x[lane + 32 * h], s[lane + 32 * h]);
+            }
             // the accepted point is bitwise the last probe whenever the search returns the probe it just made:
             // that probe's (f, grad) are the next outer iteration's evaluation
             const bool reuse = same_bits(hi, cand);
@@ -214,6 +246,15 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             const bool stop_step = !(nrm > p.min_step);                         // :203-207 (strict >)
             if (stop_step || k >= p.max_iters) {                                // :118
                 reason = stop_step ? DAVO_REASON_STEP : DAVO_REASON_CAP;
+                if (reuse) {
+                    f = cand_f;
+                    break;
+                }
+                mode = kEvalFinal;
+                continue;
+            }
+            if (Rec::kActive && rec.drop(b, k)) {                                 // :122-125, top of iteration k
+                reason = DAVO_REASON_DROPPED;
                 if (reuse) {
                     f = cand_f;
                     break;
@@ -396,6 +437,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
         if (p.fevals_out) p.fevals_out[b] = fevals;
         if (p.reason_out) p.reason_out[b] = reason;
     }
+    rec.finish(b, iters, lane);
 }
 
 }  // namespace davo

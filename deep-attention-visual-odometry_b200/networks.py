@@ -5,8 +5,9 @@ bundle-adjustment objective.
 The refinement is the hot path and runs in the sm_100a solve kernel (AngleDistanceObjective + BFGSSolver through
 the C-ABI).  The initial-guess MLP is outside this repo's scope table and is kept as the
 same stock torch modules the reference builds, with the same parameter names, so a reference checkpoint loads
-with ``load_state_dict``.  Inference (``.eval()``) only: the reference's training mode differentiates through the
-solve, which is not implemented here (BFGSSolver raises NotImplementedError).
+with ``load_state_dict``.  In training mode (and whenever the guess requires grad, as in the reference:
+create_graph = parameters.requires_grad, autograd_solvers/bfgs_solver.py:85) the solve is differentiable: gradients
+reach the MLP's weights through BFGSSolver's backward kernel (csrc/solver_train.cuh).
 """
 from __future__ import annotations
 
@@ -63,7 +64,7 @@ class CalibrationNetwork(nn.Module):
         inputs = true_projected_points.reshape(-1, 2 * self.num_views * self.num_points)
         initial_guess = self.initial_estimator(inputs)
         objective = AngleDistanceObjective(true_projected_points, visibility_mask, dtype=initial_guess.dtype)
-        info = self.solver(initial_guess.detach(), objective, return_info=True)
+        info = self.solver(initial_guess, objective, return_info=True)
         if return_info:
             return info
         if return_error:

@@ -81,6 +81,24 @@ class CalibrationObjective:
         _lib.check(st, "davo_eval_cost_grad")
         return cost, grad
 
+    def as_float64(self) -> "CalibrationObjective":
+        """This problem set with float64 buffers (the backward pass of the differentiable solve runs in float64);
+        `self` when it already is, otherwise a cached twin that shares nothing mutable."""
+        if self.dtype == torch.float64:
+            return self
+        twin = getattr(self, "_twin64", None)
+        if twin is None:
+            import copy
+            d0, d1, w = self.data0, self.data1, self.weights  # stages a lazily staged problem set first
+            twin = copy.copy(self)
+            twin.dtype = torch.float64
+            if hasattr(twin, "_raw"):
+                twin._raw = None
+            up = lambda t: None if t is None else t.double()
+            twin.data0, twin.data1, twin.weights = up(d0), up(d1), up(w)
+            self._twin64 = twin
+        return twin
+
     # ---- the reference's calling convention ------------------------------------------------------
     def __call__(self, params: torch.Tensor, mask: torch.Tensor | None = None) -> torch.Tensor:
         index = None

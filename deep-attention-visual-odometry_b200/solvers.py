@@ -47,6 +47,86 @@ class SolveBuffers(NamedTuple):
                    torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device))
 
 
+class _DifferentiableSolve(torch.autograd.Function):
+    """x_out = solve(x0) with d loss / d x0 from the stored-iterate reverse sweep (csrc/solver_train.cuh).
+
+    Forward: davo_solve_training on the objective's device in the parameters' precision; when a gradient is wanted
+    the accepted iterates (x_k, g_k, alpha_k) are recorded and compacted to sum(steps) rows.  Backward:
+    davo_solve_backward in float64 (a float32 trajectory and problem set are up-cast)."""
+
+    @staticmethod
+    def forward(ctx, parameters, obj, cfg, record):
+        device = obj.device
+        n, B = obj.n, obj.B
+        batch_shape = parameters.shape[:-1]
+        data0 = obj.data0  # stages a lazily staged (host-input) problem set
+        K = int(cfg["iterations"])
+        with torch.cuda.device(device):
+            x0 = parameters.detach().to(device=device, dtype=obj.dtype).reshape(B, n).contiguous()
+            buf = SolveBuffers.allocate(B, n, obj.dtype, device)
+            traj = (None, None, None, None)
+            if record:
+                item = torch.empty((), dtype=obj.dtype).element_size()
+                need = B * max(K, 1) * (2 * n + 1) * item
+                if need > cfg["budget"]:
+                    raise _lib.DavoError(
+                        f"recording {B} problems x {K} iterations x {n} parameters needs {need / 2**30:.1f} GiB; lower "
+                        "training_iterations or raise BFGSSolver.trajectory_budget_bytes")
+                traj = (torch.empty(B, max(K, 1), n, dtype=obj.dtype, device=device),
+                        torch.empty(B, max(K, 1), n, dtype=obj.dtype, device=device),
+                        torch.empty(B, max(K, 1), dtype=obj.dtype, device=device),
+                        torch.zeros(B, dtype=torch.int32, device=device))
+            desc = obj.desc(iterations=K, strong=True, sufficient_decrease=cfg["sufficient_decrease"],
+                            curvature=cfg["curvature"], error_threshold=cfg["error_threshold"],
+                            minimum_step=cfg["minimum_step"])
+            tdesc = _lib.TrainingDesc(max(K, 1), int(cfg["return_second_last"]), float(cfg["drop_path_p"]),
+                                      int(cfg["seed"]), 0.0)
+            st = _lib.lib().davo_solve_training(
+                ctypes.byref(desc), ctypes.byref(tdesc), _lib.ptr(data0), _lib.ptr(obj.data1), _lib.ptr(obj.weights),
+                _lib.ptr(x0), _lib.ptr(buf.x), _lib.ptr(buf.cost), _lib.ptr(buf.converged), _lib.ptr(buf.iterations),
+                _lib.ptr(buf.evaluations), _lib.ptr(buf.reason), _lib.ptr(traj[0]), _lib.ptr(traj[1]),
+                _lib.ptr(traj[2]), _lib.ptr(traj[3]), _lib.ptr(buf.workspace), _lib.stream_ptr())
+            _lib.check(st, "davo_solve_training")
+            if record:
+                # keep only the recorded rows: [sum(steps), n] instead of [B, K, n]
+                steps = traj[3].long()
+                keep = torch.arange(max(K, 1), device=device).unsqueeze(0) < steps.unsqueeze(1)
+                ctx.traj = (traj[0][keep].double(), traj[1][keep].double(), traj[2][keep].double(), traj[3],
+                            torch.cumsum(steps, 0) - steps)
+                ctx.obj, ctx.cfg = obj, cfg
+        ctx.in_device, ctx.in_dtype, ctx.in_shape = parameters.device, parameters.dtype, parameters.shape
+        out_dev = parameters.device
+        outs = (buf.x.reshape(parameters.shape).to(device=out_dev, dtype=parameters.dtype),
+                buf.cost.reshape(batch_shape).to(out_dev), buf.converged.reshape(batch_shape).to(out_dev).bool(),
+                buf.iterations.reshape(batch_shape).to(out_dev), buf.evaluations.reshape(batch_shape).to(out_dev),
+                buf.reason.reshape(batch_shape).to(out_dev))
+        ctx.mark_non_differentiable(*outs[1:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, grad_x, *unused):
+        if not hasattr(ctx, "traj"):
+            return None, None, None, None
+        obj, cfg = ctx.obj.as_float64(), ctx.cfg
+        device, n, B = obj.device, obj.n, obj.B
+        tx, tg, ta, tlen, offsets = ctx.traj
+        with torch.cuda.device(device):
+            g_out = grad_x.detach().to(device=device, dtype=torch.float64).reshape(B, n).contiguous()
+            g_x0 = torch.empty_like(g_out)
+            rows = int(tx.shape[0])
+            scratch = torch.empty(max(rows, 1) * (n * n + n), dtype=torch.float64, device=device)
+            workspace = torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+            desc = obj.desc(iterations=int(cfg["iterations"]), strong=True)
+            tdesc = _lib.TrainingDesc(max(int(cfg["iterations"]), 1), int(cfg["return_second_last"]), 0.0, 0, 0.0)
+            st = _lib.lib().davo_solve_backward(
+                ctypes.byref(desc), ctypes.byref(tdesc), _lib.ptr(obj.data0), _lib.ptr(obj.data1),
+                _lib.ptr(obj.weights), _lib.ptr(tx), _lib.ptr(tg), _lib.ptr(ta), _lib.ptr(tlen), _lib.ptr(offsets),
+                _lib.ptr(offsets), _lib.ptr(scratch), _lib.ptr(g_out), _lib.ptr(g_x0), _lib.ptr(workspace),
+                _lib.stream_ptr())
+            _lib.check(st, "davo_solve_backward")
+        return g_x0.reshape(ctx.in_shape).to(device=ctx.in_device, dtype=ctx.in_dtype), None, None, None
+
+
 _STREAMS: dict = {}
 
 
@@ -74,9 +154,16 @@ class BFGSSolver(Module):
     arguments and defaults, same ``forward(parameters, error_function) -> parameters`` contract, batch
     dimensions ``(B..)`` of any rank.  ``error_function`` must be a CalibrationObjective descriptor.
 
-    Eval-mode semantics: the stochastic training-time behaviours (drop-path, return_second_last) and
-    differentiating through the solve are not implemented and raise NotImplementedError.
+    Training mode (`self.training`) uses the training thresholds, drop-path and return_second_last exactly as
+    bfgs_solver.py:88-93,122-125,196-212; parameters that require grad make the solve differentiable (the
+    reference's create_graph=True, :85,133-135): the forward keeps the accepted iterates and `backward` runs the
+    reverse sweep through them in a CUDA kernel (csrc/solver_train.cuh).  Drop-path draws come from a counter-based
+    device generator seeded from torch's default generator (torch.manual_seed makes them reproducible); they are
+    not torch.rand's numbers.
     """
+
+    #: refuse to record trajectories larger than this (bytes): B x training_iterations x (2n+1) values
+    trajectory_budget_bytes = 32 << 30
 
     def __init__(self, sufficient_decrease: float = 1e-4, curvature: float = 0.9, error_threshold: float = 1e-4,
                  iterations: int = 1000, minimum_step: float = 1e-8, drop_path_p: float = 0.1,
@@ -96,13 +183,7 @@ class BFGSSolver(Module):
 
     def forward(self, parameters: torch.Tensor, error_function, return_info: bool = False, out=None):
         obj = _require_descriptor(error_function)
-        if parameters.requires_grad:
-            raise NotImplementedError("differentiating through the solve (create_graph) is not implemented")
         if self.training:
-            if self.drop_path_p > 0.0 or self.return_second_last:
-                raise NotImplementedError(
-                    "training-mode drop-path / return_second_last are not implemented: call .eval() "
-                    "(the reference's default training mode randomly retires 10% of problems per iteration)")
             error_threshold, iterations = self.training_error_threshold, self.training_iterations
         else:
             error_threshold, iterations = self.error_threshold, self.iterations
@@ -115,6 +196,9 @@ class BFGSSolver(Module):
         if tuple(batch_shape) != obj.batch_shape and parameters.numel() // n != obj.B:
             raise ValueError(f"parameters batch {tuple(batch_shape)} does not match the objective's {obj.batch_shape}")
         out_dev = parameters.device
+        differentiable = parameters.requires_grad and torch.is_grad_enabled()
+        if differentiable or (self.training and (self.drop_path_p > 0.0 or self.return_second_last)):
+            return self._forward_training(parameters, obj, error_threshold, iterations, differentiable, return_info)
         if getattr(obj, "is_staged", True):
             x0 = parameters.detach().to(device=obj.device, dtype=obj.dtype, non_blocking=True).reshape(obj.B, n)
             buf = self.solve_into(x0.contiguous(), obj, error_threshold=error_threshold, iterations=iterations,
@@ -140,6 +224,21 @@ class BFGSSolver(Module):
         back = lambda t: t.reshape(batch_shape).to(out_dev)
         return SolveInfo(result, back(buf.cost), back(buf.converged).bool(), back(buf.iterations),
                          back(buf.evaluations), back(buf.reason))
+
+    def _forward_training(self, parameters, obj, error_threshold, iterations, differentiable, return_info):
+        """Training-mode / differentiable solve (davo_solve_training, davo_solve_backward)."""
+        seed = 0
+        drop_p = self.drop_path_p if self.training else 0.0
+        if drop_p > 0.0:  # one draw from torch's default generator per call: torch.manual_seed reproduces a run
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        cfg = dict(error_threshold=error_threshold, iterations=iterations, drop_path_p=drop_p, seed=seed,
+                   return_second_last=bool(self.training and self.return_second_last),
+                   sufficient_decrease=self.sufficient_decrease, curvature=self.curvature,
+                   minimum_step=self.minimum_step, budget=self.trajectory_budget_bytes)
+        x, cost, converged, iters, fevals, reason = _DifferentiableSolve.apply(parameters, obj, cfg, differentiable)
+        if not return_info:
+            return x
+        return SolveInfo(x, cost, converged, iters, fevals, reason)
 
     #: problems per chunk of the streamed (host-input) path; each chunk is one H2D copy + stage + solve
     stream_chunk = 4096

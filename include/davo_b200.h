@@ -106,6 +106,8 @@ typedef enum davo_status {
 #define DAVO_REASON_STEP 1      /* |step| <= minimum_step       (bfgs_solver.py:203-207)        */
 #define DAVO_REASON_CAP 2       /* `iterations` outer iterations (bfgs_solver.py:118)           */
 #define DAVO_REASON_NAN 3       /* cost is NaN: `NaN > thr` is false, the reference retires it  */
+/* 4 is internal (hand-off between the two launches of a DISTORT10 solve) and never returned */
+#define DAVO_REASON_DROPPED 5   /* training mode: retired by drop-path (bfgs_solver.py:122-125) */
 
 /* ---- problem descriptor ---------------------------------------------------------------
  * Mirrors BFGSSolver.__init__ (autograd_solvers/bfgs_solver.py:49-60) and the arguments of
@@ -154,6 +156,45 @@ int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, con
                            const void* weights, const void* x0, void* x_out, void* cost_out,
                            uint8_t* converged_out, int32_t* iters_out, int32_t* fevals_out,
                            int32_t* reason_out, void* workspace, void* stream);
+
+/* ---- training-mode / differentiable solve -------------------------------------------------------------
+ * Replaces BFGSSolver.forward when `self.training` is set or the parameters require grad
+ * (autograd_solvers/bfgs_solver.py:80-215): the caller passes the training thresholds in `desc`
+ * (training_error_threshold / training_iterations, :88-93); drop-path (:122-125) retires each problem at the top
+ * of every outer iteration with probability drop_path_p, from a counter-based generator that is a pure function
+ * of (seed, problem index, iteration); return_second_last (:196-212) withholds the step that retires a problem on
+ * its length.  One warp per problem on the generic solver, every model, n <= 128. */
+typedef struct davo_training_desc {
+    int32_t capacity;           /* rows per problem of the trajectory buffers (>= max_iters records every step) */
+    int32_t return_second_last; /* BFGSSolver(return_second_last=...)                                           */
+    double drop_path_p;         /* BFGSSolver(drop_path_p=...); 0 = never                                       */
+    uint64_t seed;
+    double hvp_rel_step;        /* backward: |h v| = hvp_rel_step (1 + |x|) in the central differences; 0 = 5e-7 */
+} davo_training_desc;
+
+/* Forward.  Outputs as davo_solve_calibration (reason_out may also be DAVO_REASON_DROPPED).  The trajectory the
+ * backward pass needs (create_graph=True, :85,133-135): traj_x[B,capacity,n] = iterate at which line search k
+ * started, traj_g[B,capacity,n] = its gradient, traj_alpha[B,capacity] = step length applied (0 where
+ * return_second_last withheld the step), traj_len[B] = recorded steps.  All four NULL: nothing is recorded. */
+int davo_solve_training(const davo_problem_desc* desc, const davo_training_desc* train, const void* data0,
+                        const void* data1, const void* weights, const void* x0, void* x_out, void* cost_out,
+                        uint8_t* converged_out, int32_t* iters_out, int32_t* fevals_out, int32_t* reason_out,
+                        void* traj_x, void* traj_g, void* traj_alpha, int32_t* traj_len, void* workspace,
+                        void* stream);
+
+/* Backward: grad_x0[B,n] = d loss / d x0 given grad_out[B,n] = d loss / d x_out, i.e. what torch.autograd computes
+ * through the reference's unrolled iteration (eq. 6.17 update, eq. 6.20 scale, InverseCurvature.backward of
+ * utils/func_inverse_curvature.py:22-37, alpha constant, Hessian-vector products of the objective).
+ * desc->dtype must be DAVO_F64 (every buffer float64).  Problem b's recorded steps are rows traj_offset[b] ..
+ * traj_offset[b] + traj_len[b] - 1 of traj_x[rows,n], traj_g[rows,n], traj_alpha[rows]: traj_offset[b] = b * capacity
+ * reads the forward's buffers as they are, an exclusive prefix sum of traj_len reads a compacted copy.
+ * scratch_offset[B] = exclusive prefix sum of traj_len (int64); scratch = sum(traj_len) * (n*n + n) float64 values
+ * (the replayed inverse Hessians and search directions). */
+int davo_solve_backward(const davo_problem_desc* desc, const davo_training_desc* train, const void* data0,
+                        const void* data1, const void* weights, const void* traj_x, const void* traj_g,
+                        const void* traj_alpha, const int32_t* traj_len, const int64_t* traj_offset,
+                        const int64_t* scratch_offset, void* scratch, const void* grad_out, void* grad_x0,
+                        void* workspace, void* stream);
 
 /* One evaluation of the objective and its gradient for every problem: cost[B], grad[B,n]
  * (grad may be NULL).  Replaces `error_function(...)` + torch.autograd.grad

@@ -190,3 +190,13 @@ def solve_with_grad(prob_batch: Problem, x0, w, **kw):
         xs.append(x)
         grads.append(solve_backward(prob, traj, w[b]))
     return np.stack(xs), np.stack(grads)
+
+
+def drop_path_uniform(seed, problem, iteration):
+    """The uniform in [0, 1) the training kernel draws for (problem, iteration) — csrc/train_params.cuh
+    drop_path_bits: Philox4x32-10 with counter (problem, 0, iteration, 'DROP'), key = seed; word 0, top 24 bits.
+    The problem keeps updating iff u > drop_path_p (bfgs_solver.py:122-125)."""
+    from . import gen_oracle
+    c = np.array([[problem & 0xFFFFFFFF, 0, iteration, 0x44524F50]], dtype=np.uint64)
+    w = gen_oracle.philox4x32(c, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    return float(np.float32(int(w[0, 0]) >> 8) * np.float32(1.0 / 16777216.0))

@@ -273,13 +273,12 @@ def test_solver_reference_behaviours():
     assert errs[-1] < 1e-6
 
 
-def test_solver_refuses_unimplemented_modes():
+def test_solver_default_training_mode_and_bad_width():
     obj = davo_b200.AnalyticObjective("sphere", (2,), 3, dtype=torch.float32)
     x0 = torch.ones(2, 3)
-    with pytest.raises(NotImplementedError):
-        davo_b200.BFGSSolver()(x0, obj)  # training mode with drop-path 0.1 (the reference default)
-    with pytest.raises(NotImplementedError):
-        davo_b200.BFGSSolver().eval()(x0.clone().requires_grad_(True), obj)
+    out = davo_b200.BFGSSolver()(x0, obj)  # training mode with drop-path 0.1 (the reference default)
+    assert out.shape == x0.shape and not out.requires_grad
+    assert davo_b200.BFGSSolver().eval()(x0.clone().requires_grad_(True), obj).requires_grad  # create_graph path
     with pytest.raises(ValueError):
         davo_b200.BFGSSolver().eval()(torch.ones(2, 4), obj)
     out = davo_b200.BFGSSolver(drop_path_p=0.0, training_error_threshold=1e-2)(x0, obj)  # training thresholds
@@ -754,8 +753,7 @@ def test_calibration_network_forward_refines_its_initial_guess():
     assert torch.equal(direct.parameters, params) and torch.equal(direct.cost, err)
     assert bool((err <= start).all()) and float(err.median()) < 0.5 * float(start.median())
     net.train()
-    with pytest.raises(NotImplementedError):
-        net(obs, vis)
+    assert net(obs, vis).requires_grad  # training mode differentiates through the solve (tests/test_gpu_training.py)
 
 
 def test_randomised_sweep_against_oracle():
