@@ -90,7 +90,7 @@ def lib() -> ctypes.CDLL:
         L.davo_solve_calibration.argtypes = [dp] + [vp] * 12
         tp = ctypes.POINTER(TrainingDesc)
         L.davo_solve_training.argtypes = [dp, tp] + [vp] * 16
-        L.davo_solve_backward.argtypes = [dp, tp] + [vp] * 14
+        L.davo_solve_backward.argtypes = [dp, tp] + [vp] * 15
         L.davo_eval_cost_grad.argtypes = [dp] + [vp] * 7
         L.davo_line_search.argtypes = [dp] + [vp] * 10
         L.davo_stage_matches.argtypes = [dp] + [vp] * 5

@@ -193,7 +193,7 @@ int davo_solve_backward(const davo_problem_desc* desc, const davo_training_desc*
                         const void* data1, const void* weights, const void* traj_x, const void* traj_g,
                         const void* traj_alpha, const int32_t* traj_len, const int64_t* traj_offset,
                         const int64_t* scratch_offset, void* scratch, const void* grad_out, void* grad_x0,
-                        void* workspace, void* stream) {
+                        void* grad_data, void* workspace, void* stream) {
     int st = check_desc(desc);
     if (st) return st;
     if (!train) return DAVO_ERR_NULL_POINTER;
@@ -207,7 +207,8 @@ int davo_solve_backward(const davo_problem_desc* desc, const davo_training_desc*
     BackwardParams<double> bp{static_cast<const double*>(traj_x), static_cast<const double*>(traj_g),
                               static_cast<const double*>(traj_alpha), traj_len, traj_offset, scratch_offset,
                               static_cast<double*>(scratch), static_cast<const double*>(grad_out),
-                              static_cast<double*>(grad_x0), train->hvp_rel_step > 0.0 ? train->hvp_rel_step : 5e-7};
+                              static_cast<double*>(grad_x0), static_cast<double*>(grad_data),
+                              train->hvp_rel_step > 0.0 ? train->hvp_rel_step : 5e-7};
     return launch_train_backward(p, bp, static_cast<cudaStream_t>(stream));
 }
 

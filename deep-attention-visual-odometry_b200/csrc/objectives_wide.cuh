@@ -86,6 +86,47 @@ struct Distort10WideObjective {
     }
 };
 
+// d loss / d (problem data) of the differentiable solve.  x_out depends on the data only through the gradients
+// g_k = grad f(x_k; data), so d loss / d data = sum_k d/d data [ g_k . gbar_k ] with gbar_k the adjoint of g_k in the
+// reverse sweep (solver_train.cuh).  Generic objectives: not provided.
+template <typename Obj, typename T>
+struct DataGradient {
+    static constexpr bool kSupported = false;
+    __device__ static void accumulate(Obj&, const T*, const T*, T*, int) {}
+};
+
+// DISTORT10, observations: f = sum w |proj_i(x) - obs_i|^2 gives d (g . v) / d obs_i = -2 w_i J_i v with J_i the
+// 2 x 10 Jacobian of (u', v') at match i (camera_model/distorted_camera_model.py:59-86 differentiated; SURVEY.md
+// Appendix C).  out: this problem's [N, 2] row block, owned by the calling warp.
+template <typename T>
+struct DataGradient<Distort10WideObjective<T>, T> {
+    static constexpr bool kSupported = true;
+    __device__ static void accumulate(Distort10WideObjective<T>& obj, const T* th, const T* v, T* out, int lane) {
+        Intrinsics<T> I;
+        I.load(th);
+        const T vcx = v[DAVO_CX], vcy = v[DAVO_CY], vk1 = v[DAVO_K1], vk2 = v[DAVO_K2], vk3 = v[DAVO_K3],
+                vp1 = v[DAVO_P1], vp2 = v[DAVO_P2], vfx = v[DAVO_FX], vs = v[DAVO_S], vfy = v[DAVO_FY];
+        for (int i = lane; i < obj.p.N; i += 32) {
+            const typename Vec4<T>::type m = obj.matches[i];
+            const T a = m.x, b = m.y;
+            const T u = I.fx * a + I.s * b, w_ = I.fy * b;
+            const T uu = u * u, vv = w_ * w_, uv = u * w_, r2 = uu + vv, r4 = r2 * r2, r6 = r4 * r2;
+            const T rad = T(1) + I.k1 * r2 + I.k2 * r4 + I.k3 * r6;
+            const T radp2 = T(2) * I.k1 + T(4) * I.k2 * r2 + T(6) * I.k3 * r4;  // 2 d rad / d r2
+            const T Duu = rad + uu * radp2 + T(2) * I.p1 * w_ + T(6) * I.p2 * u;
+            const T Dvv = rad + vv * radp2 + T(6) * I.p1 * w_ + T(2) * I.p2 * u;
+            const T Duv = uv * radp2 + T(2) * I.p1 * u + T(2) * I.p2 * w_;
+            const T du = vfx * a + vs * b, dv = vfy * b;  // d(u, v) along v
+            const T dk = vk1 * r2 + vk2 * r4 + vk3 * r6;
+            const T Ju = vcx + u * dk + T(2) * uv * vp1 + (r2 + T(2) * uu) * vp2 + Duu * du + Duv * dv;
+            const T Jv = vcy + w_ * dk + (r2 + T(2) * vv) * vp1 + T(2) * uv * vp2 + Duv * du + Dvv * dv;
+            const T wt = obj.p.has_w ? obj.weights[i] : T(1);
+            out[2 * i] -= T(2) * wt * Ju;
+            out[2 * i + 1] -= T(2) * wt * Jv;
+        }
+    }
+};
+
 // The analytic objectives (n <= 16): AnalyticObjective's arithmetic, gradient written out as a vector.
 template <typename T>
 struct AnalyticWideObjective {

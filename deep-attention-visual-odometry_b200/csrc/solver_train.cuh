@@ -19,6 +19,7 @@
 #pragma once
 #include "davo_common.cuh"
 #include "solver_wide.cuh"
+#include "objectives_wide.cuh"
 
 namespace davo {
 
@@ -119,6 +120,8 @@ __device__ __forceinline__ void backward_one(Obj& obj, const SolveParams<T>& p, 
     const T* A = bp.traj_alpha + row0;
     __syncwarp();
     for (int c = lane; c < n; c += 32) xbar[c] = bp.grad_out[(size_t)b * n + c];
+    if (DataGradient<Obj, T>::kSupported && bp.grad_data)
+        for (int i = lane; i < 2 * p.N; i += 32) bp.grad_data[(size_t)b * p.N * 2 + i] = T(0);
     __syncwarp();
     if (K > 0) {
         // ---- (a) replay: H_k and d_k for every recorded step ----------------------------------------------
@@ -275,7 +278,10 @@ __device__ __forceinline__ void backward_one(Obj& obj, const SolveParams<T>& p, 
             __syncwarp();
             // xbar += (d g_k / d x_k)^T gbar: Hessian-vector product at x_k
             for (int c = lane; c < n; c += 32) gk[c] = X[(size_t)k * n + c];   // gk now holds x_k
+            for (int c = n + lane; c < wide_vec(n); c += 32) gk[c] = T(0);
             __syncwarp();
+            if (DataGradient<Obj, T>::kSupported && bp.grad_data)
+                DataGradient<Obj, T>::accumulate(obj, gk, gbar, bp.grad_data + (size_t)b * p.N * 2, lane);
             const T nv = sqrt(dot(gbar, gbar, n, lane));
             if (nv > T(0) && isfinite(nv)) {
                 const T nx = sqrt(dot(gk, gk, n, lane));

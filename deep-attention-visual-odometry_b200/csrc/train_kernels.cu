@@ -111,6 +111,7 @@ static int launch_train_forward_t(const SolveParams<T>& p, const TrainRecorder<T
 template <typename T, typename Obj>
 static int launch_train_backward_t(const SolveParams<T>& p, const BackwardParams<T>& bp, cudaStream_t stream) {
     if (p.n > kWideMax) return DAVO_ERR_UNSUPPORTED;
+    if (bp.grad_data && !DataGradient<Obj, T>::kSupported) return DAVO_ERR_UNSUPPORTED;
     auto kernel = train_backward_kernel<T, Obj>;
     int warps = 0;
     size_t smem = 0;

@@ -75,6 +75,7 @@ struct BackwardParams {
     T* scratch;                     // sum(traj_len) x (n*n + n): H_k then d_k per recorded step
     const T* grad_out;              // [B, n] d loss / d x_out
     T* grad_x0;                     // [B, n] d loss / d x0
+    T* grad_data;                   // DISTORT10: [B, N, 2] d loss / d observations (NULL: not wanted)
     T rel_step;
 };
 

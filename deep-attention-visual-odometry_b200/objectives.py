@@ -43,6 +43,8 @@ class CalibrationObjective:
 
     model: str = ""
     views: int = 1
+    #: a tensor of the problem data that requires grad (the solve then back-propagates into it), or None
+    differentiable_data = None
 
     def __init__(self, batch_shape, n, N, dtype, device):
         self.batch_shape = tuple(batch_shape)
@@ -134,6 +136,10 @@ class DistortionObjective(CalibrationObjective):
         if points_3d.shape[-1] != 3:
             raise ValueError("points_3d must end in a dimension of 3")
         flat = lambda t, tail: None if t is None else torch.as_tensor(t).reshape((self.B,) + tail)
+        # the differentiable solve also returns d loss / d observed_2d (davo_solve_backward, grad_data)
+        self.differentiable_data = observed_2d if observed_2d.requires_grad else None
+        detach = lambda t: t.detach() if isinstance(t, torch.Tensor) else t
+        points_3d, observed_2d, pose, weights = detach(points_3d), detach(observed_2d), detach(pose), detach(weights)
         self._raw = (flat(points_3d, (N, 3)), flat(observed_2d, (N, 2)), flat(pose, (6,)), flat(weights, (N,)))
         self._data0 = None
         self.weights = None

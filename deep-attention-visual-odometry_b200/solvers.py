@@ -55,7 +55,7 @@ class _DifferentiableSolve(torch.autograd.Function):
     davo_solve_backward in float64 (a float32 trajectory and problem set are up-cast)."""
 
     @staticmethod
-    def forward(ctx, parameters, obj, cfg, record):
+    def forward(ctx, parameters, obj, cfg, record, data):
         device = obj.device
         n, B = obj.n, obj.B
         batch_shape = parameters.shape[:-1]
@@ -95,6 +95,8 @@ class _DifferentiableSolve(torch.autograd.Function):
                             torch.cumsum(steps, 0) - steps)
                 ctx.obj, ctx.cfg = obj, cfg
         ctx.in_device, ctx.in_dtype, ctx.in_shape = parameters.device, parameters.dtype, parameters.shape
+        if data is not None:
+            ctx.data_device, ctx.data_dtype, ctx.data_shape = data.device, data.dtype, data.shape
         out_dev = parameters.device
         outs = (buf.x.reshape(parameters.shape).to(device=out_dev, dtype=parameters.dtype),
                 buf.cost.reshape(batch_shape).to(out_dev), buf.converged.reshape(batch_shape).to(out_dev).bool(),
@@ -106,13 +108,15 @@ class _DifferentiableSolve(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_x, *unused):
         if not hasattr(ctx, "traj"):
-            return None, None, None, None
+            return None, None, None, None, None
         obj, cfg = ctx.obj.as_float64(), ctx.cfg
         device, n, B = obj.device, obj.n, obj.B
         tx, tg, ta, tlen, offsets = ctx.traj
         with torch.cuda.device(device):
             g_out = grad_x.detach().to(device=device, dtype=torch.float64).reshape(B, n).contiguous()
             g_x0 = torch.empty_like(g_out)
+            want_data = ctx.needs_input_grad[4]
+            g_data = torch.empty(B, obj.N, 2, dtype=torch.float64, device=device) if want_data else None
             rows = int(tx.shape[0])
             scratch = torch.empty(max(rows, 1) * (n * n + n), dtype=torch.float64, device=device)
             workspace = torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)
@@ -121,10 +125,13 @@ class _DifferentiableSolve(torch.autograd.Function):
             st = _lib.lib().davo_solve_backward(
                 ctypes.byref(desc), ctypes.byref(tdesc), _lib.ptr(obj.data0), _lib.ptr(obj.data1),
                 _lib.ptr(obj.weights), _lib.ptr(tx), _lib.ptr(tg), _lib.ptr(ta), _lib.ptr(tlen), _lib.ptr(offsets),
-                _lib.ptr(offsets), _lib.ptr(scratch), _lib.ptr(g_out), _lib.ptr(g_x0), _lib.ptr(workspace),
-                _lib.stream_ptr())
+                _lib.ptr(offsets), _lib.ptr(scratch), _lib.ptr(g_out), _lib.ptr(g_x0), _lib.ptr(g_data),
+                _lib.ptr(workspace), _lib.stream_ptr())
             _lib.check(st, "davo_solve_backward")
-        return g_x0.reshape(ctx.in_shape).to(device=ctx.in_device, dtype=ctx.in_dtype), None, None, None
+        if want_data:
+            g_data = g_data.reshape(ctx.data_shape).to(device=ctx.data_device, dtype=ctx.data_dtype)
+        g_par = g_x0.reshape(ctx.in_shape).to(device=ctx.in_device, dtype=ctx.in_dtype) if ctx.needs_input_grad[0] else None
+        return g_par, None, None, None, g_data
 
 
 _STREAMS: dict = {}
@@ -196,7 +203,8 @@ class BFGSSolver(Module):
         if tuple(batch_shape) != obj.batch_shape and parameters.numel() // n != obj.B:
             raise ValueError(f"parameters batch {tuple(batch_shape)} does not match the objective's {obj.batch_shape}")
         out_dev = parameters.device
-        differentiable = parameters.requires_grad and torch.is_grad_enabled()
+        differentiable = torch.is_grad_enabled() and (parameters.requires_grad or
+                                                      getattr(obj, "differentiable_data", None) is not None)
         if differentiable or (self.training and (self.drop_path_p > 0.0 or self.return_second_last)):
             return self._forward_training(parameters, obj, error_threshold, iterations, differentiable, return_info)
         if getattr(obj, "is_staged", True):
@@ -235,7 +243,8 @@ class BFGSSolver(Module):
                    return_second_last=bool(self.training and self.return_second_last),
                    sufficient_decrease=self.sufficient_decrease, curvature=self.curvature,
                    minimum_step=self.minimum_step, budget=self.trajectory_budget_bytes)
-        x, cost, converged, iters, fevals, reason = _DifferentiableSolve.apply(parameters, obj, cfg, differentiable)
+        x, cost, converged, iters, fevals, reason = _DifferentiableSolve.apply(
+            parameters, obj, cfg, differentiable, obj.differentiable_data if differentiable else None)
         if not return_info:
             return x
         return SolveInfo(x, cost, converged, iters, fevals, reason)

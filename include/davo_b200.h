@@ -189,12 +189,14 @@ int davo_solve_training(const davo_problem_desc* desc, const davo_training_desc*
  * traj_offset[b] + traj_len[b] - 1 of traj_x[rows,n], traj_g[rows,n], traj_alpha[rows]: traj_offset[b] = b * capacity
  * reads the forward's buffers as they are, an exclusive prefix sum of traj_len reads a compacted copy.
  * scratch_offset[B] = exclusive prefix sum of traj_len (int64); scratch = sum(traj_len) * (n*n + n) float64 values
- * (the replayed inverse Hessians and search directions). */
+ * (the replayed inverse Hessians and search directions).
+ * grad_data (may be NULL): d loss / d problem data.  DISTORT10: [B,N,2], the gradient with respect to the
+ * observations (u*, v*) of the staged matches; other models: DAVO_ERR_UNSUPPORTED when not NULL. */
 int davo_solve_backward(const davo_problem_desc* desc, const davo_training_desc* train, const void* data0,
                         const void* data1, const void* weights, const void* traj_x, const void* traj_g,
                         const void* traj_alpha, const int32_t* traj_len, const int64_t* traj_offset,
                         const int64_t* scratch_offset, void* scratch, const void* grad_out, void* grad_x0,
-                        void* workspace, void* stream);
+                        void* grad_data, void* workspace, void* stream);
 
 /* One evaluation of the objective and its gradient for every problem: cost[B], grad[B,n]
  * (grad may be NULL).  Replaces `error_function(...)` + torch.autograd.grad

@@ -175,3 +175,25 @@ def test_calibration_network_trains_through_the_solve():
     before = [p.detach().clone() for p in net.initial_estimator.parameters()]
     opt.step()
     assert any(not torch.equal(a, p.detach()) for a, p in zip(before, net.initial_estimator.parameters()))
+
+
+@pytest.mark.parametrize("setting", SETTINGS)
+def test_gradient_with_respect_to_observations(setting):
+    """d(sum(w * x_out)) / d observed_2d of the distortion objective against the reference's autograd."""
+    g = load_golden("training")
+    skw = g["meta"]["settings"][setting]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    obs = t(g["d10_obs"]).requires_grad_(True)
+    obj = davo_b200.DistortionObjective(t(g["d10_points"]), obs, t(g["d10_pose"]))
+    x0 = t(g["d10_x0"]).requires_grad_(True)
+    x = train_solver(skw)(x0, obj)
+    g_x0, g_obs = torch.autograd.grad((x * t(g["d10_w"])).sum(), [x0, obs])
+    assert relative_gradient_error(g_x0.numpy(), g[f"d10_{setting}_grad_x0"]) <= 1e-6
+    want = g[f"d10_{setting}_grad_obs"]
+    err = np.abs(g_obs.numpy() - want).max() / np.abs(want).max()
+    print("d10", setting, "observation gradient error", err)
+    assert err <= 1e-6
+    # data gradient alone (parameters do not require grad)
+    x = train_solver(skw)(t(g["d10_x0"]), obj)
+    (g_only,) = torch.autograd.grad((x * t(g["d10_w"])).sum(), [obs])
+    assert torch.equal(g_only, g_obs)
