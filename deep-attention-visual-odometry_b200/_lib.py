@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DAVO_B200_LIB") or os.path.join(_HERE, "libdavo_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 WORKSPACE_BYTES = 256
 F32, F64 = 0, 1
 
@@ -29,6 +29,7 @@ REASON_NAMES = {0: "threshold", 1: "step", 2: "cap", 3: "nan", 5: "dropped"}
 EXPORTED = ("davo_abi_version", "davo_strerror", "davo_launch_count", "davo_solve_calibration",
             "davo_solve_training", "davo_solve_backward", "davo_eval_cost_grad", "davo_line_search", "davo_stage_matches", "davo_project",
             "davo_project_jacobian", "davo_least_squares", "davo_bfgs_update", "davo_bfgs_initial_scale",
+            "davo_interpolate_alpha", "davo_interpolate_alpha_backward",
             "davo_generate_distort10", "davo_generate_joint", "davo_generate_views_and_points")
 
 
@@ -36,7 +37,8 @@ class ProblemDesc(ctypes.Structure):
     """davo_problem_desc (include/davo_b200.h)."""
 
     _fields_ = [(k, ctypes.c_int32) for k in
-                ("B", "N", "V", "n", "model", "dtype", "max_iters", "max_ls_iters", "strong", "has_weights")] + \
+                ("B", "N", "V", "n", "model", "dtype", "max_iters", "max_ls_iters", "strong", "has_weights",
+                 "zoom_interpolation", "reserved0")] + \
                [(k, ctypes.c_double) for k in ("sufficient_decrease", "curvature", "error_threshold", "minimum_step")]
 
 
@@ -99,6 +101,8 @@ def lib() -> ctypes.CDLL:
         L.davo_least_squares.argtypes = [i32] * 4 + [vp] * 6
         L.davo_bfgs_update.argtypes = [i32] * 3 + [vp] * 4
         L.davo_bfgs_initial_scale.argtypes = [i32] * 3 + [vp] * 4
+        L.davo_interpolate_alpha.argtypes = [i32, i64] + [vp] * 6
+        L.davo_interpolate_alpha_backward.argtypes = [i32, i64] + [vp] * 10
         gp = ctypes.POINTER(GeneratorDesc)
         L.davo_generate_distort10.argtypes = [gp] + [vp] * 6
         L.davo_generate_joint.argtypes = [gp] + [vp] * 5
@@ -151,8 +155,10 @@ def launch_count() -> int:
 
 
 def make_desc(B, N, V, n, model, dtype, *, iterations=1000, max_ls_iters=1000, strong=True, has_weights=False,
-              sufficient_decrease=1e-4, curvature=0.9, error_threshold=1e-4, minimum_step=1e-8) -> ProblemDesc:
+              sufficient_decrease=1e-4, curvature=0.9, error_threshold=1e-4, minimum_step=1e-8,
+              zoom_interpolation=False) -> ProblemDesc:
     model_id = MODEL_IDS[model] if isinstance(model, str) else int(model)
     return ProblemDesc(int(B), int(N), int(V), int(n), model_id, dtype_code(dtype), int(iterations),
-                       int(max_ls_iters), int(bool(strong)), int(bool(has_weights)), float(sufficient_decrease),
+                       int(max_ls_iters), int(bool(strong)), int(bool(has_weights)), int(bool(zoom_interpolation)), 0,
+                       float(sufficient_decrease),
                        float(curvature), float(error_threshold), float(minimum_step))

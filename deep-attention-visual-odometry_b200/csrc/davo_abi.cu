@@ -76,6 +76,7 @@ static SolveParams<T> make_params(const davo_problem_desc* d, const void* data0,
     SolveParams<T> p{};
     p.B = d->B; p.N = d->N; p.V = d->V; p.n = d->n; p.model = d->model;
     p.max_iters = d->max_iters; p.max_ls = d->max_ls_iters; p.strong = d->strong; p.has_w = d->has_weights;
+    p.zoom = d->zoom_interpolation != 0;
     // thresholds are rounded to the arithmetic type exactly like torch rounds a Python float that meets a tensor
     p.c1 = static_cast<T>(d->sufficient_decrease);
     p.c2 = static_cast<T>(d->curvature);
@@ -141,6 +142,7 @@ int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, con
         p.cost_out = static_cast<float*>(cost_out); p.converged_out = converged_out;
         p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
         p.queue = static_cast<unsigned*>(workspace);
+        if (p.zoom) return launch_train_forward<float>(p, TrainRecorder<float>{nullptr, nullptr, nullptr, nullptr, 0, 0.0f, 0, 0, 1}, s);
         return DAVO_DISPATCH(solve, f32, p, s);
     }
     SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
@@ -148,6 +150,7 @@ int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, con
     p.cost_out = static_cast<double*>(cost_out); p.converged_out = converged_out;
     p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
     p.queue = static_cast<unsigned*>(workspace);
+    if (p.zoom) return launch_train_forward<double>(p, TrainRecorder<double>{nullptr, nullptr, nullptr, nullptr, 0, 0.0f, 0, 0, 1}, s);
     return DAVO_DISPATCH(solve, f64, p, s);
 }
 
@@ -175,7 +178,8 @@ int davo_solve_training(const davo_problem_desc* desc, const davo_training_desc*
         p.queue = static_cast<unsigned*>(workspace);
         TrainRecorder<float> rec{static_cast<float*>(traj_x), static_cast<float*>(traj_g),
                                  static_cast<float*>(traj_alpha), traj_len, train->capacity,
-                                 static_cast<float>(train->drop_path_p), train->seed, train->return_second_last};
+                                 static_cast<float>(train->drop_path_p), train->seed, train->return_second_last,
+                                 desc->zoom_interpolation != 0};
         return launch_train_forward<float>(p, rec, s);
     }
     SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
@@ -185,7 +189,8 @@ int davo_solve_training(const davo_problem_desc* desc, const davo_training_desc*
     p.queue = static_cast<unsigned*>(workspace);
     TrainRecorder<double> rec{static_cast<double*>(traj_x), static_cast<double*>(traj_g),
                               static_cast<double*>(traj_alpha), traj_len, train->capacity,
-                              static_cast<float>(train->drop_path_p), train->seed, train->return_second_last};
+                              static_cast<float>(train->drop_path_p), train->seed, train->return_second_last,
+                                 desc->zoom_interpolation != 0};
     return launch_train_forward<double>(p, rec, s);
 }
 
@@ -246,13 +251,55 @@ int davo_line_search(const davo_problem_desc* desc, const void* data0, const voi
         p.x0 = static_cast<const float*>(x); p.dir = static_cast<const float*>(direction);
         p.base_cost = static_cast<const float*>(base_cost); p.base_grad = static_cast<const float*>(base_grad);
         p.alpha_out = static_cast<float*>(alpha_out); p.fevals_out = fevals_out;
+        if (p.zoom) return launch_line_search_generic<float>(p, s);
         return DAVO_DISPATCH(line_search, f32, p, s);
     }
     SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
     p.x0 = static_cast<const double*>(x); p.dir = static_cast<const double*>(direction);
     p.base_cost = static_cast<const double*>(base_cost); p.base_grad = static_cast<const double*>(base_grad);
     p.alpha_out = static_cast<double*>(alpha_out); p.fevals_out = fevals_out;
+    if (p.zoom) return launch_line_search_generic<double>(p, s);
     return DAVO_DISPATCH(line_search, f64, p, s);
+}
+
+int davo_interpolate_alpha(int32_t dtype, int64_t k, const void* alpha_1, const void* alpha_2, const void* value_1,
+                           const void* value_2, void* out, void* stream) {
+    if (k < 0) return DAVO_ERR_BAD_SHAPE;
+    if (k == 0) return DAVO_OK;
+    if (!alpha_1 || !alpha_2 || !value_1 || !value_2 || !out) return DAVO_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == DAVO_F32)
+        return launch_interpolate_alpha<float>(k, static_cast<const float*>(alpha_1), static_cast<const float*>(alpha_2),
+                                               static_cast<const float*>(value_1), static_cast<const float*>(value_2),
+                                               static_cast<float*>(out), nullptr, nullptr, nullptr, nullptr, nullptr, s);
+    if (dtype == DAVO_F64)
+        return launch_interpolate_alpha<double>(k, static_cast<const double*>(alpha_1), static_cast<const double*>(alpha_2),
+                                                static_cast<const double*>(value_1), static_cast<const double*>(value_2),
+                                                static_cast<double*>(out), nullptr, nullptr, nullptr, nullptr, nullptr, s);
+    return DAVO_ERR_UNSUPPORTED;
+}
+
+int davo_interpolate_alpha_backward(int32_t dtype, int64_t k, const void* alpha_1, const void* alpha_2,
+                                    const void* value_1, const void* value_2, const void* grad_out,
+                                    void* grad_alpha_1, void* grad_alpha_2, void* grad_value_1, void* grad_value_2,
+                                    void* stream) {
+    if (k < 0) return DAVO_ERR_BAD_SHAPE;
+    if (k == 0) return DAVO_OK;
+    if (!alpha_1 || !alpha_2 || !value_1 || !value_2 || !grad_out) return DAVO_ERR_NULL_POINTER;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == DAVO_F32)
+        return launch_interpolate_alpha<float>(k, static_cast<const float*>(alpha_1), static_cast<const float*>(alpha_2),
+                                               static_cast<const float*>(value_1), static_cast<const float*>(value_2),
+                                               nullptr, static_cast<const float*>(grad_out),
+                                               static_cast<float*>(grad_alpha_1), static_cast<float*>(grad_alpha_2),
+                                               static_cast<float*>(grad_value_1), static_cast<float*>(grad_value_2), s);
+    if (dtype == DAVO_F64)
+        return launch_interpolate_alpha<double>(k, static_cast<const double*>(alpha_1), static_cast<const double*>(alpha_2),
+                                                static_cast<const double*>(value_1), static_cast<const double*>(value_2),
+                                                nullptr, static_cast<const double*>(grad_out),
+                                                static_cast<double*>(grad_alpha_1), static_cast<double*>(grad_alpha_2),
+                                                static_cast<double*>(grad_value_1), static_cast<double*>(grad_value_2), s);
+    return DAVO_ERR_UNSUPPORTED;
 }
 
 int davo_stage_matches(const davo_problem_desc* desc, const void* points_3d, const void* obs,

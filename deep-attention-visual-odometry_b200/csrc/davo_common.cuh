@@ -52,6 +52,21 @@ __device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
 __device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
 
+// interpolate_alpha (utils/func_interpolate_alpha.py:15-33): the zero of the line through (a1, v1), (a2, v2); the
+// midpoint when the values are equal or the zero is within 1e-3 of (or outside) the interval.  Operation by operation.
+template <typename T>
+__device__ __forceinline__ T interpolate_alpha_value(T a1, T a2, T v1, T v2, bool* nonlinear = nullptr) {
+    const T lo = a1 < a2 ? a1 : a2, hi = a1 < a2 ? a2 : a1;          // torch.minimum / maximum (:15-16)
+    const T diff = sub_rn(v2, v1);                                          // :18
+    const T inv_gradient = div_rn(sub_rn(a2, a1), diff);                         // :19
+    T cand = sub_rn(a1, mul_rn(v1, inv_gradient));   // two roundings, as torch's mul then sub                                 // :20
+    const bool nl = (diff == T(0)) || (cand < add_rn(lo, T(1e-3))) || (cand > sub_rn(hi, T(1e-3)));   // :23-29
+    if (nl) cand = div_rn(add_rn(a1, a2), T(2));                                  // :30-32
+    if (nonlinear) *nonlinear = nl;
+    return cand;
+}
+
+
 // ---- warp shuffles for float / double ---------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T shfl_xor(T v, int mask) { return __shfl_xor_sync(kFull, v, mask); }
@@ -159,6 +174,7 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 template <typename T>
 struct SolveParams {
     int B, N, V, n, model, max_iters, max_ls, strong, has_w;
+    int zoom;  // 1: secant zoom (davo_problem_desc.zoom_interpolation), generic solver only
     T c1, c2, thr, min_step;
     const T* data0;
     const T* data1;

@@ -572,4 +572,44 @@ int launch_bfgs_initial_scale(int k, int n, const T* s_, const T* y, T* scale, c
 template int launch_bfgs_initial_scale<float>(int, int, const float*, const float*, float*, cudaStream_t);
 template int launch_bfgs_initial_scale<double>(int, int, const double*, const double*, double*, cudaStream_t);
 
+// ---- interpolate_alpha (utils/func_interpolate_alpha.py) -----------------------------------------------------
+// Forward :15-33 (davo_common.cuh interpolate_alpha_value) or the custom backward :42-79, one element per thread.
+template <typename T>
+__global__ void interpolate_alpha_kernel(long long k, const T* __restrict__ a1, const T* __restrict__ a2,
+                                         const T* __restrict__ v1, const T* __restrict__ v2, T* __restrict__ out,
+                                         const T* __restrict__ grad_out, T* __restrict__ g_a1, T* __restrict__ g_a2,
+                                         T* __restrict__ g_v1, T* __restrict__ g_v2) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < k; i += (long long)gridDim.x * blockDim.x) {
+        bool nl;
+        const T x1 = a1[i], x2 = a2[i], y1 = v1[i], y2 = v2[i];
+        const T c = interpolate_alpha_value(x1, x2, y1, y2, &nl);
+        if (out) out[i] = c;
+        if (grad_out) {
+            const T go = grad_out[i];
+            const T diff = y2 - y1;
+            const T inv_gradient = (x2 - x1) / diff;            // :19 (saved for backward, :35-37)
+            const T one_on_diff = nl ? T(0) : T(1) / diff;      // :34-35
+            if (g_a1) g_a1[i] = nl ? T(0.5) * go : one_on_diff * y2 * go;                           // :56-61
+            if (g_a2) g_a2[i] = nl ? T(0.5) * go : T(-1) * one_on_diff * y1 * go;                   // :62-67
+            if (g_v1) g_v1[i] = nl ? T(0) : T(-1) * y2 * inv_gradient * one_on_diff * go;           // :68-73
+            if (g_v2) g_v2[i] = nl ? T(0) : y1 * inv_gradient * one_on_diff * go;                   // :74-79
+        }
+    }
+}
+
+template <typename T>
+int launch_interpolate_alpha(long long k, const T* a1, const T* a2, const T* v1, const T* v2, T* out, const T* grad_out,
+                             T* g_a1, T* g_a2, T* g_v1, T* g_v2, cudaStream_t s) {
+    const int threads = 256;
+    long long blocks = (k + threads - 1) / threads;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    interpolate_alpha_kernel<T><<<(unsigned)blocks, threads, 0, s>>>(k, a1, a2, v1, v2, out, grad_out, g_a1, g_a2, g_v1, g_v2);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
+}
+template int launch_interpolate_alpha<float>(long long, const float*, const float*, const float*, const float*, float*,
+                                             const float*, float*, float*, float*, float*, cudaStream_t);
+template int launch_interpolate_alpha<double>(long long, const double*, const double*, const double*, const double*,
+                                              double*, const double*, double*, double*, double*, double*, cudaStream_t);
+
 }  // namespace davo

@@ -37,6 +37,13 @@ int launch_line_search_ba_f64(const SolveParams<double>& p, cudaStream_t s);
 template <typename T>
 int launch_train_forward(const SolveParams<T>& p, const TrainRecorder<T>& rec, cudaStream_t s);
 int launch_train_backward(const SolveParams<double>& p, const BackwardParams<double>& bp, cudaStream_t s);
+// davo_line_search with the secant zoom for the models whose default line search runs on the specialised kernels
+template <typename T>
+int launch_line_search_generic(const SolveParams<T>& p, cudaStream_t s);
+// interpolate_alpha forward (out != NULL) or backward (grad_out != NULL), elementwise
+template <typename T>
+int launch_interpolate_alpha(long long k, const T* a1, const T* a2, const T* v1, const T* v2, T* out, const T* grad_out,
+                             T* g_a1, T* g_a2, T* g_v1, T* g_v2, cudaStream_t s);
 
 template <typename T>
 int launch_stage(int B, int N, const T* pts, const T* obs, const T* pose, T* staged, cudaStream_t s);

@@ -145,6 +145,9 @@ static int launch_resolve_cta(const SolveParams<T>& p, cudaStream_t stream);
 #ifndef DAVO_RESOLVE_WARP
 #define DAVO_RESOLVE_WARP 0  // 1: A/B builds re-solve the stragglers one warp per problem
 #endif
+#ifndef DAVO_EVAL_CAP_PER_ITER
+#define DAVO_EVAL_CAP_PER_ITER 4  // ... or this many evaluations per allowed outer iteration, whichever is larger
+#endif
 #ifndef DAVO_EVAL_CAP
 #define DAVO_EVAL_CAP 4096  // reference-equivalent evaluations after which the two-per-warp launch hands a problem off
 #endif
@@ -159,7 +162,8 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
 #ifdef DAVO_EVAL_CAP_EXACT  // test builds (tools/resolve_check.py): hand nearly every problem to the second launch
     const long long cap = DAVO_EVAL_CAP;
 #else
-    const long long cap = 4LL * p.max_iters > DAVO_EVAL_CAP ? 4LL * p.max_iters : DAVO_EVAL_CAP;
+    const long long per_iter = (long long)DAVO_EVAL_CAP_PER_ITER * p.max_iters;
+    const long long cap = per_iter > DAVO_EVAL_CAP ? per_iter : DAVO_EVAL_CAP;
 #endif
     p.eval_cap = p.reason_out ? (int)(cap > 0x7fffffffLL ? 0x7fffffffLL : cap) : 0;
     auto kernel = (p.N == 256)     ? half_problem_kernel<T, false, 256>   // BASELINE configs 2, 4, 5
@@ -201,18 +205,24 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
 
 // ---- second launch of a DISTORT10 solve: one CTA (4 warps) per handed-off problem ------------------------------
 #ifndef DAVO_RESOLVE_WARPS
-#define DAVO_RESOLVE_WARPS 4
+// Warps that share one evaluation x groups (DAVO_SPEC_PROBES, solver_cta.cuh) = one 512-thread CTA per straggler.
+// Measured on config 4 (64K problems; 13.7 ms of it is the first launch), whole solve: 4 x 1 (no speculation) 43.4 ms,
+// 4 x 4 32.8, 2 x 8 28.7, 1 x 16 27.6, 1 x 24 30.0, 4 x 8 (1024 threads, spills) 49.4.  The longest straggler alone
+// (47.8 K probes in ~45-probe D chains): 16.0 ms of re-solve at 4 x 4, 10.5 ms at 1 x 16 (tools/straggler_probe.py).
+#define DAVO_RESOLVE_WARPS 1
 #endif
-constexpr int kResolveWarps = DAVO_RESOLVE_WARPS;
+constexpr int kResolveWarps = DAVO_RESOLVE_WARPS;   // warps that share one evaluation
+constexpr int kResolveGroups = DAVO_SPEC_PROBES;    // groups of kResolveWarps warps: trial points per line-search round
+constexpr int kResolveCtaWarps = kResolveWarps * kResolveGroups;
 
 template <typename T>
-__global__ void __launch_bounds__(32 * kResolveWarps) resolve_cta_kernel(const SolveParams<T> p) {
+__global__ void __launch_bounds__(32 * kResolveCtaWarps, 1) resolve_cta_kernel(const SolveParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    using Obj = Distort10CtaObjective<T, kResolveWarps>;
+    using Obj = Distort10CtaObjective<T, kResolveWarps, kResolveGroups>;
     const size_t data = Obj::data_bytes(p.N, 1, false);
     CtaWorkspace<T> ws;
-    ws.carve(smem + data, p.n, kResolveWarps);
-    unsigned char* tail = smem + data + CtaWorkspace<T>::bytes(p.n, kResolveWarps);
+    ws.carve(smem + data, p.n, kResolveCtaWarps);
+    unsigned char* tail = smem + data + CtaWorkspace<T>::bytes(p.n, kResolveCtaWarps);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
     volatile unsigned* slot = reinterpret_cast<volatile unsigned*>(tail + 16);  // [0] chunk base, [1] flag mask
     Obj obj(p, smem, ws.red, bar);
@@ -241,16 +251,16 @@ __global__ void __launch_bounds__(32 * kResolveWarps) resolve_cta_kernel(const S
             const int j = __ffs(todo) - 1;
             todo &= todo - 1;
             obj.bind((int)(base + j));
-            solve_one_cta<T, kResolveWarps>(obj, p, (int)(base + j), ws);
+            solve_one_cta<T, kResolveCtaWarps>(obj, p, (int)(base + j), ws);
         }
     }
 }
 
 template <typename T>
 static int launch_resolve_cta(const SolveParams<T>& p, cudaStream_t stream) {
-    using Obj = Distort10CtaObjective<T, kResolveWarps>;
+    using Obj = Distort10CtaObjective<T, kResolveWarps, kResolveGroups>;
     auto kernel = resolve_cta_kernel<T>;
-    const size_t smem = Obj::data_bytes(p.N, 1, false) + CtaWorkspace<T>::bytes(p.n, kResolveWarps) + 32;
+    const size_t smem = Obj::data_bytes(p.N, 1, false) + CtaWorkspace<T>::bytes(p.n, kResolveCtaWarps) + 32;
     int dev = 0, sms = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -259,14 +269,14 @@ static int launch_resolve_cta(const SolveParams<T>& p, cudaStream_t stream) {
     if (!ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem))
         return DAVO_ERR_CUDA;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * kResolveWarps, smem) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * kResolveCtaWarps, smem) != cudaSuccess ||
         per_sm < 1)
         return DAVO_ERR_CUDA;
     long long grid = (long long)per_sm * sms;
     const long long need = ((long long)p.B + 31) / 32;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kernel<<<(unsigned)grid, 32 * kResolveWarps, smem, stream>>>(p);
+    kernel<<<(unsigned)grid, 32 * kResolveCtaWarps, smem, stream>>>(p);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
 }

@@ -53,6 +53,8 @@ struct CtaWorkspace {
 template <typename T, int W, bool kWeighted, int kV = 0, int kN = 0>
 struct JointCtaObjective {
     static constexpr int kParams = kV > 0 ? 10 + 6 * kV : 0;  // compile-time n (0: run time)
+    static constexpr int kSpecProbes = 1;                      // no speculative line search (line_search_cta)
+    static constexpr bool kSpeculative = false;
     const SolveParams<T>& p;
     T* world;  // [N,3]
     T* obs;    // [V,N,2]
@@ -256,21 +258,30 @@ struct JointCtaObjective {
     }
 };
 
-// The DISTORT10 objective (objectives.cuh) evaluated by a whole CTA: the second launch of a DISTORT10 solve gives
-// each straggler W warps, because there the latency of one evaluation — not the batch's throughput — sets the
-// launch time.  Thread t handles the match pair (t, t + 32 W) of every block of 64 W matches; the 11 sums are
-// reduced inside each warp (reduce-scatter) and across warps through `red` with one barrier.
-template <typename T, int W>
+// The DISTORT10 objective (objectives.cuh) evaluated by a CTA: the second launch of a DISTORT10 solve gives each
+// straggler a whole CTA, because there the LATENCY of one evaluation — not the batch's throughput — sets the launch
+// time.  The CTA is G groups of W warps.  One evaluation is the work of ONE group (thread t of the group handles the
+// match pair (t, t + 32 W) of every block of 64 W matches; the 11 sums are reduced inside each warp and across the
+// group's warps through `red` with one barrier); the G groups exist for the speculative line search below, where each
+// group evaluates a different trial point.  Results do not depend on G.
+#ifndef DAVO_SPEC_PROBES
+#define DAVO_SPEC_PROBES 16  // G: trial points evaluated per round of the stragglers' line search (1: no speculation)
+#endif
+
+template <typename T, int W, int G = 1>
 struct Distort10CtaObjective {
     static constexpr int kParams = 10;
+    static constexpr int kSpecProbes = G;
+    static constexpr bool kSpeculative = true;
+    static constexpr int kKeep = 11;  // folded per-thread sums of one probe: 10 gradient sums + cost
     using V4 = typename Vec4<T>::type;
     using P = typename Vec2<T>::type;
     const SolveParams<T>& p;
     V4* matches;  // [N] {a, b, -u*, -v*} (observations negated once per problem)
-    T* red;       // [W][16]
+    T* red;       // [W G][16]
     uint64_t* bar;
     unsigned parity;
-    int lane, warp, tid;
+    int lane, warp, tid, grp;  // warp, tid: within the group
 
     __host__ __device__ static size_t data_bytes(int N, int, bool) {
         return (sizeof(V4) * (size_t)N + 127) & ~size_t(127);
@@ -278,11 +289,12 @@ struct Distort10CtaObjective {
 
     __device__ Distort10CtaObjective(const SolveParams<T>& p_, unsigned char* slab, T* red_, uint64_t* bar_)
         : p(p_), matches(reinterpret_cast<V4*>(slab)), red(red_), bar(bar_), parity(0) {
-        tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
+        grp = threadIdx.x / (32 * W);
+        tid = threadIdx.x - grp * 32 * W; lane = tid & 31; warp = tid >> 5;
     }
 
     __device__ __forceinline__ void init() {
-        if (tid == 0) {
+        if (threadIdx.x == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
         }
@@ -292,14 +304,14 @@ struct Distort10CtaObjective {
     __device__ __forceinline__ void bind(int b) {
         fence_proxy_async();
         __syncthreads();  // every warp is done with the previous problem's slab
-        if (tid == 0) {
+        if (threadIdx.x == 0) {
             const unsigned bytes = (unsigned)(sizeof(V4) * (size_t)p.N);
             mbar_expect_tx(bar, bytes);
             tma_load_1d(matches, p.data0 + (size_t)b * p.N * 4, bytes, bar);
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
-        for (int i = tid; i < p.N; i += 32 * W) {
+        for (int i = threadIdx.x; i < p.N; i += 32 * W * G) {
             V4 m = matches[i];
             m.z = -m.z;
             m.w = -m.w;
@@ -308,7 +320,8 @@ struct Distort10CtaObjective {
         __syncthreads();
     }
 
-    __device__ __forceinline__ T eval(const T* th, T* gout) {
+    // this thread's share of one evaluation at the parameter line `th`
+    __device__ __forceinline__ void accumulate(const T* th, T (&acc)[kSlots]) {
         Intrinsics<T> I;
         I.load(th);
         P acc2[kPairAcc];
@@ -327,26 +340,92 @@ struct Distort10CtaObjective {
             nus.x = m0.z; nus.y = m1.z; nvs.x = m0.w; nvs.y = m1.w;
             match_pair_cost_grad<T, false>(I, a, b, nus, nvs, pk(T(1)), second_valid, acc2, gu, gv);
         }
-        T acc[kSlots];
 #pragma unroll
         for (int k = 0; k < kPairAcc; ++k) acc[k] = acc2[k].x + acc2[k].y;
 #pragma unroll
         for (int k = kPairAcc; k < kSlots; ++k) acc[k] = T(0);
         fold_uv_terms(acc);
-        const T mine = reduce_scatter16<true>(acc, lane);
-        if (!(lane & 1)) red[warp * kSlots + (lane >> 1)] = mine;
+    }
+
+    // One evaluation (group 0 computes; every thread of the CTA gets f, gout is visible to the CTA on return).
+    __device__ __forceinline__ T eval(const T* th, T* gout) {
+        if (grp == 0) {
+            T acc[kSlots];
+            accumulate(th, acc);
+            const T mine = reduce_scatter16<true>(acc, lane);
+            if (!(lane & 1)) red[warp * kSlots + (lane >> 1)] = mine;
+        }
         __syncthreads();
         T f = T(0);
 #pragma unroll
         for (int w = 0; w < W; ++w) f += red[w * kSlots + 10];
-        if (tid < 10) {
+        if (threadIdx.x < 10) {
             T gsum = T(0);
 #pragma unroll
-            for (int w = 0; w < W; ++w) gsum += red[w * kSlots + tid];
-            gout[tid] = T(2) * gsum;  // least_squares_utils.py:43
+            for (int w = 0; w < W; ++w) gsum += red[w * kSlots + threadIdx.x];
+            gout[threadIdx.x] = T(2) * gsum;  // least_squares_utils.py:43
         }
         __syncthreads();
         return f;
+    }
+
+    // ---- speculative line search (line_search_cta_spec) ----------------------------------------------------
+    // G trial points per round, one per group.  A probe reduces only TWO scalars — the cost and d . grad — and keeps
+    // its 11 folded sums in registers; the full gradient is reduced once, for the probe the search accepts
+    // (finish_gradient).  xt: G parameter lines of 16 entries; d2[c] = 2 d_c (least_squares_utils.py:43's factor
+    // folded in).  Leaves this group's per-warp partial (cost, d . grad) in red[(grp W + warp) 2 + {0, 1}].
+    __device__ __forceinline__ void probe_partial(const T* xt, const T (&d2)[10], T (&keep)[kKeep]) {
+        T acc[kSlots];
+        accumulate(xt + 16 * grp, acc);
+#pragma unroll
+        for (int k = 0; k < kKeep; ++k) keep[k] = acc[k];
+        T e = d2[0] * acc[0], o = d2[1] * acc[1];
+#pragma unroll
+        for (int c = 2; c < 10; c += 2) {
+            e = fma_t(d2[c], acc[c], e);
+            o = fma_t(d2[c + 1], acc[c + 1], o);
+        }
+        T pf = acc[10], pd = e + o;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            pf += shfl_xor(pf, m);
+            pd += shfl_xor(pd, m);
+        }
+        if (lane == 0) {
+            red[(grp * W + warp) * 2] = pf;
+            red[(grp * W + warp) * 2 + 1] = pd;
+        }
+    }
+    // (cost, d . grad) of probe j from the partials (every thread that calls it adds them in the same order)
+    __device__ __forceinline__ void probe_result(int j, T& f, T& dphi) const {
+        T fs = T(0), ds = T(0);
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            fs += red[(j * W + w) * 2];
+            ds += red[(j * W + w) * 2 + 1];
+        }
+        f = fs;
+        dphi = ds;
+    }
+
+    // The gradient of the probe group `sel` evaluated in the last eval_probes round: the tail of eval().
+    __device__ __forceinline__ void finish_gradient(const T (&kept)[kKeep], int sel, T* gout) {
+        T acc[kSlots];
+#pragma unroll
+        for (int k = 0; k < kKeep; ++k) acc[k] = kept[k];
+#pragma unroll
+        for (int k = kKeep; k < kSlots; ++k) acc[k] = T(0);
+        const T mine = reduce_scatter16<true>(acc, lane);
+        __syncthreads();  // every thread has read the probe round's `red`
+        if (grp == sel && !(lane & 1)) red[warp * kSlots + (lane >> 1)] = mine;
+        __syncthreads();
+        if (threadIdx.x < 10) {
+            T gsum = T(0);
+#pragma unroll
+            for (int w = 0; w < W; ++w) gsum += red[w * kSlots + threadIdx.x];
+            gout[threadIdx.x] = T(2) * gsum;  // least_squares_utils.py:43
+        }
+        __syncthreads();
     }
 };
 
@@ -438,6 +517,158 @@ __device__ __forceinline__ LineSearchResult<T> line_search_cta(Obj& obj, const S
     return r;
 }
 
+// One probe of wolfe_conditions.py:23-239 consumed by the state machine (the body of line_search_cta's loop), with the
+// top-of-loop update of the NEXT trial step folded in.  Returns false when the search has ended.
+template <typename T>
+struct WolfeState {
+    bool widening, zooming;
+    T lo, hi, cand, lo_f, hi_f, cand_f, f0, g0, neg_c2_g0;
+    int i, probes;
+    __device__ __forceinline__ void start(T f0_, T g0_, T c2) {                      // :77-114
+        widening = true; zooming = false;
+        lo = T(0); hi = T(0); cand = T(1);
+        f0 = lo_f = hi_f = cand_f = f0_;
+        g0 = g0_;
+        neg_c2_g0 = mul_rn(T(-1) * c2, g0_);
+        i = 0; probes = 0;
+    }
+    __device__ __forceinline__ bool consume(const SolveParams<T>& p, T f, T dphi) {  // :143-237, then :116-131
+        cand_f = f;
+        ++probes;
+        bool D = cand_f > add_rn(f0, mul_rn(mul_rn(p.c1, cand), g0));               // :146-150
+        if (zooming) D = D || (cand_f >= lo_f);                                     // :151-153
+        if (widening && i > 0) D = D || (cand_f >= hi_f);                           // :154-157
+        const bool C = p.strong ? (fabs(dphi) <= neg_c2_g0) : (mul_rn(T(-1), dphi) <= neg_c2_g0);  // :160-169
+        const bool G = widening ? (dphi >= T(0)) : (mul_rn(dphi, sub_rn(hi, lo)) >= T(0));         // :174-180
+        if (zooming) {                                                              // :187-207
+            if (D) { hi = cand; hi_f = cand_f; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; zooming = false; }
+            else { if (G) { hi = lo; hi_f = lo_f; } lo = cand; lo_f = cand_f; }
+        } else {                                                                    // :216-237
+            if (D) { lo = hi; lo_f = hi_f; hi = cand; hi_f = cand_f; widening = false; zooming = true; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; widening = false; }
+            else if (G) { lo = cand; lo_f = cand_f; widening = false; zooming = true; }
+        }
+        if (zooming && !(lo != hi)) zooming = false;                                // :236
+        ++i;
+        if (!(widening || zooming) || i >= p.max_ls) return false;                  // :116-121
+        if (widening) { hi = cand; hi_f = cand_f; cand = mul_rn(T(2), cand); }      // :125-127
+        if (zooming) cand = mul_rn(T(0.5), add_rn(lo, hi));                          // :128-131
+        return true;
+    }
+};
+
+// line_search_cta with K = Obj::kSpecProbes trial points per round, one per group of warps
+// (Distort10CtaObjective::probe_partial).  The state machine is wolfe_conditions.py:23-239 unchanged, consumed one
+// probe at a time; what is speculative is only WHICH points get evaluated: next to the probe the search asks for, the
+// points it will ask for if this probe and its successors fail the sufficient-decrease test (the "D" branch,
+// :146-157 -> :187-189 / :216-219: the bracket's upper end moves to the probe and the next one bisects again).  A
+// straggler's line searches are such chains, ~45 probes long, repeated for 1000 iterations (a float32 problem that
+// has stopped making progress: alpha ~ 4e-6 every time).  A probe is consumed only if its trial step is bitwise the
+// one the state machine computed, so the sequence of consumed probes, every decision and the result are those of
+// the one-probe-at-a-time search; unconsumed probes are discarded.
+//
+// Every warp evaluating and then replaying the state machine redundantly made a round cost as many issue slots as
+// G sequential probes (ncu: issue slots 60 % busy, no gain).  So the bookkeeping is warp 0's alone, between two
+// barriers: it consumes probe 0 with the general code, tests the rest of the chain in PARALLEL (lane j: "is probe j
+// another plain D step?" — along a D chain lo, f(lo) and the test's constants do not change), takes the leading run
+// in one go, consumes the probe that broke the chain with the general code, and writes the next round's trial points.
+// On return gt holds the gradient at the last consumed probe if that is the accepted point.  xt: 16 K words for the
+// trial points; ctl: 8 words of scratch.
+template <typename T, int W, typename Obj>
+__device__ __forceinline__ LineSearchResult<T> line_search_cta_spec(Obj& obj, const SolveParams<T>& p, const T* x,
+                                                                    const T* d, T f0, const T* g, T* xt, T* gt,
+                                                                    T* ctl) {
+    constexpr int K = Obj::kSpecProbes;
+    constexpr int n = Obj::kParams;
+    static_assert(n == 10 && 16 * K <= 3 * kWideMax && K <= 24, "speculative probes: 10 parameters, K lines of 16 in xt");
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool boss = tid < 32;  // warp 0 owns the state machine
+    T d2[10];
+#pragma unroll
+    for (int c = 0; c < 10; ++c) d2[c] = T(2) * d[c];
+    T keep[Obj::kKeep];
+    WolfeState<T> st;
+    st.start(f0, wide_dot(d, g, n, lane), p.c2);
+    T c_mine = T(0);  // warp 0, lane j < K: trial step of probe j in the current round
+    int last = 0;
+    // trial points of a round: the step the search asks for, then its successors along the D chain
+    auto write_round = [&]() {
+        bool z = st.zooming;
+        T slo = st.lo, shi = st.hi, sc = st.cand;
+        c_mine = sc;
+#pragma unroll
+        for (int j = 1; j < K; ++j) {
+            if (z) { shi = sc; } else { slo = shi; shi = sc; z = true; }   // the D branch
+            sc = mul_rn(T(0.5), add_rn(slo, shi));
+            if (lane == j) c_mine = sc;
+        }
+#pragma unroll
+        for (int e0 = 0; e0 < 16 * K; e0 += 32) {   // warp-uniform trip count: the shuffle needs every lane
+            const int e = e0 + lane, col = e & 15;
+            const T cj = shfl_idx(c_mine, (e >> 4) < K ? (e >> 4) : 0);
+            if (e < 16 * K) xt[e] = (col < n) ? add_rn(x[col], mul_rn(cj, d[col])) : T(0);   // :139
+        }
+    };
+    if (boss) {
+        const bool go = p.max_ls > 0;
+        if (go) write_round();
+        if (lane == 0) ctl[0] = go ? T(1) : T(0);
+    }
+    __syncthreads();
+    while (ctl[0] != T(0)) {
+        obj.probe_partial(xt, d2, keep);
+        __syncthreads();
+        if (boss) {
+            T fl = T(0), dl = T(0);
+            if (lane < K) obj.probe_result(lane, fl, dl);
+            bool go = st.consume(p, shfl_idx(fl, 0), shfl_idx(dl, 0));
+            last = 0;
+            if (K > 1 && go && st.zooming && same_bits(st.cand, shfl_idx(c_mine, 1))) {
+                // lanes 1 .. K-1: is probe j another plain D step (bracket end moves to it, search goes on)?
+                bool D = fl > add_rn(st.f0, mul_rn(mul_rn(p.c1, c_mine), st.g0));   // :146-150
+                D = D || (fl >= st.lo_f);                                            // :151-153
+                // probe j >= 2 sits on the chain only if it bisects [lo, c_{j-1}] for the lo of NOW (probe 0 may have
+                // moved lo and still landed on c_1: widening, no decrease failure, positive slope -> [1, 0] -> 0.5)
+                const T c_prev = __shfl_up_sync(kFull, c_mine, 1);
+                const bool on_chain = lane == 1 || same_bits(c_mine, mul_rn(T(0.5), add_rn(st.lo, c_prev)));
+                const unsigned chain = __ballot_sync(kFull, lane >= 1 && lane < K && on_chain) >> 1;
+                const bool plain = lane >= 1 && lane < K && D && (st.lo != c_mine) && (st.i + lane < p.max_ls);
+                const unsigned m = (__ballot_sync(kFull, plain) >> 1) & chain;
+                int run = __ffs(~m) - 1;        // leading plain-D probes after probe 0 ...
+                const int reach = __ffs(~chain) - 1;  // ... among the probes that sit on the chain
+                if (run > reach) run = reach;
+                if (run > 0) {
+                    st.hi = shfl_idx(c_mine, run);
+                    st.hi_f = st.cand_f = shfl_idx(fl, run);
+                    st.probes += run;
+                    st.i += run;
+                    st.cand = mul_rn(T(0.5), add_rn(st.lo, st.hi));                  // :128-131
+                    last = run;
+                }
+                if (run + 1 < K && run < reach) {  // the probe that broke the chain sits at the step the search asks for now
+                    last = run + 1;
+                    go = st.consume(p, shfl_idx(fl, run + 1), shfl_idx(dl, run + 1));
+                }
+            }
+            if (go) {
+                write_round();
+            } else if (lane == 0) {
+                ctl[1] = st.hi; ctl[2] = st.cand; ctl[3] = st.cand_f;
+                ctl[4] = T(st.probes); ctl[5] = T(last);
+            }
+            if (lane == 0) ctl[0] = go ? T(1) : T(0);
+        }
+        __syncthreads();
+    }
+    LineSearchResult<T> r;
+    r.alpha = ctl[1]; r.last_cand = ctl[2]; r.last_f = ctl[3]; r.last_g = T(0); r.probes = (int)ctl[4];
+    last = (int)ctl[5];
+    if (p.max_ls <= 0) { r.alpha = T(0); r.last_cand = T(1); r.last_f = f0; r.probes = 0; }
+    if (r.probes > 0 && same_bits(r.alpha, r.last_cand)) obj.finish_gradient(keep, last, gt);
+    return r;
+}
+
 // bfgs_solver.py:80-215 for one problem, executed by the whole CTA.
 template <typename T, int W, typename Obj>
 __device__ __forceinline__ void solve_one_cta(Obj& obj, const SolveParams<T>& p, int b, CtaWorkspace<T>& ws) {
@@ -523,7 +754,9 @@ __device__ __forceinline__ void solve_one_cta(Obj& obj, const SolveParams<T>& p,
             }
         }
         __syncthreads();
-        const LineSearchResult<T> ls = line_search_cta<T, W>(obj, p, x, d, f, g, ws.xt, gt);  // :181-190
+        LineSearchResult<T> ls;                                                                // :181-190
+        if constexpr (Obj::kSpeculative) ls = line_search_cta_spec<T, W>(obj, p, x, d, f, g, ws.y /* y, yH, Hy: 3 kWideMax words, free here */, gt, ws.xt);
+        else ls = line_search_cta<T, W>(obj, p, x, d, f, g, ws.xt, gt);
         fevals += ls.probes;
         ++iters;
         if (tid < n) {                                         // :191-199

@@ -63,6 +63,17 @@ __device__ __forceinline__ T wide_dot(const T* a, const T* b, int n, int lane) {
     return warp_allreduce(acc);
 }
 
+// The zoom step.  Bisection (wolfe_conditions.py:128-131, :242-253) or, with `secant`, the older solvers/ generation's
+// interpolate_alpha(lo, hi, phi'(lo), phi'(hi)) (solvers/line_search_strong_wolfe_conditions.py:147-155,
+// utils/func_interpolate_alpha.py:15-33); a non-finite interpolant (phi' = NaN or inf at a bracket end) bisects.
+template <typename T>
+__device__ __forceinline__ T zoom_step(bool secant, T lo, T hi, T lo_d, T hi_d) {
+    const T mid = mul_rn(T(0.5), add_rn(lo, hi));
+    if (!secant) return mid;
+    const T c = interpolate_alpha_value(lo, hi, lo_d, hi_d);
+    return isfinite(c) ? c : mid;
+}
+
 // wolfe_conditions.py:23-239.  x, d, g live in shared memory; probes are evaluated at ws.xt with the
 // gradient written to ws.gt.
 template <int kCols = 2, typename T, typename Obj>
@@ -74,13 +85,14 @@ __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const 
     bool widening = true, zooming = false;      // :80-82
     T lo = T(0), hi = T(0), cand = T(1);        // :97-108
     T lo_f = f0, hi_f = f0, cand_f = f0;        // :109-111
+    T lo_d = g0, hi_d = g0, cand_d = g0;        // secant zoom: phi' at the bracket ends and at the last probe
     int probes = 0;
     const T neg_c2_g0 = mul_rn(T(-1) * p.c2, g0);
     for (int i = 0; i < p.max_ls; ++i) {        // :116
         if (!(widening || zooming)) break;      // :119-121
         if (i > 0) {
-            if (widening) { hi = cand; hi_f = cand_f; cand = mul_rn(T(2), cand); }  // :125-127
-            if (zooming) cand = mul_rn(T(0.5), add_rn(lo, hi));                      // :128-131
+            if (widening) { hi = cand; hi_f = cand_f; hi_d = cand_d; cand = mul_rn(T(2), cand); }  // :125-127
+            if (zooming) cand = zoom_step(p.zoom != 0, lo, hi, lo_d, hi_d);           // :128-131
         }
         __syncwarp();
 #pragma unroll
@@ -89,6 +101,7 @@ __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const 
         __syncwarp();
         cand_f = obj.eval(xt, gt);
         const T dphi = wide_dot<kCols>(d, gt, n, lane);                                    // :141
+        cand_d = dphi;
         ++probes;
         bool D = cand_f > add_rn(f0, mul_rn(mul_rn(p.c1, cand), g0));               // :146-150
         if (zooming) D = D || (cand_f >= lo_f);                                     // :151-153
@@ -96,13 +109,13 @@ __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const 
         const bool C = p.strong ? (fabs(dphi) <= neg_c2_g0) : (mul_rn(T(-1), dphi) <= neg_c2_g0);  // :160-169
         const bool G = widening ? (dphi >= T(0)) : (mul_rn(dphi, sub_rn(hi, lo)) >= T(0));         // :174-180
         if (zooming) {                                                              // :187-207
-            if (D) { hi = cand; hi_f = cand_f; }
-            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; zooming = false; }
-            else { if (G) { hi = lo; hi_f = lo_f; } lo = cand; lo_f = cand_f; }
+            if (D) { hi = cand; hi_f = cand_f; hi_d = dphi; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; hi_d = lo_d = dphi; zooming = false; }
+            else { if (G) { hi = lo; hi_f = lo_f; hi_d = lo_d; } lo = cand; lo_f = cand_f; lo_d = dphi; }
         } else {                                                                    // :216-237
-            if (D) { lo = hi; lo_f = hi_f; hi = cand; hi_f = cand_f; widening = false; zooming = true; }
-            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; widening = false; }
-            else if (G) { lo = cand; lo_f = cand_f; widening = false; zooming = true; }
+            if (D) { lo = hi; lo_f = hi_f; lo_d = hi_d; hi = cand; hi_f = cand_f; hi_d = dphi; widening = false; zooming = true; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; hi_d = lo_d = dphi; widening = false; }
+            else if (G) { lo = cand; lo_f = cand_f; lo_d = dphi; widening = false; zooming = true; }
         }
         if (zooming && !(lo != hi)) zooming = false;                                // :236
     }
@@ -138,6 +151,8 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
     bool widening = false, zooming = false;                                    // wolfe_conditions.py:77-114
     T lo = T(0), hi = T(0), cand = T(1), lo_f = T(0), hi_f = T(0), cand_f = T(0), f0 = T(0), g0 = T(0),
       neg_c2_g0 = T(0);
+    T lo_d = T(0), hi_d = T(0), cand_d = T(0);  // secant zoom only (dead code in the eval-mode instantiation)
+    const bool secant = Rec::kActive && rec.secant();
     int ls_i = 0;
     int mode = (p.max_iters > 0) ? kEvalOuter : kEvalFinal;
     if (Rec::kActive && mode == kEvalOuter && rec.drop(b, 0)) {  // dropped before its first evaluation (:122-125)
@@ -175,6 +190,18 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             if (widening && ls_i > 0) D = D || (cand_f >= hi_f);                // :154-157
             const bool C = p.strong ? (fabs(dphi) <= neg_c2_g0) : (mul_rn(T(-1), dphi) <= neg_c2_g0);  // :160-169
             const bool G = widening ? (dphi >= T(0)) : (mul_rn(dphi, sub_rn(hi, lo)) >= T(0));         // :174-180
+            if (Rec::kActive) {  // phi' at the bracket ends follows every assignment of (lo, lo_f) / (hi, hi_f) below
+                cand_d = dphi;
+                if (zooming) {
+                    if (D) { hi_d = dphi; }
+                    else if (C) { hi_d = lo_d = dphi; }
+                    else { if (G) hi_d = lo_d; lo_d = dphi; }
+                } else {
+                    if (D) { lo_d = hi_d; hi_d = dphi; }
+                    else if (C) { hi_d = lo_d = dphi; }
+                    else if (G) { lo_d = dphi; }
+                }
+            }
             if (zooming) {                                                      // :187-207
                 if (D) { hi = cand; hi_f = cand_f; }
                 else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; zooming = false; }
@@ -187,8 +214,8 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             if (zooming && !(lo != hi)) zooming = false;                        // :236
             ++ls_i;
             if ((widening || zooming) && ls_i < p.max_ls) {                     // :116-121: another probe
-                if (widening) { hi = cand; hi_f = cand_f; cand = mul_rn(T(2), cand); }  // :125-127
-                if (zooming) cand = mul_rn(T(0.5), add_rn(lo, hi));                      // :128-131
+                if (widening) { hi = cand; hi_f = cand_f; if (Rec::kActive) hi_d = cand_d; cand = mul_rn(T(2), cand); }  // :125-127
+                if (zooming) cand = zoom_step(secant, lo, hi, lo_d, hi_d);               // :128-131
                 continue;
             }
             // ---- line search finished, alpha = upper_alpha (:239): take the step, bfgs_solver.py:191-207 ----
@@ -424,6 +451,7 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
             widening = true; zooming = false;                                   // :80-82
             lo = T(0); hi = T(0); cand = T(1);                                  // :97-108
             lo_f = f0; hi_f = f0; cand_f = f0;                                  // :109-111
+            if (Rec::kActive) lo_d = hi_d = cand_d = g0;
             ls_i = 0;
             mode = kEvalProbe;
         }

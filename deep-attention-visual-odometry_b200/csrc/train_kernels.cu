@@ -10,6 +10,7 @@
 #include "objectives_ba.cuh"
 #include "solver_wide.cuh"
 #include "solver_train.cuh"
+#include "wide_kernel.cuh"
 #include "launch.h"
 
 namespace davo {
@@ -151,6 +152,23 @@ int launch_train_backward(const SolveParams<double>& p, const BackwardParams<dou
     if (analytic_model(p.model)) return launch_train_backward_t<double, AnalyticWideObjective<double>>(p, bp, s);
     return DAVO_ERR_UNSUPPORTED;
 }
+
+template <typename T>
+int launch_line_search_generic(const SolveParams<T>& p, cudaStream_t s) {
+    if (p.model == DAVO_MODEL_DISTORT10) return launch_wide<T, Distort10WideObjective<T>, WMode::kLineSearch>(p, s);
+    if (p.model == DAVO_MODEL_JOINT) {
+        if (p.V < 1 || p.V > kMaxViews) return DAVO_ERR_UNSUPPORTED;
+        return launch_wide<T, JointObjective<T>, WMode::kLineSearch>(p, s);
+    }
+    if (p.model == DAVO_MODEL_ANGLE_BA) {
+        if (p.n > 64) return launch_wide<T, AngleBAObjective<T>, WMode::kLineSearch, 4>(p, s);
+        return launch_wide<T, AngleBAObjective<T>, WMode::kLineSearch>(p, s);
+    }
+    if (analytic_model(p.model)) return launch_wide<T, AnalyticWideObjective<T>, WMode::kLineSearch>(p, s);
+    return DAVO_ERR_UNSUPPORTED;
+}
+template int launch_line_search_generic<float>(const SolveParams<float>&, cudaStream_t);
+template int launch_line_search_generic<double>(const SolveParams<double>&, cudaStream_t);
 
 template int launch_train_forward<float>(const SolveParams<float>&, const TrainRecorder<float>&, cudaStream_t);
 template int launch_train_forward<double>(const SolveParams<double>&, const TrainRecorder<double>&, cudaStream_t);

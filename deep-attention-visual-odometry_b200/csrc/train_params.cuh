@@ -12,6 +12,7 @@ struct NoRecorder {
     static constexpr bool kActive = false;
     __device__ __forceinline__ bool drop(int, int) const { return false; }
     __device__ __forceinline__ bool second_last() const { return false; }
+    __device__ __forceinline__ bool secant() const { return false; }
     template <typename T>
     __device__ __forceinline__ void record(int, int, int, const T*, const T*, T, int) const {}
     __device__ __forceinline__ void finish(int, int, int) const {}
@@ -44,12 +45,14 @@ struct TrainRecorder {
     float drop_p;       // drop_path_p (0: never)
     uint64_t seed;
     int second;         // return_second_last
+    int zoom;           // 1: secant zoom (davo_problem_desc.zoom_interpolation)
     __device__ __forceinline__ bool drop(int b, int k) const {   // bfgs_solver.py:122-125: keep iff rand > p
         if (!(drop_p > 0.0f)) return false;
         const float u = (float)(drop_path_bits(seed, (uint32_t)b, (uint32_t)k) >> 8) * (1.0f / 16777216.0f);
         return !(u > drop_p);
     }
     __device__ __forceinline__ bool second_last() const { return second != 0; }
+    __device__ __forceinline__ bool secant() const { return zoom != 0; }
     __device__ __forceinline__ void record(int b, int k, int n, const T* x, const T* g, T alpha, int lane) const {
         if (!traj_x || k >= capacity) return;
         const size_t row = ((size_t)b * capacity + k) * n;

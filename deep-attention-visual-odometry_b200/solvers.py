@@ -78,7 +78,7 @@ class _DifferentiableSolve(torch.autograd.Function):
                         torch.zeros(B, dtype=torch.int32, device=device))
             desc = obj.desc(iterations=K, strong=True, sufficient_decrease=cfg["sufficient_decrease"],
                             curvature=cfg["curvature"], error_threshold=cfg["error_threshold"],
-                            minimum_step=cfg["minimum_step"])
+                            minimum_step=cfg["minimum_step"], zoom_interpolation=cfg["zoom_interpolation"])
             tdesc = _lib.TrainingDesc(max(K, 1), int(cfg["return_second_last"]), float(cfg["drop_path_p"]),
                                       int(cfg["seed"]), 0.0)
             st = _lib.lib().davo_solve_training(
@@ -172,6 +172,11 @@ class BFGSSolver(Module):
     #: refuse to record trajectories larger than this (bytes): B x training_iterations x (2n+1) values
     trajectory_budget_bytes = 32 << 30
 
+    #: opt-in line-search variant: the zoom step interpolates phi' at the bracket ends
+    #: (utils/func_interpolate_alpha.py, as the older solvers/line_search_strong_wolfe_conditions.py:147-155 does)
+    #: instead of bisecting; set on an instance.  Not a constructor argument: the constructor is the reference's.
+    zoom_interpolation = False
+
     def __init__(self, sufficient_decrease: float = 1e-4, curvature: float = 0.9, error_threshold: float = 1e-4,
                  iterations: int = 1000, minimum_step: float = 1e-8, drop_path_p: float = 0.1,
                  return_second_last: bool = False, training_iterations: int = None,
@@ -207,7 +212,7 @@ class BFGSSolver(Module):
                                                       getattr(obj, "differentiable_data", None) is not None)
         if differentiable or (self.training and (self.drop_path_p > 0.0 or self.return_second_last)):
             return self._forward_training(parameters, obj, error_threshold, iterations, differentiable, return_info)
-        if getattr(obj, "is_staged", True):
+        if getattr(obj, "is_staged", True) or self.zoom_interpolation:
             x0 = parameters.detach().to(device=obj.device, dtype=obj.dtype, non_blocking=True).reshape(obj.B, n)
             buf = self.solve_into(x0.contiguous(), obj, error_threshold=error_threshold, iterations=iterations,
                                   out=out)
@@ -242,7 +247,8 @@ class BFGSSolver(Module):
         cfg = dict(error_threshold=error_threshold, iterations=iterations, drop_path_p=drop_p, seed=seed,
                    return_second_last=bool(self.training and self.return_second_last),
                    sufficient_decrease=self.sufficient_decrease, curvature=self.curvature,
-                   minimum_step=self.minimum_step, budget=self.trajectory_budget_bytes)
+                   minimum_step=self.minimum_step, budget=self.trajectory_budget_bytes,
+                   zoom_interpolation=bool(self.zoom_interpolation))
         x, cost, converged, iters, fevals, reason = _DifferentiableSolve.apply(
             parameters, obj, cfg, differentiable, obj.differentiable_data if differentiable else None)
         if not return_info:
@@ -335,7 +341,7 @@ class BFGSSolver(Module):
             data0 = obj.data0  # stages a lazily staged problem set (and its weights) before the descriptor is built
             desc = obj.desc(iterations=iterations, strong=True, sufficient_decrease=self.sufficient_decrease,
                             curvature=self.curvature, error_threshold=error_threshold,
-                            minimum_step=self.minimum_step)
+                            minimum_step=self.minimum_step, zoom_interpolation=bool(self.zoom_interpolation))
             st = _lib.lib().davo_solve_calibration(
                 ctypes.byref(desc), _lib.ptr(data0), _lib.ptr(obj.data1), _lib.ptr(obj.weights), _lib.ptr(x0),
                 _lib.ptr(buf.x), _lib.ptr(buf.cost), _lib.ptr(buf.converged), _lib.ptr(buf.iterations),
@@ -376,8 +382,10 @@ class BFGSSolver(Module):
 
 def line_search_wolfe_conditions(parameters: torch.Tensor, search_direction: torch.Tensor, base_error: torch.Tensor,
                                  base_gradient: torch.Tensor, error_function, sufficient_decrease: float = 1e-4,
-                                 curvature: float = 0.9, strong: bool = False, return_probes: bool = False):
-    """Drop-in for autograd_solvers/line_search/wolfe_conditions.py:23-239: alpha of shape (B..)."""
+                                 curvature: float = 0.9, strong: bool = False, return_probes: bool = False,
+                                 zoom_interpolation: bool = False):
+    """Drop-in for autograd_solvers/line_search/wolfe_conditions.py:23-239: alpha of shape (B..).
+    zoom_interpolation=True: the zoom step is interpolate_alpha(lo, hi, phi'(lo), phi'(hi)) instead of the midpoint."""
     obj = _require_descriptor(error_function)
     if not 0.0 < sufficient_decrease < curvature < 1.0:
         warnings.warn(f"Line search conditions should satisfy 0 < c1 < c2 < 1. "
@@ -393,7 +401,8 @@ def line_search_wolfe_conditions(parameters: torch.Tensor, search_direction: tor
         alpha = torch.empty(B, dtype=obj.dtype, device=device)
         probes = torch.empty(B, dtype=torch.int32, device=device)
         data0 = obj.data0  # stages a lazily staged problem set (and its weights) before the descriptor is built
-        desc = obj.desc(strong=strong, sufficient_decrease=sufficient_decrease, curvature=curvature)
+        desc = obj.desc(strong=strong, sufficient_decrease=sufficient_decrease, curvature=curvature,
+                        zoom_interpolation=zoom_interpolation)
         st = _lib.lib().davo_line_search(ctypes.byref(desc), _lib.ptr(data0), _lib.ptr(obj.data1),
                                          _lib.ptr(obj.weights), _lib.ptr(x), _lib.ptr(d), _lib.ptr(f0), _lib.ptr(g),
                                          _lib.ptr(alpha), _lib.ptr(probes), _lib.stream_ptr())
@@ -402,3 +411,46 @@ def line_search_wolfe_conditions(parameters: torch.Tensor, search_direction: tor
     if return_probes:
         return alpha, probes.reshape(batch_shape).to(parameters.device)
     return alpha
+
+
+class _InterpolateAlpha(torch.autograd.Function):
+    """utils/func_interpolate_alpha.py:5-79 on the GPU (davo_interpolate_alpha, davo_interpolate_alpha_backward)."""
+
+    @staticmethod
+    def forward(ctx, alpha_1, alpha_2, value_1, value_2):
+        device = _lib.require_cuda()
+        dt = alpha_1.dtype
+        shape = torch.broadcast_shapes(alpha_1.shape, alpha_2.shape, value_1.shape, value_2.shape)
+        ins = [t.detach().to(device=device, dtype=dt).expand(shape).contiguous() for t in (alpha_1, alpha_2, value_1, value_2)]
+        out = torch.empty(shape, dtype=dt, device=device)
+        with torch.cuda.device(device):
+            st = _lib.lib().davo_interpolate_alpha(_lib.dtype_code(dt), out.numel(), *[_lib.ptr(t) for t in ins],
+                                                   _lib.ptr(out), _lib.stream_ptr())
+        _lib.check(st, "davo_interpolate_alpha")
+        ctx.save_for_backward(*ins)
+        ctx.shapes = [t.shape for t in (alpha_1, alpha_2, value_1, value_2)]
+        ctx.in_device = alpha_1.device
+        ctx.set_materialize_grads(False)
+        return out.to(alpha_1.device)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if grad_output is None:
+            return None, None, None, None
+        ins = ctx.saved_tensors
+        device, dt = ins[0].device, ins[0].dtype
+        go = grad_output.detach().to(device=device, dtype=dt).expand(ins[0].shape).contiguous()
+        grads = [torch.empty_like(ins[0]) if need else None for need in ctx.needs_input_grad]
+        with torch.cuda.device(device):
+            st = _lib.lib().davo_interpolate_alpha_backward(
+                _lib.dtype_code(dt), go.numel(), *[_lib.ptr(t) for t in ins], _lib.ptr(go),
+                *[_lib.ptr(g) for g in grads], _lib.stream_ptr())
+        _lib.check(st, "davo_interpolate_alpha_backward")
+        return tuple(None if g is None else g.sum_to_size(shape).to(ctx.in_device) for g, shape in zip(grads, ctx.shapes))
+
+
+def interpolate_alpha(alpha_1: torch.Tensor, alpha_2: torch.Tensor, value_1: torch.Tensor,
+                      value_2: torch.Tensor) -> torch.Tensor:
+    """Drop-in for utils/func_interpolate_alpha.py:82-: the zero of the line through (alpha_1, value_1),
+    (alpha_2, value_2), or the midpoint when it is degenerate or within 1e-3 of the interval's ends."""
+    return _InterpolateAlpha.apply(alpha_1, alpha_2, value_1, value_2)

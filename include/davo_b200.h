@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DAVO_ABI_VERSION 1
+#define DAVO_ABI_VERSION 2
 
 /* ---- status codes -------------------------------------------------------------------- */
 typedef enum davo_status {
@@ -123,6 +123,12 @@ typedef struct davo_problem_desc {
     int32_t max_ls_iters; /* line-search probe cap, 1000 in the reference (wolfe_conditions.py:116) */
     int32_t strong;       /* 1 = strong Wolfe (what BFGSSolver passes, bfgs_solver.py:189)  */
     int32_t has_weights;  /* 1 = `weights` [B,V,N] multiplies each squared residual pair    */
+    int32_t zoom_interpolation; /* 0 = bisection zoom (wolfe_conditions.py:128-131, :242-253); 1 = the older
+                                 * solvers/ generation's secant zoom: the zoom step is interpolate_alpha(lo, hi,
+                                 * phi'(lo), phi'(hi)) (utils/func_interpolate_alpha.py:5-40, as used by
+                                 * solvers/line_search_strong_wolfe_conditions.py:147-155); runs on the generic
+                                 * one-warp-per-problem solver for every model */
+    int32_t reserved0;    /* 0 */
     double sufficient_decrease; /* c1, default 1e-4                                         */
     double curvature;           /* c2, default 0.9                                          */
     double error_threshold;     /* default 1e-4                                             */
@@ -245,6 +251,17 @@ int davo_bfgs_update(int32_t dtype, int32_t k, int32_t n, void* H, const void* s
 /* BFGSSolver.scale_initial_inverse_hessian (bfgs_solver.py:217-233): scale[k]. */
 int davo_bfgs_initial_scale(int32_t dtype, int32_t k, int32_t n, const void* s, const void* y,
                             void* scale, void* stream);
+
+/* interpolate_alpha (utils/func_interpolate_alpha.py:5-40), elementwise over k values: the zero of the line through
+ * (alpha_1, value_1), (alpha_2, value_2), or the midpoint when the values are equal or the zero falls within 1e-3 of
+ * (or outside) the interval.  out[k].  The backward entry point returns the four input gradients of the reference's
+ * custom backward (:42-79) given grad_out[k]; any of the four outputs may be NULL. */
+int davo_interpolate_alpha(int32_t dtype, int64_t k, const void* alpha_1, const void* alpha_2, const void* value_1,
+                           const void* value_2, void* out, void* stream);
+int davo_interpolate_alpha_backward(int32_t dtype, int64_t k, const void* alpha_1, const void* alpha_2,
+                                    const void* value_1, const void* value_2, const void* grad_out,
+                                    void* grad_alpha_1, void* grad_alpha_2, void* grad_value_1, void* grad_value_2,
+                                    void* stream);
 
 /* ---- synthetic oracle-match generator, on the device -------------------------------------------------
  * Replaces the reference's host-side dataset (data/camera_and_parameters_dataset.py:48-61,85-151, batch layout

@@ -23,15 +23,18 @@ class ProblemDesc(ctypes.Structure):
     """davo_problem_desc, include/davo_b200.h."""
 
     _fields_ = [(k, ctypes.c_int32) for k in
-                ("B", "N", "V", "n", "model", "dtype", "max_iters", "max_ls_iters", "strong", "has_weights")] + \
+                ("B", "N", "V", "n", "model", "dtype", "max_iters", "max_ls_iters", "strong", "has_weights",
+                 "zoom_interpolation", "reserved0")] + \
                [(k, ctypes.c_double) for k in ("sufficient_decrease", "curvature", "error_threshold", "minimum_step")]
 
 
 def make_desc(B, N, V, n, model, dtype, *, iterations=1000, max_ls_iters=1000, strong=True, has_weights=False,
-              sufficient_decrease=1e-4, curvature=0.9, error_threshold=1e-4, minimum_step=1e-8) -> ProblemDesc:
+              sufficient_decrease=1e-4, curvature=0.9, error_threshold=1e-4, minimum_step=1e-8,
+              zoom_interpolation=False) -> ProblemDesc:
     model_id = MODEL_IDS[model] if isinstance(model, str) else int(model)
     return ProblemDesc(int(B), int(N), int(V), int(n), model_id, 1 if np.dtype(dtype) == np.float64 else 0,
                        int(iterations), int(max_ls_iters), int(bool(strong)), int(bool(has_weights)),
+                       int(bool(zoom_interpolation)), 0,
                        float(sufficient_decrease), float(curvature), float(error_threshold), float(minimum_step))
 
 
@@ -107,11 +110,12 @@ def eval_cost_grad(model, x, data0=None, data1=None, weights=None, *, N=0, V=1, 
 
 
 def line_search(model, x, direction, base_cost, base_grad, data0=None, data1=None, weights=None, *, N=0, V=1,
-                sufficient_decrease=1e-4, curvature=0.9, strong=False, max_ls_iters=1000):
+                sufficient_decrease=1e-4, curvature=0.9, strong=False, max_ls_iters=1000, zoom_interpolation=False):
     dt = x.dtype
     B, n = x.shape
     d = make_desc(B, N, V, n, model, dt, has_weights=weights is not None, strong=strong,
-                  sufficient_decrease=sufficient_decrease, curvature=curvature, max_ls_iters=max_ls_iters)
+                  sufficient_decrease=sufficient_decrease, curvature=curvature, max_ls_iters=max_ls_iters,
+                  zoom_interpolation=zoom_interpolation)
     args = [_c(a, dt) for a in (data0, data1, weights, x, direction, base_cost, base_grad)]
     alpha = np.empty(B, dt)
     fevals = np.empty(B, np.int32)
@@ -120,6 +124,21 @@ def line_search(model, x, direction, base_cost, base_grad, data0=None, data1=Non
     if st != 0:
         raise ValueError(f"davo_oracle_line_search failed with status {st}")
     return alpha, fevals
+
+
+def interpolate_alpha(alpha_1, alpha_2, value_1, value_2, grad_out=None):
+    """utils/func_interpolate_alpha.py: candidate (and, with grad_out, the four input gradients)."""
+    dt = alpha_1.dtype
+    a1, a2, v1, v2 = (_c(np.ravel(a), dt) for a in (alpha_1, alpha_2, value_1, value_2))
+    out = np.empty_like(a1)
+    go = None if grad_out is None else _c(np.ravel(grad_out), dt)
+    grads = [np.empty_like(a1) for _ in range(4)] if go is not None else [None] * 4
+    fn = getattr(lib(), "davo_oracle_interpolate_alpha_" + _suffix(dt))
+    fn(ctypes.c_longlong(a1.size), _p(a1), _p(a2), _p(v1), _p(v2), _p(out), _p(go), *[_p(g) for g in grads])
+    out = out.reshape(alpha_1.shape)
+    if go is None:
+        return out
+    return (out,) + tuple(g.reshape(alpha_1.shape) for g in grads)
 
 
 def bfgs_update(H, s, y):

@@ -444,11 +444,47 @@ static void FN(update_inverse_hessian)(REAL* H, const REAL* s, const REAL* y, in
         }
 }
 
+/* utils/func_interpolate_alpha.py:15-33, one element.  `nonlinear` (may be NULL) receives the bisection mask. */
+static REAL FN(interpolate_alpha)(REAL a1, REAL a2, REAL v1, REAL v2, int* nonlinear) {
+    const REAL lo = a1 < a2 ? a1 : a2, hi = a1 < a2 ? a2 : a1; /* :15-16 */
+    const REAL diff = v2 - v1;                                 /* :18 */
+    const REAL inv_gradient = (a2 - a1) / diff;                /* :19 */
+    REAL cand = a1 - v1 * inv_gradient;                        /* :20 */
+    const int nl = (diff == R(0.0)) || (cand < lo + R(1e-3)) || (cand > hi - R(1e-3)); /* :23-29 */
+    if (nl) cand = (a1 + a2) / R(2.0);                         /* :30-32 */
+    if (nonlinear) *nonlinear = nl;
+    return cand;
+}
+
+/* forward and the custom backward (:42-79), elementwise; any output may be NULL */
+int FN(davo_oracle_interpolate_alpha)(long long k, const REAL* a1, const REAL* a2, const REAL* v1, const REAL* v2,
+                                      REAL* out, const REAL* grad_out, REAL* g_a1, REAL* g_a2, REAL* g_v1,
+                                      REAL* g_v2) {
+    for (long long i = 0; i < k; ++i) {
+        int nl;
+        const REAL c = FN(interpolate_alpha)(a1[i], a2[i], v1[i], v2[i], &nl);
+        if (out) out[i] = c;
+        if (grad_out) {
+            const REAL go = grad_out[i], diff = v2[i] - v1[i];
+            const REAL inv_gradient = (a2[i] - a1[i]) / diff;
+            const REAL one_on_diff = nl ? R(0.0) : R(1.0) / diff;                         /* :34-35 */
+            if (g_a1) g_a1[i] = nl ? R(0.5) * go : one_on_diff * v2[i] * go;             /* :56-61 */
+            if (g_a2) g_a2[i] = nl ? R(0.5) * go : R(-1.0) * one_on_diff * v1[i] * go;   /* :62-67 */
+            if (g_v1) g_v1[i] = nl ? R(0.0) : R(-1.0) * v2[i] * inv_gradient * one_on_diff * go; /* :68-73 */
+            if (g_v2) g_v2[i] = nl ? R(0.0) : v1[i] * inv_gradient * one_on_diff * go;   /* :74-79 */
+        }
+    }
+    return DAVO_OK;
+}
+
 /* autograd_solvers/line_search/wolfe_conditions.py:23-239, one problem.
+ * secant != 0: the zoom step (:128-131) is interpolate_alpha(lo, hi, phi'(lo), phi'(hi)) as in the older
+ * solvers/line_search_strong_wolfe_conditions.py:147-155 (bisection when the interpolant is not finite); this
+ * composition has no reference implementation: PARITY UNPINNED for the composition, pinned for interpolate_alpha.
  * Returns `upper_alpha` (:239).  g_at_hi (n values) receives the gradient at x + hi d when the
  * final hi is the last probe (valid flag), so the caller can check the reuse identity. */
 static REAL FN(line_search)(const FN(problem)* p, const REAL* x, const REAL* d, REAL f0, const REAL* g,
-                            REAL c1, REAL c2, int strong, int max_probes, int* probes, REAL* xt,
+                            REAL c1, REAL c2, int strong, int secant, int max_probes, int* probes, REAL* xt,
                             REAL* gt) {
     const int n = p->n;
     REAL g0 = 0;
@@ -456,16 +492,24 @@ static REAL FN(line_search)(const FN(problem)* p, const REAL* x, const REAL* d, 
     int widening = 1, zooming = 0;                /* :80-82 */
     REAL lo = 0, hi = 0, cand = 1;                /* :97-108 */
     REAL lo_f = f0, hi_f = f0, cand_f = f0;       /* :109-111 */
+    REAL lo_d = g0, hi_d = g0, cand_d = g0;       /* secant zoom: phi' at the bracket ends / last probe */
     for (int i = 0; i < max_probes; ++i) {        /* :116 */
         if (!(widening || zooming)) break;        /* :119-121 */
         if (i > 0) {
-            if (widening) { hi = cand; hi_f = cand_f; cand = R(2.0) * cand; } /* :125-127 */
-            if (zooming) cand = R(0.5) * (lo + hi);                            /* :128-131, :242-253 */
+            if (widening) { hi = cand; hi_f = cand_f; hi_d = cand_d; cand = R(2.0) * cand; } /* :125-127 */
+            if (zooming) {
+                cand = R(0.5) * (lo + hi);                                     /* :128-131, :242-253 */
+                if (secant) {
+                    const REAL c = FN(interpolate_alpha)(lo, hi, lo_d, hi_d, NULL);
+                    if (isfinite((double)c)) cand = c;
+                }
+            }
         }
         for (int j = 0; j < n; ++j) xt[j] = x[j] + cand * d[j]; /* :139 */
         cand_f = FN(objective)(p, xt, gt);                      /* :134-143 */
         REAL dphi = 0;
         for (int j = 0; j < n; ++j) dphi += d[j] * gt[j];
+        cand_d = dphi;
         ++*probes;
         int D = cand_f > f0 + c1 * cand * g0;                 /* :146-150 */
         if (zooming) D = D || (cand_f >= lo_f);               /* :151-153 */
@@ -476,16 +520,16 @@ static REAL FN(line_search)(const FN(problem)* p, const REAL* x, const REAL* d, 
         else        C = R(-1.0) * dphi <= R(-1.0) * c2 * g0;            /* :165-169 */
         int G = widening ? (dphi >= R(0.0)) : (dphi * (hi - lo) >= R(0.0)); /* :174-180 */
         if (zooming) {                                        /* :187-207 */
-            if (D) { hi = cand; hi_f = cand_f; }
-            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; zooming = 0; }
+            if (D) { hi = cand; hi_f = cand_f; hi_d = dphi; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; hi_d = lo_d = dphi; zooming = 0; }
             else {
-                if (G) { hi = lo; hi_f = lo_f; }
-                lo = cand; lo_f = cand_f;
+                if (G) { hi = lo; hi_f = lo_f; hi_d = lo_d; }
+                lo = cand; lo_f = cand_f; lo_d = dphi;
             }
         } else if (widening) {                                /* :216-237 */
-            if (D) { lo = hi; lo_f = hi_f; hi = cand; hi_f = cand_f; widening = 0; zooming = 1; }
-            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; widening = 0; }
-            else if (G) { lo = cand; lo_f = cand_f; widening = 0; zooming = 1; }
+            if (D) { lo = hi; lo_f = hi_f; lo_d = hi_d; hi = cand; hi_f = cand_f; hi_d = dphi; widening = 0; zooming = 1; }
+            else if (C) { hi = lo = cand; hi_f = lo_f = cand_f; hi_d = lo_d = dphi; widening = 0; }
+            else if (G) { lo = cand; lo_f = cand_f; lo_d = dphi; widening = 0; zooming = 1; }
         }
         if (zooming && !(lo != hi)) zooming = 0;              /* :236 */
     }
@@ -541,7 +585,7 @@ static FN(result) FN(solve_one)(const FN(problem)* p, REAL* x, const davo_proble
             }
         }
         int probes = 0;
-        REAL alpha = FN(line_search)(p, x, dir, f, g, c1, c2, d->strong, d->max_ls_iters, &probes, xt, gt); /* :181-190 */
+        REAL alpha = FN(line_search)(p, x, dir, f, g, c1, c2, d->strong, d->zoom_interpolation, d->max_ls_iters, &probes, xt, gt); /* :181-190 */
         r.fevals += probes;
         r.iters++;
         REAL nrm = 0;
@@ -642,7 +686,7 @@ int FN(davo_oracle_line_search)(const davo_problem_desc* d, const REAL* data0, c
         int probes = 0;
         alpha_out[b] = FN(line_search)(&p, x + (size_t)b * n, dir + (size_t)b * n, f0[b], g + (size_t)b * n,
                                        R(d->sufficient_decrease), R(d->curvature), d->strong,
-                                       d->max_ls_iters, &probes, tmp, tmp + n);
+                                       d->zoom_interpolation, d->max_ls_iters, &probes, tmp, tmp + n);
         if (fevals_out) fevals_out[b] = probes;
     }
     free(tmp);

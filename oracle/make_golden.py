@@ -308,12 +308,42 @@ def gen_training():
     _save("training", **out)
 
 
+def gen_interpolate_alpha():
+    """utils/func_interpolate_alpha.py run as is: the reference tests' known answers (tests/utils/
+    test_interpolate_alpha.py:29-62) plus random vectors (interior zeros, forced bisections, equal values), forward and
+    the custom backward, float32 and float64."""
+    sys.path.insert(0, "/root/reference")
+    from deep_attention_visual_odometry.utils import interpolate_alpha
+    rng = np.random.default_rng(17)
+    out = {"kat_in": np.array([[-1.0, 2.0, 0.8, -0.4], [-1.0, 2.0, 0.2, 0.4], [-3.0, -1.0, 6.0, 1.0],
+                               [16.0, 2.0, 4.0, 4.0]]),
+           "kat_out": np.array([1.0, 0.5, -2.0, 9.0])}
+    for name, dt in (("f32", np.float32), ("f64", np.float64)):
+        k = 4096
+        a1, a2, v1 = rng.standard_normal(k), rng.standard_normal(k), rng.standard_normal(k)
+        t = (0.05 + 0.9 * rng.random(k)) * (a2 - a1) + a1          # interior zero for the first half
+        v2 = (a2 - t) * v1 / (a1 - t)
+        v2[k // 2:] = rng.standard_normal(k - k // 2)              # anything for the rest
+        v2[-64:] = v1[-64:]                                         # equal values
+        a2[-128:-64] = a1[-128:-64] + 1e-3 * rng.standard_normal(64)  # narrow intervals
+        ins = [torch.tensor(a.astype(dt), requires_grad=True) for a in (a1, a2, v1, v2)]
+        res = interpolate_alpha(*ins)
+        go = torch.tensor(rng.standard_normal(k).astype(dt))
+        grads = torch.autograd.grad((res * go).sum(), ins)
+        out[f"{name}_in"] = np.stack([t_.detach().numpy() for t_ in ins])
+        out[f"{name}_out"] = res.detach().numpy()
+        out[f"{name}_grad_out"] = go.numpy()
+        out[f"{name}_grads"] = np.stack([g.numpy() for g in grads])
+    _save("interpolate_alpha", **out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*", default=None)
     args = ap.parse_args()
     small = {"camera_model": gen_camera_model, "bfgs_update": gen_bfgs_update, "line_search": gen_line_search,
-             "analytic_solves": gen_analytic_solves, "angle_ba": gen_angle_ba, "training": gen_training}
+             "analytic_solves": gen_analytic_solves, "angle_ba": gen_angle_ba, "training": gen_training,
+             "interpolate_alpha": gen_interpolate_alpha}
     names = args.only or (list(small) + list(SOLVE_CASES))
     for name in names:
         print(name, flush=True)

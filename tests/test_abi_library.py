@@ -39,8 +39,8 @@ def test_abi_version_and_strerror():
 
 def test_descriptor_layout_matches_header():
     # 10 int32 + 4 double, no padding surprises: the C struct is 40 + 32 bytes
-    assert ctypes.sizeof(_lib.ProblemDesc) == 72
-    assert _lib.ProblemDesc.sufficient_decrease.offset == 40
+    assert ctypes.sizeof(_lib.ProblemDesc) == 80
+    assert _lib.ProblemDesc.sufficient_decrease.offset == 48
 
 
 def test_validation_status_codes_without_gpu():

@@ -1,0 +1,101 @@
+"""GPU: the secant-zoom line-search variant and interpolate_alpha through the Python surface ->
+C-ABI, against the reference function's fixture and the C oracle's restatement of the variant."""
+import numpy as np
+import pytest
+import torch
+
+import davo_b200
+from conftest import load_golden
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+TDT = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+
+
+@pytest.mark.parametrize("name,dt", [("f32", np.float32), ("f64", np.float64)])
+def test_interpolate_alpha_matches_reference_fixture(name, dt):
+    g = load_golden("interpolate_alpha")
+    ins = [torch.from_numpy(g[f"{name}_in"][i]).requires_grad_(True) for i in range(4)]
+    out = davo_b200.interpolate_alpha(*ins)
+    assert out.shape == ins[0].shape and out.dtype == ins[0].dtype
+    assert np.array_equal(out.detach().numpy(), g[f"{name}_out"], equal_nan=True)      # bit for bit
+    grads = torch.autograd.grad((out * torch.from_numpy(g[f"{name}_grad_out"])).sum(), ins)
+    for got, want in zip(grads, g[f"{name}_grads"]):
+        assert np.allclose(got.numpy(), want, rtol=4 * np.finfo(dt).eps, atol=0, equal_nan=True)
+
+
+def test_interpolate_alpha_reference_known_answers_and_shapes():
+    """tests/utils/test_interpolate_alpha.py:6-62."""
+    g = load_golden("interpolate_alpha")
+    k = torch.from_numpy(g["kat_in"]).float()
+    assert torch.equal(davo_b200.interpolate_alpha(k[:, 0], k[:, 1], k[:, 2], k[:, 3]), torch.from_numpy(g["kat_out"]).float())
+    a1, a2, v1, v2 = (torch.randn(5, 1, 2, 3) for _ in range(4))
+    r = davo_b200.interpolate_alpha(a1, a2, v1, v2)
+    assert r.shape == (5, 1, 2, 3)
+    assert torch.all(r >= torch.minimum(a1, a2)) and torch.all(r <= torch.maximum(a1, a2))
+
+
+def test_interpolate_alpha_gradcheck():
+    """tests/utils/test_interpolate_alpha.py:65-99 (interior zeros; the backward is the reference's custom one)."""
+    torch.manual_seed(0)
+    a1, a2, v1 = (torch.randn(100, dtype=torch.double) for _ in range(3))
+    t = (0.1 + 0.8 * torch.rand(100, dtype=torch.double)) * (a2 - a1) + a1
+    v2 = (a2 - t) * v1 / (a1 - t)
+    ins = [x.clone().requires_grad_(True) for x in (a1, a2, v1, v2)]
+    assert torch.autograd.gradcheck(davo_b200.interpolate_alpha, ins, eps=1e-6, atol=1e-4)
+
+
+def _objective(batch, dt):
+    if batch.model == "distort10":
+        return davo_b200.DistortionObjective(torch.from_numpy(batch.points_3d), torch.from_numpy(batch.obs), dtype=dt)
+    return davo_b200.JointPoseObjective(torch.from_numpy(batch.points_3d), torch.from_numpy(batch.obs), dtype=dt)
+
+
+@pytest.mark.parametrize("model", ["distort10", "joint", "log_sphere"])
+def test_secant_line_search_matches_oracle(model):
+    rng = np.random.default_rng(11)
+    if model == "distort10":
+        b = davo_b200.synthetic.make_distort10(300, 64, seed=5, dtype=np.float64)
+        obj, x = _objective(b, torch.float64), b.x0
+        okw = dict(data0=c_oracle.stage(b.points_3d, b.obs, None), N=b.N)
+    elif model == "joint":
+        b = davo_b200.synthetic.make_joint(200, 32, 2, seed=6, dtype=np.float64)
+        obj, x = _objective(b, torch.float64), b.x0
+        okw = dict(data0=b.points_3d, data1=b.obs, N=b.N, V=b.views)
+    else:
+        x = rng.normal(0, 3, (300, 5))
+        obj = davo_b200.AnalyticObjective(model, (300,), 5, dtype=torch.float64)
+        okw = {}
+    f0, g = c_oracle.eval_cost_grad(model, x, **okw)
+    d = -g * rng.uniform(0.05, 20.0, (x.shape[0], 1))
+    want_a, want_p = c_oracle.line_search(model, x, d, f0, g, strong=True, zoom_interpolation=True, **okw)
+    T = torch.from_numpy
+    got_a, got_p = davo_b200.line_search_wolfe_conditions(T(x), T(d), T(f0), T(g), obj, strong=True, return_probes=True,
+                                                          zoom_interpolation=True)
+    same = got_p.numpy() == want_p
+    assert same.mean() >= 0.99
+    assert np.allclose(got_a.numpy()[same], want_a[same], rtol=1e-9, atol=1e-12)
+    plain_a, plain_p = davo_b200.line_search_wolfe_conditions(T(x), T(d), T(f0), T(g), obj, strong=True, return_probes=True)
+    # the secant step usually needs fewer probes than bisection, not always (log-sphere with random step scales)
+    print(model, "probes: secant", int(got_p.sum()), "bisection", int(plain_p.sum()))
+    assert int(got_p.sum()) <= 1.1 * int(plain_p.sum())
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_secant_solve_matches_oracle_and_saves_evaluations(dt):
+    b = davo_b200.synthetic.make_distort10(1024, 128, seed=21, dtype=dt)
+    thr = 1e-5 if dt == np.float32 else 1e-10
+    want = c_oracle.solve("distort10", b.x0, c_oracle.stage(b.points_3d, b.obs, None), N=b.N, error_threshold=thr,
+                          zoom_interpolation=True)
+    obj = _objective(b, TDT[np.dtype(dt)])
+    solver = davo_b200.BFGSSolver(error_threshold=thr).eval()
+    plain = solver(torch.from_numpy(b.x0), obj, return_info=True)
+    solver.zoom_interpolation = True
+    got = solver(torch.from_numpy(b.x0), obj, return_info=True)
+    same = got.iterations.numpy() == want["iters"]
+    print("identical steps", same.mean(), "evals secant", int(got.evaluations.sum()), "bisection", int(plain.evaluations.sum()))
+    assert same.mean() >= (0.99 if dt == np.float64 else 0.9)
+    tol = 1e-6 if dt == np.float64 else 2e-2
+    assert np.allclose(got.parameters.numpy()[same], want["x"][same], rtol=tol, atol=tol)
+    assert float(got.converged.float().mean()) >= float(plain.converged.float().mean()) - 0.02
+    assert int(got.evaluations.sum()) <= 1.05 * int(plain.evaluations.sum())
