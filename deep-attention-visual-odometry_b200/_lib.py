@@ -26,10 +26,11 @@ MODEL_IDS = {"distort10": 0, "joint": 1, "angle_ba": 2, "sphere": 16, "sphere_of
 REASON_NAMES = {0: "threshold", 1: "step", 2: "cap", 3: "nan", 5: "dropped"}
 
 # every symbol include/davo_b200.h declares (tests check the library exports all of them)
-EXPORTED = ("davo_abi_version", "davo_strerror", "davo_launch_count", "davo_solve_calibration",
+EXPORTED = ("davo_abi_version", "davo_strerror", "davo_launch_count", "davo_mlp_packed_bytes", "davo_solve_calibration",
             "davo_solve_training", "davo_solve_backward", "davo_eval_cost_grad", "davo_line_search", "davo_stage_matches", "davo_project",
             "davo_project_jacobian", "davo_least_squares", "davo_bfgs_update", "davo_bfgs_initial_scale",
             "davo_interpolate_alpha", "davo_interpolate_alpha_backward",
+            "davo_mlp_pack_weights", "davo_mlp_forward",
             "davo_generate_distort10", "davo_generate_joint", "davo_generate_views_and_points")
 
 
@@ -47,6 +48,12 @@ class TrainingDesc(ctypes.Structure):
 
     _fields_ = [("capacity", ctypes.c_int32), ("return_second_last", ctypes.c_int32),
                 ("drop_path_p", ctypes.c_double), ("seed", ctypes.c_uint64), ("hvp_rel_step", ctypes.c_double)]
+
+
+class MlpDesc(ctypes.Structure):
+    """davo_mlp_desc (include/davo_b200.h)."""
+
+    _fields_ = [(k, ctypes.c_int32) for k in ("B", "in_features", "hidden", "out_features")]
 
 
 class GeneratorDesc(ctypes.Structure):
@@ -103,11 +110,15 @@ def lib() -> ctypes.CDLL:
         L.davo_bfgs_initial_scale.argtypes = [i32] * 3 + [vp] * 4
         L.davo_interpolate_alpha.argtypes = [i32, i64] + [vp] * 6
         L.davo_interpolate_alpha_backward.argtypes = [i32, i64] + [vp] * 10
+        L.davo_mlp_packed_bytes.argtypes = [i32, i32]
+        L.davo_mlp_packed_bytes.restype = i64
+        L.davo_mlp_pack_weights.argtypes = [i32, i32] + [vp] * 3
+        L.davo_mlp_forward.argtypes = [ctypes.POINTER(MlpDesc)] + [vp] * 13
         gp = ctypes.POINTER(GeneratorDesc)
         L.davo_generate_distort10.argtypes = [gp] + [vp] * 6
         L.davo_generate_joint.argtypes = [gp] + [vp] * 5
         L.davo_generate_views_and_points.argtypes = [gp] + [vp] * 9
-        for name in EXPORTED[3:]:
+        for name in EXPORTED[4:]:
             getattr(L, name).restype = ctypes.c_int
         if L.davo_abi_version() != ABI_VERSION:
             raise DavoError(f"libdavo_b200.so has ABI {L.davo_abi_version()}, expected {ABI_VERSION}")

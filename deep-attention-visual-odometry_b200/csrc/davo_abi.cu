@@ -302,6 +302,32 @@ int davo_interpolate_alpha_backward(int32_t dtype, int64_t k, const void* alpha_
     return DAVO_ERR_UNSUPPORTED;
 }
 
+int64_t davo_mlp_packed_bytes(int32_t N, int32_t K) { return launch_mlp_packed_bytes(N, K); }
+
+int davo_mlp_pack_weights(int32_t N, int32_t K, const void* weight, void* packed, void* stream) {
+    if (!weight || !packed) return DAVO_ERR_NULL_POINTER;
+    if (!aligned16(weight) || !aligned16(packed)) return DAVO_ERR_MISALIGNED;
+    return launch_mlp_pack_weights(N, K, static_cast<const float*>(weight), packed, static_cast<cudaStream_t>(stream));
+}
+
+int davo_mlp_forward(const davo_mlp_desc* desc, const void* x, const void* w1_packed, const void* b1,
+                     const void* scale1, const void* shift1, const void* w2_packed, const void* b2,
+                     const void* scale2, const void* shift2, const void* w3_packed, const void* b3, void* x0_out,
+                     void* stream) {
+    if (!desc) return DAVO_ERR_NULL_POINTER;
+    if (desc->B < 0) return DAVO_ERR_BAD_SHAPE;
+    if (desc->B == 0) return DAVO_OK;
+    if (!x || !w1_packed || !b1 || !scale1 || !shift1 || !w2_packed || !b2 || !scale2 || !shift2 || !w3_packed || !b3 ||
+        !x0_out)
+        return DAVO_ERR_NULL_POINTER;
+    if (!aligned16(x) || !aligned16(w1_packed) || !aligned16(w2_packed) || !aligned16(w3_packed))
+        return DAVO_ERR_MISALIGNED;
+    auto f = [](const void* q) { return static_cast<const float*>(q); };
+    return launch_mlp_forward(desc->B, desc->in_features, desc->hidden, desc->out_features, f(x), w1_packed, f(b1),
+                              f(scale1), f(shift1), w2_packed, f(b2), f(scale2), f(shift2), w3_packed, f(b3),
+                              static_cast<float*>(x0_out), static_cast<cudaStream_t>(stream));
+}
+
 int davo_stage_matches(const davo_problem_desc* desc, const void* points_3d, const void* obs,
                        const void* pose, void* staged, void* stream) {
     if (!desc) return DAVO_ERR_NULL_POINTER;

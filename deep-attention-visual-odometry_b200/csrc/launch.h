@@ -57,6 +57,13 @@ int launch_bfgs_update(int k, int n, T* H, const T* s_, const T* y, cudaStream_t
 template <typename T>
 int launch_bfgs_initial_scale(int k, int n, const T* s_, const T* y, T* scale, cudaStream_t s);
 
+// the initial-guess MLP on the tensor cores (mlp_kernels.cu)
+long long launch_mlp_packed_bytes(int N, int K);
+int launch_mlp_pack_weights(int N, int K, const float* W, void* packed, cudaStream_t s);
+int launch_mlp_forward(int B, int K1, int H, int P, const float* x, const void* w1, const float* b1, const float* s1,
+                       const float* t1, const void* w2, const float* b2, const float* s2, const float* t2,
+                       const void* w3, const float* b3, float* out, cudaStream_t s);
+
 template <typename T>
 int launch_generate_distort10(const davo_generator_desc* d, T* pts, T* obs, T* pose, T* x0, T* truth, cudaStream_t s);
 template <typename T>

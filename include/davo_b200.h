@@ -263,6 +263,27 @@ int davo_interpolate_alpha_backward(int32_t dtype, int64_t k, const void* alpha_
                                     void* grad_alpha_1, void* grad_alpha_2, void* grad_value_1, void* grad_value_2,
                                     void* stream);
 
+/* ---- the initial-guess network, fused (networks/calibration_network.py:35-43) ------------------------------------
+ * Linear(in, H) - GELU - BatchNorm1d(H) - Linear(H, H) - GELU - BatchNorm1d(H) - Linear(H, P) in inference form, one
+ * kernel on the tcgen05 tensor cores (TF32 with operand splitting: float32 accuracy), writing the solver's start
+ * parameters x0[B, P].  float32 only; in_features % 8 == 0, hidden % 16 == 0, hidden <= 256, P <= 256.
+ * Each Linear's weight [N, K] (row major, as torch stores it) is first re-laid by davo_mlp_pack_weights into a buffer
+ * of davo_mlp_packed_bytes(N, K) bytes (split into TF32 high and low parts in the tensor cores' shared-memory
+ * layout; repack when the weights change).  scale/shift fold BatchNorm1d's running statistics and affine
+ * parameters: scale = weight / sqrt(running_var + eps), shift = bias - running_mean * scale. */
+typedef struct davo_mlp_desc {
+    int32_t B;             /* rows                                     */
+    int32_t in_features;   /* 2 * views * points                       */
+    int32_t hidden;        /* H                                        */
+    int32_t out_features;  /* P = 3 + 3 N + 6 (M - 1)                  */
+} davo_mlp_desc;
+int64_t davo_mlp_packed_bytes(int32_t N, int32_t K);
+int davo_mlp_pack_weights(int32_t N, int32_t K, const void* weight, void* packed, void* stream);
+int davo_mlp_forward(const davo_mlp_desc* desc, const void* x, const void* w1_packed, const void* b1,
+                     const void* scale1, const void* shift1, const void* w2_packed, const void* b2,
+                     const void* scale2, const void* shift2, const void* w3_packed, const void* b3, void* x0_out,
+                     void* stream);
+
 /* ---- synthetic oracle-match generator, on the device -------------------------------------------------
  * Replaces the reference's host-side dataset (data/camera_and_parameters_dataset.py:48-61,85-151, batch layout
  * base_types/camera_views_and_points.py:21-33; that file does not parse at HEAD) and this repo's numpy generators

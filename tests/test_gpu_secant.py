@@ -99,3 +99,41 @@ def test_secant_solve_matches_oracle_and_saves_evaluations(dt):
     assert np.allclose(got.parameters.numpy()[same], want["x"][same], rtol=tol, atol=tol)
     assert float(got.converged.float().mean()) >= float(plain.converged.float().mean()) - 0.02
     assert int(got.evaluations.sum()) <= 1.05 * int(plain.evaluations.sum())
+
+
+# ---- the fused initial-guess network (csrc/mlp_kernels.cu) ------------------------------------------------------
+
+def _reference_mlp(net, x):
+    """The torch modules in float64 on the CPU (no GPU library call: the GPU test run must show no cuBLAS kernel)."""
+    import copy
+    ref = copy.deepcopy(net.initial_estimator).double().cpu().eval()
+    with torch.no_grad():
+        return ref(x.double().cpu())
+
+
+@pytest.mark.parametrize("views,points,hidden,B", [(4, 8, -1, 300), (4, 8, -1, 65536), (2, 4, 64, 129), (3, 12, 144, 1000)])
+def test_fused_initial_estimator_matches_torch_modules(views, points, hidden, B):
+    torch.manual_seed(views * 100 + points)
+    net = davo_b200.CalibrationNetwork(views, points, hidden_size=hidden).cuda()
+    # non-trivial BatchNorm statistics and affine parameters
+    for bn in (net.initial_estimator[2], net.initial_estimator[5]):
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.data.uniform_(0.5, 1.5)
+        bn.bias.data.normal_(0, 0.2)
+    net.eval()
+    x = torch.randn(B, 2 * views * points, device="cuda")
+    with torch.no_grad():
+        got = net.estimate(x)
+    want = _reference_mlp(net, x)
+    assert got.shape == want.shape and got.dtype == torch.float32
+    err = float((got.double().cpu() - want).abs().max() / want.abs().max())
+    print("fused MLP", (views, points, hidden, B), "max error relative to max |output|", err)
+    assert err <= 1e-5
+    # weights changed in place -> the packed copy is rebuilt
+    with torch.no_grad():
+        net.initial_estimator[6].bias.add_(1.0)
+        again = net.estimate(x)
+    assert float((again - got - 1.0).abs().max()) <= 1e-5
+    # training mode and grad mode run the torch modules
+    assert net.estimate(x[:64]).requires_grad
