@@ -223,6 +223,8 @@ def main():
                     help="arithmetic type (BASELINE asks for f32; the entry script itself trains in f64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="time the K steps one batch at a time on one stream (no second batch in flight)")
     ap.add_argument("--no-side-configs", action="store_true",
                     help="skip the 'configs' object (cfg3, cfg4, bundle adjustment, cfg5 strong scaling)")
     ap.add_argument("--side-steps", type=int, default=5, help="timed steps per side configuration")
@@ -298,6 +300,13 @@ def main():
         flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev) if input_bytes <= L2_BYTES else None
         slab = ResultSlab(B * world, batch.n, t_dt, world, dev)
         out = slab.buffers(rank)
+        # Throughput pass: the K timed steps alternate between two streams, each with its own result slab (a step
+        # allocates its own staged matches), so the tail of one launch — the last problems of a persistent grid, or
+        # config 4's stragglers on a handful of SMs — overlaps the head of the next.  Only without the L2 flush
+        # (its per-step events need the steps one after the other).
+        pipelined = flush is None and not args.no_pipeline
+        slab2 = ResultSlab(B * world, batch.n, t_dt, world, dev) if pipelined else None
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)] if pipelined else None
 
         def make_objective(pts, obs):
             if batch.model == "distort10":
@@ -306,7 +315,8 @@ def main():
                 return davo_b200.AngleDistanceObjective(obs, pts)
             return davo_b200.JointPoseObjective(pts, obs)
 
-        def step(ev=None):
+        def step(ev=None, which=0):
+            sl = slab if which == 0 else slab2
             if flush is not None:
                 flush.zero_()
             if ev:
@@ -314,10 +324,10 @@ def main():
             obj = make_objective(d_pts, d_obs)
             if ev:
                 ev[1].record()
-            solver.solve_into(d_x0, obj, out=out)
+            solver.solve_into(d_x0, obj, out=sl.buffers(rank))
             if ev:
                 ev[2].record()
-            slab.all_gather(rank)
+            sl.all_gather(rank)
             if ev:
                 ev[3].record()
 
@@ -345,10 +355,27 @@ def main():
                     else float(sum(e[0].elapsed_time(e[3]) for e in events)))
         solve_kernel_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
         stage_kernel_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
+        sequential_ms = total_ms
+        if pipelined:
+            main_stream = torch.cuda.current_stream()
+            barrier()
+            launches0 = _lib.launch_count()
+            t_start.record()
+            for st in streams:
+                st.wait_stream(main_stream)
+            for k in range(steps):
+                with torch.cuda.stream(streams[k % 2]):
+                    step(None, k % 2)
+            for st in streams:
+                main_stream.wait_stream(st)
+            t_end.record()
+            barrier()
+            launches = _lib.launch_count() - launches0
+            total_ms = t_start.elapsed_time(t_end)
         if world > 1:
-            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            t = torch.tensor([total_ms, sequential_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
+            total_ms, sequential_ms = float(t[0].item()), float(t[1].item())
         ms_per_step = total_ms / steps
 
         iters = out.iterations.cpu().numpy()
@@ -415,7 +442,11 @@ def main():
                               else f"L2 flushed between timed steps (a {2 * L2_BYTES >> 20} MiB buffer is rewritten, "
                                    f"outside the per-step events; inputs are {input_bytes / 1e6:.0f} MB per GPU)"),
                        "collective": "one all_gather_into_tensor of the solved records"
-                       if world > 1 else "none (single GPU)"},
+                       if world > 1 else "none (single GPU)",
+                       "pipeline": ("the K timed steps alternate between 2 CUDA streams (2 batches in flight): the tail of "
+                                    "one launch overlaps the head of the next; ms_per_step_sequential is the same K steps "
+                                    "one batch at a time on one stream") if pipelined else "one batch at a time"},
+            "ms_per_step_sequential": sequential_ms / steps,
             "kernel_ms": {"solve": solve_kernel_ms, "stage": stage_kernel_ms},
             "mean_iters": float(iters.mean()), "mean_fevals": float(fevals.mean()), "reasons_rank0": reasons,
             "roofline": {"bound": "fp32" if dtype == "f32" else "fp64", "achieved": achieved, "peak": pipe_peak,
@@ -433,7 +464,7 @@ def main():
                 "traffic": stage_traffic, "bytes_counted": "20 B read + 16 B written per match"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
-        del d_pts, d_obs, d_x0, slab, out, flush
+        del d_pts, d_obs, d_x0, slab, slab2, out, flush
         torch.cuda.empty_cache()
         return res
 
@@ -454,7 +485,9 @@ def main():
         for label, cfg, dt, skw in plan:
             r = measure(cfg, default_B(cfg, world), dt, side_steps, 3, skw, with_e2e=False, with_clocks=False)
             side[label] = {"workload": r["config"]["workload"], "solver": skw, "dtype": dt, "value": r["value"],
-                           "unit": "solves/s", "ms_per_step": r["ms_per_step"], "steps": side_steps,
+                           "unit": "solves/s", "ms_per_step": r["ms_per_step"],
+                           "ms_per_step_sequential": r["ms_per_step_sequential"], "pipeline": r["timing"]["pipeline"],
+                           "steps": side_steps,
                            "kernel_ms": r["kernel_ms"]["solve"], "bfgs_iters_per_sec": r["bfgs_iters_per_sec"],
                            "mean_iters": r["mean_iters"], "mean_fevals": r["mean_fevals"],
                            "converged_frac": r["converged_frac"], "reasons_rank0": r["reasons_rank0"],
@@ -475,7 +508,7 @@ def main():
             "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic"}
-    for k in ("config", "timing", "kernel_ms", "mean_iters", "mean_fevals", "reasons_rank0", "roofline", "roofline_staging",
+    for k in ("config", "timing", "ms_per_step_sequential", "kernel_ms", "mean_iters", "mean_fevals", "reasons_rank0", "roofline", "roofline_staging",
               "clocks", "gpu_launches", "e2e"):
         line[k] = head[k]
     if side:

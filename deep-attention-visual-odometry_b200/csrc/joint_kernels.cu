@@ -23,7 +23,10 @@ __host__ __device__ inline size_t joint_cta_smem(int N, int V, int n, bool has_w
 }
 
 #ifndef DAVO_JOINT_MIN_BLOCKS
-#define DAVO_JOINT_MIN_BLOCKS 8  // CTAs of 2 warps per SM (128 registers, no spills): 25.1 ms for config 3; 10: 25.7, 12: 29.2
+// CTAs of 2 warps per SM.  With the pose gradient accumulated as sum X' x gX' (3 sums instead of the 9 of
+// sum gX' (x) X, solver_cta.cuh) the evaluator fits 96 registers without spills: config 3 takes 22.8 ms at 8 CTAs
+// (122 registers), 21.6 ms at 10, 23.7 ms at 11-12; the 9-sum form took 25.0 ms at 8 and spilled at 10 (25.7 ms).
+#define DAVO_JOINT_MIN_BLOCKS 10
 #endif
 #ifndef DAVO_JOINT_WARPS
 #define DAVO_JOINT_WARPS 2       // warps per problem for V >= 2: 25.1 ms vs 27.3 ms with 4 (fewer barriers; still ~11 problems per CTA)

@@ -145,15 +145,15 @@ struct JointCtaObjective {
             const T r00 = cy * cz, r01 = sx * sy * cz - cx * sz, r02 = cx * sy * cz + sx * sz;
             const T r10 = cy * sz, r11 = sx * sy * sz + cx * cz, r12 = cx * sy * sz - sx * cz;
             const T r20 = -sy, r21 = sx * cy, r22 = cx * cy;
-            T part[kSlots];  // 0..8: M = sum gX' (x) X (row major), 9..11: g_t = sum gX'
+            T part[kSlots];  // 0..2: sum X' x gX', 3..5: g_t = sum gX'
 #pragma unroll
             for (int k = 0; k < kSlots; ++k) part[k] = T(0);
             const V2* ob = reinterpret_cast<const V2*>(obs) + (size_t)v * N;
             const T* wv = wts + (size_t)v * N;
 #if DAVO_JOINT_PACKED
-            P part2[12];
+            P part2[6];
 #pragma unroll
-            for (int k = 0; k < 12; ++k) part2[k] = pk(T(0));
+            for (int k = 0; k < 6; ++k) part2[k] = pk(T(0));
             for (int i = lane; i < N; i += 64) {
                 const bool second_valid = i + 32 < N;
                 const int i1 = second_valid ? i + 32 : i;  // a missing second match re-reads the first; its residuals are zeroed
@@ -165,7 +165,8 @@ struct JointCtaObjective {
                 if (kWeighted) { w2.x = wv[i]; w2.y = second_valid ? wv[i1] : T(0); }
                 const P xp = pfma(X, pk(r00), pfma(Y, pk(r01), pfma(Z, pk(r02), pk(t0))));
                 const P yp = pfma(X, pk(r10), pfma(Y, pk(r11), pfma(Z, pk(r12), pk(t1))));
-                P zp = pfma(X, pk(r20), pfma(Y, pk(r21), pfma(Z, pk(r22), pk(t2))));
+                const P zr = pfma(X, pk(r20), pfma(Y, pk(r21), pfma(Z, pk(r22), pk(t2))));
+                P zp = zr;
                 if (zp.x == T(0)) zp.x += T(1e-8);  // :57
                 if (zp.y == T(0)) zp.y += T(1e-8);
                 P iz;
@@ -178,13 +179,14 @@ struct JointCtaObjective {
                 const P gB = pfma(gu, pk(I.s), pmul(gv, pk(I.fy)));
                 const P gx = pmul(gA, iz), gy = pmul(gB, iz);
                 const P gz = pmul(pfma(gA, a, pmul(gB, b)), pmul(pk(T(-1)), iz));
-                part2[0] = pfma(gx, X, part2[0]); part2[1] = pfma(gx, Y, part2[1]); part2[2] = pfma(gx, Z, part2[2]);
-                part2[3] = pfma(gy, X, part2[3]); part2[4] = pfma(gy, Y, part2[4]); part2[5] = pfma(gy, Z, part2[5]);
-                part2[6] = pfma(gz, X, part2[6]); part2[7] = pfma(gz, Y, part2[7]); part2[8] = pfma(gz, Z, part2[8]);
-                part2[9] = padd(part2[9], gx); part2[10] = padd(part2[10], gy); part2[11] = padd(part2[11], gz);
+                const P ngx = pmul(pk(T(-1)), gx), ngy = pmul(pk(T(-1)), gy), ngz = pmul(pk(T(-1)), gz);
+                part2[0] = pfma(yp, gz, pfma(zr, ngy, part2[0]));   // X' x gX'
+                part2[1] = pfma(zr, gx, pfma(xp, ngz, part2[1]));
+                part2[2] = pfma(xp, gy, pfma(yp, ngx, part2[2]));
+                part2[3] = padd(part2[3], gx); part2[4] = padd(part2[4], gy); part2[5] = padd(part2[5], gz);
             }
 #pragma unroll
-            for (int k = 0; k < 12; ++k) part[k] = part2[k].x + part2[k].y;
+            for (int k = 0; k < 6; ++k) part[k] = part2[k].x + part2[k].y;
 #else
 #pragma unroll 2
             for (int i = lane; i < N; i += 32) {
@@ -192,7 +194,8 @@ struct JointCtaObjective {
                 const V2 o = ob[i];
                 const T xp = fma_t(X, r00, fma_t(Y, r01, fma_t(Z, r02, t0)));
                 const T yp = fma_t(X, r10, fma_t(Y, r11, fma_t(Z, r12, t1)));
-                T zp = fma_t(X, r20, fma_t(Y, r21, fma_t(Z, r22, t2)));
+                const T zr = fma_t(X, r20, fma_t(Y, r21, fma_t(Z, r22, t2)));
+                T zp = zr;
                 if (zp == T(0)) zp += T(1e-8);  // :57
                 const T iz = div_rn(T(1), zp);
                 const T a = xp * iz, b = yp * iz;
@@ -202,36 +205,28 @@ struct JointCtaObjective {
                 const T gB = fma_t(gu, I.s, gv * I.fy);
                 const T gx = gA * iz, gy = gB * iz;
                 const T gz = -fma_t(gA, a, gB * b) * iz;
-                part[0] = fma_t(gx, X, part[0]); part[1] = fma_t(gx, Y, part[1]); part[2] = fma_t(gx, Z, part[2]);
-                part[3] = fma_t(gy, X, part[3]); part[4] = fma_t(gy, Y, part[4]); part[5] = fma_t(gy, Z, part[5]);
-                part[6] = fma_t(gz, X, part[6]); part[7] = fma_t(gz, Y, part[7]); part[8] = fma_t(gz, Z, part[8]);
-                part[9] += gx; part[10] += gy; part[11] += gz;
+                part[0] = fma_t(yp, gz, fma_t(-zr, gy, part[0]));   // X' x gX'
+                part[1] = fma_t(zr, gx, fma_t(-xp, gz, part[1]));
+                part[2] = fma_t(xp, gy, fma_t(-yp, gx, part[2]));
+                part[3] += gx; part[4] += gy; part[5] += gz;
             }
 #endif
+            // d(cost/2)/dr_k = sum gX' . dX'/dr_k with dX'/dr_k = a_k x (R X): the derivative of R = Rz Ry Rx with
+            // respect to an Euler angle is the cross product with that angle's (rotated) axis, a_x = Rz Ry e_x,
+            // a_y = Rz e_y, a_z = e_z.  So sum gX' . (a_k x RX) = a_k . sum (RX x gX'), and with RX = X' - t:
+            // c = sum X' x gX' - t x sum gX'.  Three accumulators instead of the nine of sum gX' (x) X.
             const T mine = reduce_scatter16<true>(part, lane);  // total of slot lane >> 1
-            // every lane needs all of M for <dR/dr_k, M>_F: 12 broadcasts from the owning lanes
-            const T m0 = shfl_idx(mine, 0), m1 = shfl_idx(mine, 2), m2 = shfl_idx(mine, 4), m3 = shfl_idx(mine, 6),
-                    m4 = shfl_idx(mine, 8), m5 = shfl_idx(mine, 10), m6 = shfl_idx(mine, 12),
-                    m7 = shfl_idx(mine, 14), m8 = shfl_idx(mine, 16);
+            const T c0 = shfl_idx(mine, 0), c1 = shfl_idx(mine, 2), c2 = shfl_idx(mine, 4), g0 = shfl_idx(mine, 6),
+                    g1 = shfl_idx(mine, 8), g2 = shfl_idx(mine, 10);
             if (lane < 3) {
-                T d0, d1, d2, d3, d4, d5, d6, d7, d8;  // dR/dr_k of R = Rz Ry Rx
-                if (lane == 0) {
-                    d0 = T(0); d1 = cx * sy * cz + sx * sz;  d2 = -sx * sy * cz + cx * sz;
-                    d3 = T(0); d4 = cx * sy * sz - sx * cz;  d5 = -sx * sy * sz - cx * cz;
-                    d6 = T(0); d7 = cx * cy;                 d8 = -sx * cy;
-                } else if (lane == 1) {
-                    d0 = -sy * cz; d1 = sx * cy * cz; d2 = cx * cy * cz;
-                    d3 = -sy * sz; d4 = sx * cy * sz; d5 = cx * cy * sz;
-                    d6 = -cy;      d7 = -sx * sy;     d8 = -cx * sy;
-                } else {
-                    d0 = -cy * sz; d1 = -sx * sy * sz - cx * cz; d2 = -cx * sy * sz + sx * cz;
-                    d3 = cy * cz;  d4 = sx * sy * cz - cx * sz;  d5 = cx * sy * cz + sx * sz;
-                    d6 = T(0); d7 = T(0); d8 = T(0);
-                }
-                const T out = d0 * m0 + d1 * m1 + d2 * m2 + d3 * m3 + d4 * m4 + d5 * m5 + d6 * m6 + d7 * m7 + d8 * m8;
+                const T cx_ = c0 - (t1 * g2 - t2 * g1), cy_ = c1 - (t2 * g0 - t0 * g2), cz_ = c2 - (t0 * g1 - t1 * g0);
+                T out;
+                if (lane == 0) out = cz * cy * cx_ + sz * cy * cy_ - sy * cz_;   // a_x = (cz cy, sz cy, -sy)
+                else if (lane == 1) out = cz * cy_ - sz * cx_;                   // a_y = (-sz, cz, 0)
+                else out = cz_;                                                  // a_z = (0, 0, 1)
                 gout[10 + 6 * v + lane] = T(2) * out;  // least_squares_utils.py:43
             }
-            if (lane >= 18 && lane < 24 && !(lane & 1)) gout[10 + 6 * v + 3 + ((lane - 18) >> 1)] = T(2) * mine;  // d/dt
+            if (lane >= 6 && lane < 12 && !(lane & 1)) gout[10 + 6 * v + 3 + ((lane - 6) >> 1)] = T(2) * mine;  // d/dt
         }
 #if DAVO_JOINT_PACKED
         T acc[kSlots];

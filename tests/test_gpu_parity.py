@@ -744,7 +744,7 @@ def test_calibration_network_forward_refines_its_initial_guess():
     net = davo_b200.CalibrationNetwork(4, 8).cuda().eval()
     obs, vis = torch.from_numpy(b.obs).cuda(), torch.from_numpy(b.weights).cuda() > 0
     with torch.no_grad():
-        guess = net.initial_estimator(obs.reshape(-1, 64))
+        guess = net.estimate(obs.reshape(-1, 64))  # the fused tcgen05 kernel (tests/test_gpu_secant.py pins it to the modules)
         params, err = net(obs, vis, return_error=True)
     assert params.shape == (48, 45) and err.shape == (48,) and params.device.type == "cuda"
     obj = davo_b200.AngleDistanceObjective(obs, vis)
