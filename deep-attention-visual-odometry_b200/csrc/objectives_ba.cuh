@@ -20,6 +20,20 @@
 
 namespace davo {
 
+// norm = max(sqrt(sq), floor), inv = 1 / norm.  (inv is unused garbage when norm == 0 and floor == 0: callers test.)
+__device__ __forceinline__ void norm_and_inverse(double sq, double floor, double& norm, double& inv) {
+    norm = sqrt_rn(sq);
+    norm = norm < floor ? floor : norm;
+    inv = rcp_rn(norm);
+}
+__device__ __forceinline__ void norm_and_inverse(float sq, float floor, float& norm, float& inv) {
+    const float f2 = floor * floor;
+    const float v = sq < f2 ? f2 : sq;
+    inv = rsqrtf(v);
+    norm = v * inv;
+    if (v == 0.0f) { norm = 0.0f; inv = 0.0f; }
+}
+
 // kV, kN > 0 fix the number of views / points at compile time (the entry script's configuration is 4 views x 8
 // points, camera_calibration_from_oracle_matches.py:34-35: loops unroll, index arithmetic folds); 0 = run time.
 template <typename T, int kV = 0, int kN = 0>
@@ -142,22 +156,24 @@ struct AngleBAObjective {
                 P2 = x2 * cn + od * o2 + c2 * s + ts2;
             }
             const T h0 = obs[2 * i] - cx, h1 = obs[2 * i + 1] - cy, h2 = fp;  // homogeneous_projection.py:38-44
-            T nh = sqrt_rn(h0 * h0 + h1 * h1 + h2 * h2);
-            T nP = sqrt_rn(P0 * P0 + P1 * P1 + P2 * P2);
-            nh = nh < kEps ? kEps : nh;
-            nP = nP < kEps ? kEps : nP;
-            const T inh = rcp_rn(nh), inP = rcp_rn(nP);
+            // |h|, |P|, |a + b|, |a - b| and their reciprocals: float64 rounds every one correctly (the parity gates of
+            // this objective are float64); float32 takes norm and reciprocal from ONE reciprocal square root each
+            // (MUFU.RSQ, ~1 ulp): the correctly rounded sqrt and 1/x sequences were a fifth of the evaluator
+            T nh, nP, inh, inP;
+            norm_and_inverse(h0 * h0 + h1 * h1 + h2 * h2, kEps, nh, inh);
+            norm_and_inverse(P0 * P0 + P1 * P1 + P2 * P2, kEps, nP, inP);
             const T a0 = h0 * inh, a1 = h1 * inh, a2 = h2 * inh;
             const T b0 = P0 * inP, b1 = P1 * inP, b2 = P2 * inP;
             const T s0 = a0 + b0, s1 = a1 + b1, s2 = a2 + b2;
             const T d0 = a0 - b0, d1 = a1 - b1, d2 = a2 - b2;
-            const T S = sqrt_rn(s0 * s0 + s1 * s1 + s2 * s2);
-            const T D = sqrt_rn(d0 * d0 + d1 * d1 + d2 * d2);
+            T S, D, rS, rD;
+            norm_and_inverse(s0 * s0 + s1 * s1 + s2 * s2, T(0), S, rS);
+            norm_and_inverse(d0 * d0 + d1 * d1 + d2 * d2, T(0), D, rD);
             const T vz = vis[i];
             cost += T(2) * atan2(D, S) * vz;  // projective_plane_angle_distance.py:53-60
             const T w2 = T(2) * vz * rcp_rn(S * S + D * D);  // atan2 backward: d/dD = S / (S^2 + D^2), d/dS = -D / (S^2 + D^2)
-            const T iD = (D != T(0)) ? w2 * S * rcp_rn(D) : T(0);   // vector_norm backward: zero sub-gradient at 0
-            const T iS = (S != T(0)) ? -w2 * D * rcp_rn(S) : T(0);
+            const T iD = (D != T(0)) ? w2 * S * rD : T(0);   // vector_norm backward: zero sub-gradient at 0
+            const T iS = (S != T(0)) ? -w2 * D * rS : T(0);
             const T ga0 = iD * d0 + iS * s0, ga1 = iD * d1 + iS * s1, ga2 = iD * d2 + iS * s2;
             const T gb0 = iS * s0 - iD * d0, gb1 = iS * s1 - iD * d1, gb2 = iS * s2 - iD * d2;
             const T gaa = ga0 * a0 + ga1 * a1 + ga2 * a2;

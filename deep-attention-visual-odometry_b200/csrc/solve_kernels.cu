@@ -205,10 +205,12 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
 
 // ---- second launch of a DISTORT10 solve: one CTA (4 warps) per handed-off problem ------------------------------
 #ifndef DAVO_RESOLVE_WARPS
-// Warps that share one evaluation x groups (DAVO_SPEC_PROBES, solver_cta.cuh) = one 512-thread CTA per straggler.
-// Measured on config 4 (64K problems; 13.7 ms of it is the first launch), whole solve: 4 x 1 (no speculation) 43.4 ms,
-// 4 x 4 32.8, 2 x 8 28.7, 1 x 16 27.6, 1 x 24 30.0, 4 x 8 (1024 threads, spills) 49.4.  The longest straggler alone
-// (47.8 K probes in ~45-probe D chains): 16.0 ms of re-solve at 4 x 4, 10.5 ms at 1 x 16 (tools/straggler_probe.py).
+// Warps that share one evaluation; the CTA is DAVO_SPEC_PROBES groups of them, each evaluating DAVO_SPEC_PER_GROUP
+// trial points per line-search round (solver_cta.cuh).  Measured on config 4 (64K problems; 13.7 ms of it is the first
+// launch), whole solve, warps x groups x points per group: 4 x 1 x 1 (no speculation) 43.4 ms, 4 x 4 x 1 32.8,
+// 2 x 8 x 1 28.7, 1 x 16 x 1 27.6-28.5, 1 x 16 x 2 27.7, 1 x 8 x 2 28.8, 1 x 8 x 4 27.0 (256 threads), 1 x 24 x 1 30.0,
+// 4 x 8 x 1 (1024 threads, spills) 49.4.  The longest straggler alone (47.8 K probes in ~45-probe D chains): 16.0 ms
+// of re-solve at 4 x 4 x 1, ~10 ms from 16 trial points per round up (tools/straggler_probe.py).
 #define DAVO_RESOLVE_WARPS 1
 #endif
 constexpr int kResolveWarps = DAVO_RESOLVE_WARPS;   // warps that share one evaluation

@@ -260,13 +260,17 @@ struct JointCtaObjective {
 // group's warps through `red` with one barrier); the G groups exist for the speculative line search below, where each
 // group evaluates a different trial point.  Results do not depend on G.
 #ifndef DAVO_SPEC_PROBES
-#define DAVO_SPEC_PROBES 16  // G: trial points evaluated per round of the stragglers' line search (1: no speculation)
+#define DAVO_SPEC_PROBES 8  // G: groups of warps, each evaluating its own trial points (1 x 1: no speculation)
+#endif
+#ifndef DAVO_SPEC_PER_GROUP
+#define DAVO_SPEC_PER_GROUP 4  // trial points each group evaluates per round, one after the other
 #endif
 
 template <typename T, int W, int G = 1>
 struct Distort10CtaObjective {
     static constexpr int kParams = 10;
-    static constexpr int kSpecProbes = G;
+    static constexpr int kPerGroup = DAVO_SPEC_PER_GROUP;
+    static constexpr int kSpecProbes = G * kPerGroup;   // trial points per round
     static constexpr bool kSpeculative = true;
     static constexpr int kKeep = 11;  // folded per-thread sums of one probe: 10 gradient sums + cost
     using V4 = typename Vec4<T>::type;
@@ -369,26 +373,30 @@ struct Distort10CtaObjective {
     // its 11 folded sums in registers; the full gradient is reduced once, for the probe the search accepts
     // (finish_gradient).  xt: G parameter lines of 16 entries; d2[c] = 2 d_c (least_squares_utils.py:43's factor
     // folded in).  Leaves this group's per-warp partial (cost, d . grad) in red[(grp W + warp) 2 + {0, 1}].
-    __device__ __forceinline__ void probe_partial(const T* xt, const T (&d2)[10], T (&keep)[kKeep]) {
-        T acc[kSlots];
-        accumulate(xt + 16 * grp, acc);
+    __device__ __forceinline__ void probe_partial(const T* xt, const T (&d2)[10], T (&keep)[kPerGroup][kKeep]) {
 #pragma unroll
-        for (int k = 0; k < kKeep; ++k) keep[k] = acc[k];
-        T e = d2[0] * acc[0], o = d2[1] * acc[1];
+        for (int q = 0; q < kPerGroup; ++q) {
+            const int j = q * G + grp;   // this group's q-th trial point
+            T acc[kSlots];
+            accumulate(xt + 16 * j, acc);
 #pragma unroll
-        for (int c = 2; c < 10; c += 2) {
-            e = fma_t(d2[c], acc[c], e);
-            o = fma_t(d2[c + 1], acc[c + 1], o);
-        }
-        T pf = acc[10], pd = e + o;
+            for (int k = 0; k < kKeep; ++k) keep[q][k] = acc[k];
+            T e = d2[0] * acc[0], o = d2[1] * acc[1];
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            pf += shfl_xor(pf, m);
-            pd += shfl_xor(pd, m);
-        }
-        if (lane == 0) {
-            red[(grp * W + warp) * 2] = pf;
-            red[(grp * W + warp) * 2 + 1] = pd;
+            for (int c = 2; c < 10; c += 2) {
+                e = fma_t(d2[c], acc[c], e);
+                o = fma_t(d2[c + 1], acc[c + 1], o);
+            }
+            T pf = acc[10], pd = e + o;
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) {
+                pf += shfl_xor(pf, m);
+                pd += shfl_xor(pd, m);
+            }
+            if (lane == 0) {
+                red[(j * W + warp) * 2] = pf;
+                red[(j * W + warp) * 2 + 1] = pd;
+            }
         }
     }
     // (cost, d . grad) of probe j from the partials (every thread that calls it adds them in the same order)
@@ -403,11 +411,17 @@ struct Distort10CtaObjective {
         dphi = ds;
     }
 
-    // The gradient of the probe group `sel` evaluated in the last eval_probes round: the tail of eval().
-    __device__ __forceinline__ void finish_gradient(const T (&kept)[kKeep], int sel, T* gout) {
+    // The gradient of trial point `sel` of the last probe_partial round: the tail of eval().
+    __device__ __forceinline__ void finish_gradient(const T (&keep)[kPerGroup][kKeep], int sel_probe, T* gout) {
+        const int sel = sel_probe % G, q_sel = sel_probe / G;
         T acc[kSlots];
 #pragma unroll
-        for (int k = 0; k < kKeep; ++k) acc[k] = kept[k];
+        for (int k = 0; k < kKeep; ++k) {
+            T v = keep[0][k];
+#pragma unroll
+            for (int q = 1; q < kPerGroup; ++q) v = (q_sel == q) ? keep[q][k] : v;
+            acc[k] = v;
+        }
 #pragma unroll
         for (int k = kKeep; k < kSlots; ++k) acc[k] = T(0);
         const T mine = reduce_scatter16<true>(acc, lane);
@@ -576,13 +590,13 @@ __device__ __forceinline__ LineSearchResult<T> line_search_cta_spec(Obj& obj, co
                                                                     T* ctl) {
     constexpr int K = Obj::kSpecProbes;
     constexpr int n = Obj::kParams;
-    static_assert(n == 10 && 16 * K <= 3 * kWideMax && K <= 24, "speculative probes: 10 parameters, K lines of 16 in xt");
+    static_assert(n == 10 && 16 * K <= 4 * kWideMax && K <= 32, "speculative probes: 10 parameters, K lines of 16 in xt");
     const int tid = threadIdx.x, lane = tid & 31;
     const bool boss = tid < 32;  // warp 0 owns the state machine
     T d2[10];
 #pragma unroll
     for (int c = 0; c < 10; ++c) d2[c] = T(2) * d[c];
-    T keep[Obj::kKeep];
+    T keep[Obj::kPerGroup][Obj::kKeep];
     WolfeState<T> st;
     st.start(f0, wide_dot(d, g, n, lane), p.c2);
     T c_mine = T(0);  // warp 0, lane j < K: trial step of probe j in the current round
@@ -750,7 +764,7 @@ __device__ __forceinline__ void solve_one_cta(Obj& obj, const SolveParams<T>& p,
         }
         __syncthreads();
         LineSearchResult<T> ls;                                                                // :181-190
-        if constexpr (Obj::kSpeculative) ls = line_search_cta_spec<T, W>(obj, p, x, d, f, g, ws.y /* y, yH, Hy: 3 kWideMax words, free here */, gt, ws.xt);
+        if constexpr (Obj::kSpeculative) ls = line_search_cta_spec<T, W>(obj, p, x, d, f, g, ws.s /* s, y, yH, Hy: 4 kWideMax words, free here */, gt, ws.xt);
         else ls = line_search_cta<T, W>(obj, p, x, d, f, g, ws.xt, gt);
         fevals += ls.probes;
         ++iters;

@@ -10,6 +10,7 @@
 #pragma once
 #include "davo_common.cuh"
 #include "solver_warp.cuh"  // same_bits
+#include "objectives.cuh"   // pfma / pk (packed pairs)
 #include "train_params.cuh"
 
 namespace davo {
@@ -19,6 +20,13 @@ constexpr int kWideMax = 128;  // lane L works on components L, L + 32, ... (kCo
 __host__ __device__ constexpr int wide_cols(int n) { return n <= 64 ? 2 : 4; }
 // length of one n-vector in the per-warp workspace (>= 64: the sweeps park unused lanes on scratch words of xt)
 __host__ __device__ constexpr int wide_vec(int n) { return n <= 64 ? 64 : 128; }
+
+// Row stride of the inverse Hessian.  Run-time n: odd (a lane walking its row and 32 lanes reading one column are both
+// bank-conflict free).  Compile-time n: the smallest stride >= n that is 4 (mod 8): rows are 16-byte aligned, so a lane
+// reads and writes its row four values at a time, and 8 consecutive rows start in 8 different 16-byte bank groups
+// (conflict-free 128-bit accesses); a column read is still one word per lane in consecutive banks.
+__host__ __device__ constexpr int wide_ld_aligned(int n) { return ((n + 3) & ~7) + 4 >= n ? ((n + 3) & ~7) + 4 : ((n + 3) & ~7) + 12; }
+__host__ __device__ constexpr int wide_ld_max(int n) { return wide_ld_aligned(n) > (n | 1) ? wide_ld_aligned(n) : (n | 1); }
 
 #ifndef DAVO_WIDE_FAITHFUL
 #define DAVO_WIDE_FAITHFUL 0  // 1: op-by-op rounding of the BFGS update (A/B builds)
@@ -40,7 +48,7 @@ struct WideWorkspace {
     T *x, *g, *gprev, *d, *s, *y, *yH, *Hy, *xt, *gt, *H;
     int ld;  // row stride of H
     __host__ __device__ static size_t bytes(int n) {
-        return sizeof(T) * (10 * (size_t)wide_vec(n) + (size_t)n * (n + 1));
+        return sizeof(T) * (10 * (size_t)wide_vec(n) + (size_t)n * wide_ld_max(n));
     }
     __device__ void carve(unsigned char* base, int n) {
         T* p = reinterpret_cast<T*>(base);
@@ -128,9 +136,12 @@ __device__ __forceinline__ LineSearchResult<T> line_search_wide(Obj& obj, const 
 template <int kCols = 2, typename T, typename Obj, typename Rec = NoRecorder>
 __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p, int b, WideWorkspace<T>& ws,
                                                int lane, const Rec rec = Rec()) {
+    // float32 with a compile-time n: 16-byte-aligned rows and the vectorised sweeps below (float64 gains nothing from
+    // them — its packed operations are pairs of scalar ones and a row chunk is two 128-bit loads: 460 ms against 447)
+    constexpr bool kVectorRows = Obj::kParams > 0 && sizeof(T) == 4;
     // an objective with a compile-time parameter count (Obj::kParams > 0) turns n and the row stride into
     // constants: the sweeps over H below unroll with immediate offsets
-    const int n = Obj::kParams > 0 ? Obj::kParams : p.n, ld = Obj::kParams > 0 ? (Obj::kParams | 1) : ws.ld;
+    const int n = Obj::kParams > 0 ? Obj::kParams : p.n, ld = kVectorRows ? wide_ld_aligned(Obj::kParams) : (Obj::kParams > 0 ? (Obj::kParams | 1) : ws.ld);
     T *x = ws.x, *g = ws.g, *gprev = ws.gprev, *gt = ws.gt;
     T *d = ws.d, *s = ws.s, *y = ws.y, *yH = ws.yH, *Hy = ws.Hy, *H = ws.H;
     __syncwarp();
@@ -364,80 +375,174 @@ __device__ __forceinline__ void solve_one_wide(Obj& obj, const SolveParams<T>& p
                 // conflict free.  The new direction -H' g (:173-176) follows from
                 //   H' g = H g + (s rho) [ (1+q) s.g - (y^T H).g ] - (H y) rho s.g
                 // without reading H' back.  Sweep 2 rewrites the owned columns.
-                T yHc[kCols], Hyc[kCols], Hgc[kCols], yc[kCols], sc_[kCols], gc[kCols];
-                int kc[kCols];
-                bool inc[kCols];
-#pragma unroll
-                for (int h = 0; h < kCols; ++h) {
-                    inc[h] = lane + 32 * h < n;
-                    kc[h] = inc[h] ? lane + 32 * h : 0;   // safe index for lanes beyond n (results discarded)
-                    yHc[h] = Hyc[h] = Hgc[h] = T(0);
-                }
-                {
-                    const T* col[kCols];
-                    const T* row[kCols];
+                if constexpr (kVectorRows) {
+                    // Compile-time n: rows are 16-byte aligned (wide_ld_aligned) and the n-vectors are zero beyond n, so
+                    // everything that walks a ROW moves four values per shared-memory instruction and pairs of products
+                    // go through the packed FMA; only (y^T H)_c still reads a COLUMN one word at a time.  Sweep 2
+                    // rewrites H by rows: H'[c][:] = H[c][:] + (s_c rho) inner[:] - (H y)_c rho s[:].
+                    using V4 = typename Vec4<T>::type;
+                    using P2 = typename Vec2<T>::type;
+                    constexpr int kN = Obj::kParams, kChunks = (kN + 3) / 4;
+                    const V4* Y4 = reinterpret_cast<const V4*>(y);
+                    const V4* G4 = reinterpret_cast<const V4*>(g);
+                    T yHc[kCols], Hyc[kCols], Hgc[kCols], yc[kCols], sc_[kCols], gc[kCols];
+                    bool inc[kCols];
+                    int kc[kCols];
 #pragma unroll
                     for (int h = 0; h < kCols; ++h) {
-                        col[h] = H + kc[h];
-                        row[h] = H + kc[h] * ld;
+                        inc[h] = lane + 32 * h < kN;
+                        kc[h] = inc[h] ? lane + 32 * h : 0;
+                        yHc[h] = T(0);
                     }
-#pragma unroll 9
-                    for (int i = 0; i < n; ++i) {
-                        const T yi = y[i], gi = g[i];
+                    P2 hy[kCols], hg[kCols];
+#pragma unroll
+                    for (int h = 0; h < kCols; ++h) hy[h] = hg[h] = pk(T(0));
+#pragma unroll
+                    for (int ch = 0; ch < kChunks; ++ch) {
+                        const V4 y4 = Y4[ch], g4 = G4[ch];
+                        const T ye[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
                         for (int h = 0; h < kCols; ++h) {
-                            const T hc = *col[h], hr = row[h][i];
-                            col[h] += ld;
-                            yHc[h] = fma_t(yi, hc, yHc[h]);
-                            Hyc[h] = fma_t(hr, yi, Hyc[h]);
-                            Hgc[h] = fma_t(hr, gi, Hgc[h]);
+                            const V4 r4 = *reinterpret_cast<const V4*>(H + kc[h] * ld + 4 * ch);
+                            P2 ra, rb, ya, yb, ga, gb;
+                            ra.x = r4.x; ra.y = r4.y; rb.x = r4.z; rb.y = r4.w;
+                            ya.x = y4.x; ya.y = y4.y; yb.x = y4.z; yb.y = y4.w;
+                            ga.x = g4.x; ga.y = g4.y; gb.x = g4.z; gb.y = g4.w;
+                            hy[h] = pfma(rb, yb, pfma(ra, ya, hy[h]));
+                            hg[h] = pfma(rb, gb, pfma(ra, ga, hg[h]));
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (4 * ch + e < kN) yHc[h] = fma_t(ye[e], H[(4 * ch + e) * ld + kc[h]], yHc[h]);
                         }
                     }
-                }
-                T a0 = T(0), a1 = T(0), a2 = T(0);
-#pragma unroll
-                for (int h = 0; h < kCols; ++h) {
-                    yc[h] = inc[h] ? y[kc[h]] : T(0);
-                    sc_[h] = inc[h] ? s[kc[h]] : T(0);
-                    gc[h] = inc[h] ? g[kc[h]] : T(0);
-                    if (!inc[h]) { yHc[h] = T(0); Hyc[h] = T(0); Hgc[h] = T(0); }
-                    a0 = fma_t(yHc[h], yc[h], a0);
-                    a1 = fma_t(sc_[h], gc[h], a1);
-                    a2 = fma_t(yHc[h], gc[h], a2);
-                }
-                const T q = mul_rn(warp_allreduce(a0), rho);                       // y^T H y / (y^T s), :271-274
-                const T sg = warp_allreduce(a1);
-                const T yhg = warp_allreduce(a2);
-                const T onepq = add_rn(T(1), q);
-                const T dir = fma_t(onepq, sg, -yhg);
-                __syncwarp();  // sweep 1's reads of y are done before it is overwritten with the row constants
-#pragma unroll
-                for (int h = 0; h < kCols; ++h)
-                    if (inc[h]) {
-                        const int c = lane + 32 * h;
-                        d[c] = mul_rn(T(-1), fma_t(-Hyc[h] * rho, sg, fma_t(sc_[h] * rho, dir, Hgc[h])));
-                        y[c] = mul_rn(sc_[h], rho);       // row constants of sweep 2: s_i rho ...
-                        Hy[c] = -mul_rn(Hyc[h], rho);     // ... and -(H y)_i rho
-                    }
-                __syncwarp();
-                {
-                    T inner[kCols];
-                    T* col[kCols];
-                    int st[kCols];
+                    T a0 = T(0), a1 = T(0), a2 = T(0);
 #pragma unroll
                     for (int h = 0; h < kCols; ++h) {
-                        inner[h] = fma_t(sc_[h], onepq, -yHc[h]);                  // s_j (1+q) - (y^T H)_j
-                        // a lane without column h updates a scratch word of xt instead of predicating every store
-                        col[h] = inc[h] ? H + kc[h] : ws.xt + (32 * h + lane) % wide_vec(n);
-                        st[h] = inc[h] ? ld : 0;
+                        Hyc[h] = inc[h] ? hy[h].x + hy[h].y : T(0);
+                        Hgc[h] = inc[h] ? hg[h].x + hg[h].y : T(0);
+                        if (!inc[h]) yHc[h] = T(0);
+                        yc[h] = inc[h] ? y[kc[h]] : T(0);
+                        sc_[h] = inc[h] ? s[kc[h]] : T(0);
+                        gc[h] = inc[h] ? g[kc[h]] : T(0);
+                        a0 = fma_t(yHc[h], yc[h], a0);
+                        a1 = fma_t(sc_[h], gc[h], a1);
+                        a2 = fma_t(yHc[h], gc[h], a2);
                     }
-#pragma unroll 9
-                    for (int i = 0; i < n; ++i) {
-                        const T sri = y[i], nhr = Hy[i];
+                    const T q = mul_rn(warp_allreduce(a0), rho);                   // y^T H y / (y^T s), :271-274
+                    const T sg = warp_allreduce(a1);
+                    const T yhg = warp_allreduce(a2);
+                    const T onepq = add_rn(T(1), q);
+                    const T dir = fma_t(onepq, sg, -yhg);
+                    __syncwarp();  // sweep 1's reads of y are done before it is overwritten with `inner`
+                    T sri[kCols], nhr[kCols];
+#pragma unroll
+                    for (int h = 0; h < kCols; ++h) {
+                        sri[h] = mul_rn(sc_[h], rho);
+                        nhr[h] = -mul_rn(Hyc[h], rho);
+                        if (inc[h]) {
+                            const int c = lane + 32 * h;
+                            d[c] = mul_rn(T(-1), fma_t(nhr[h], sg, fma_t(sri[h], dir, Hgc[h])));
+                            y[c] = fma_t(sc_[h], onepq, -yHc[h]);   // inner_j = s_j (1+q) - (y^T H)_j
+                        }
+                    }
+                    __syncwarp();
+                    const V4* S4 = reinterpret_cast<const V4*>(s);
+#pragma unroll
+                    for (int h = 0; h < kCols; ++h) {
+                        if (inc[h]) {
+                            V4* row = reinterpret_cast<V4*>(H + kc[h] * ld);
+                            const P2 a2_ = pk(sri[h]), b2_ = pk(nhr[h]);
+#pragma unroll
+                            for (int ch = 0; ch < kChunks; ++ch) {
+                                const V4 in4 = Y4[ch], s4 = S4[ch];
+                                V4 r4 = row[ch];
+                                P2 ra, rb, ia, ib, sa, sb;
+                                ra.x = r4.x; ra.y = r4.y; rb.x = r4.z; rb.y = r4.w;
+                                ia.x = in4.x; ia.y = in4.y; ib.x = in4.z; ib.y = in4.w;
+                                sa.x = s4.x; sa.y = s4.y; sb.x = s4.z; sb.y = s4.w;
+                                ra = pfma(b2_, sa, pfma(a2_, ia, ra));
+                                rb = pfma(b2_, sb, pfma(a2_, ib, rb));
+                                r4.x = ra.x; r4.y = ra.y; r4.z = rb.x; r4.w = rb.y;
+                                row[ch] = r4;
+                            }
+                        }
+                    }
+                } else {
+                    T yHc[kCols], Hyc[kCols], Hgc[kCols], yc[kCols], sc_[kCols], gc[kCols];
+                    int kc[kCols];
+                    bool inc[kCols];
+#pragma unroll
+                    for (int h = 0; h < kCols; ++h) {
+                        inc[h] = lane + 32 * h < n;
+                        kc[h] = inc[h] ? lane + 32 * h : 0;   // safe index for lanes beyond n (results discarded)
+                        yHc[h] = Hyc[h] = Hgc[h] = T(0);
+                    }
+                    {
+                        const T* col[kCols];
+                        const T* row[kCols];
 #pragma unroll
                         for (int h = 0; h < kCols; ++h) {
-                            *col[h] = fma_t(nhr, sc_[h], fma_t(sri, inner[h], *col[h]));
-                            col[h] += st[h];
+                            col[h] = H + kc[h];
+                            row[h] = H + kc[h] * ld;
+                        }
+#pragma unroll 9
+                        for (int i = 0; i < n; ++i) {
+                            const T yi = y[i], gi = g[i];
+#pragma unroll
+                            for (int h = 0; h < kCols; ++h) {
+                                const T hc = *col[h], hr = row[h][i];
+                                col[h] += ld;
+                                yHc[h] = fma_t(yi, hc, yHc[h]);
+                                Hyc[h] = fma_t(hr, yi, Hyc[h]);
+                                Hgc[h] = fma_t(hr, gi, Hgc[h]);
+                            }
+                        }
+                    }
+                    T a0 = T(0), a1 = T(0), a2 = T(0);
+#pragma unroll
+                    for (int h = 0; h < kCols; ++h) {
+                        yc[h] = inc[h] ? y[kc[h]] : T(0);
+                        sc_[h] = inc[h] ? s[kc[h]] : T(0);
+                        gc[h] = inc[h] ? g[kc[h]] : T(0);
+                        if (!inc[h]) { yHc[h] = T(0); Hyc[h] = T(0); Hgc[h] = T(0); }
+                        a0 = fma_t(yHc[h], yc[h], a0);
+                        a1 = fma_t(sc_[h], gc[h], a1);
+                        a2 = fma_t(yHc[h], gc[h], a2);
+                    }
+                    const T q = mul_rn(warp_allreduce(a0), rho);                       // y^T H y / (y^T s), :271-274
+                    const T sg = warp_allreduce(a1);
+                    const T yhg = warp_allreduce(a2);
+                    const T onepq = add_rn(T(1), q);
+                    const T dir = fma_t(onepq, sg, -yhg);
+                    __syncwarp();  // sweep 1's reads of y are done before it is overwritten with the row constants
+#pragma unroll
+                    for (int h = 0; h < kCols; ++h)
+                        if (inc[h]) {
+                            const int c = lane + 32 * h;
+                            d[c] = mul_rn(T(-1), fma_t(-Hyc[h] * rho, sg, fma_t(sc_[h] * rho, dir, Hgc[h])));
+                            y[c] = mul_rn(sc_[h], rho);       // row constants of sweep 2: s_i rho ...
+                            Hy[c] = -mul_rn(Hyc[h], rho);     // ... and -(H y)_i rho
+                        }
+                    __syncwarp();
+                    {
+                        T inner[kCols];
+                        T* col[kCols];
+                        int st[kCols];
+#pragma unroll
+                        for (int h = 0; h < kCols; ++h) {
+                            inner[h] = fma_t(sc_[h], onepq, -yHc[h]);                  // s_j (1+q) - (y^T H)_j
+                            // a lane without column h updates a scratch word of xt instead of predicating every store
+                            col[h] = inc[h] ? H + kc[h] : ws.xt + (32 * h + lane) % wide_vec(n);
+                            st[h] = inc[h] ? ld : 0;
+                        }
+#pragma unroll 9
+                        for (int i = 0; i < n; ++i) {
+                            const T sri = y[i], nhr = Hy[i];
+#pragma unroll
+                            for (int h = 0; h < kCols; ++h) {
+                                *col[h] = fma_t(nhr, sc_[h], fma_t(sri, inner[h], *col[h]));
+                                col[h] += st[h];
+                            }
                         }
                     }
                 }

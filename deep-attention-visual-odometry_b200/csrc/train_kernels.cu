@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(kTrainWarpsPerCta * 32) train_forward_kernel(c
     obj.init();
     WideWorkspace<T> ws;
     ws.carve(mine + Obj::slab_bytes(p.N, p.V, p.has_w != 0), p.n);
-    for (int c = lane; c < 10 * wide_vec(p.n); c += 32) ws.x[c] = T(0);  // the n-vectors are contiguous from ws.x
+    for (size_t c = lane; c < WideWorkspace<T>::bytes(p.n) / sizeof(T); c += 32) ws.x[c] = T(0);  // vectors and H are contiguous from ws.x
     __syncwarp();
     for (;;) {
         unsigned b = 0;

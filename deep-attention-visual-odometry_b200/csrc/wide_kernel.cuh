@@ -31,6 +31,9 @@ __global__ void __launch_bounds__(kWideWarpsPerCta * 32) wide_problem_kernel(con
     obj.init();
     WideWorkspace<T> ws;
     ws.carve(mine + Obj::slab_bytes(p.N, p.V, p.has_w != 0), p.n);
+    // the n-vectors' tails and the padding columns of H are read by the vectorised sweeps (compile-time n): zero once
+    for (size_t c = lane; c < WideWorkspace<T>::bytes(p.n) / sizeof(T); c += 32) ws.x[c] = T(0);
+    __syncwarp();
     const int n = p.n;
     const unsigned warps_per_cta = blockDim.x >> 5;  // 2, or 1 when two slabs do not fit in shared memory
     const unsigned total_warps = gridDim.x * warps_per_cta;
