@@ -143,7 +143,10 @@ int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, con
         p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
         p.queue = static_cast<unsigned*>(workspace);
         if (p.zoom) return launch_train_forward<float>(p, TrainRecorder<float>{nullptr, nullptr, nullptr, nullptr, 0, 0.0f, 0, 0, 1}, s);
-        return DAVO_DISPATCH(solve, f32, p, s);
+        st = DAVO_DISPATCH(solve, f32, p, s);
+        if (st == DAVO_ERR_UNSUPPORTED && p.model == DAVO_MODEL_DISTORT10)   // N beyond the specialised kernels' slab
+            st = launch_train_forward<float>(p, TrainRecorder<float>{nullptr, nullptr, nullptr, nullptr, 0, 0.0f, 0, 0, 0}, s);
+        return st;
     }
     SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
     p.x0 = static_cast<const double*>(x0); p.x_out = static_cast<double*>(x_out);
@@ -151,7 +154,10 @@ int davo_solve_calibration(const davo_problem_desc* desc, const void* data0, con
     p.iters_out = iters_out; p.fevals_out = fevals_out; p.reason_out = reason_out;
     p.queue = static_cast<unsigned*>(workspace);
     if (p.zoom) return launch_train_forward<double>(p, TrainRecorder<double>{nullptr, nullptr, nullptr, nullptr, 0, 0.0f, 0, 0, 1}, s);
-    return DAVO_DISPATCH(solve, f64, p, s);
+    st = DAVO_DISPATCH(solve, f64, p, s);
+    if (st == DAVO_ERR_UNSUPPORTED && p.model == DAVO_MODEL_DISTORT10)
+        st = launch_train_forward<double>(p, TrainRecorder<double>{nullptr, nullptr, nullptr, nullptr, 0, 0.0f, 0, 0, 0}, s);
+    return st;
 }
 
 int davo_solve_training(const davo_problem_desc* desc, const davo_training_desc* train, const void* data0,
@@ -229,12 +235,16 @@ int davo_eval_cost_grad(const davo_problem_desc* desc, const void* data0, const 
         SolveParams<float> p = make_params<float>(desc, data0, data1, weights);
         p.x0 = static_cast<const float*>(x); p.cost_out = static_cast<float*>(cost);
         p.x_out = static_cast<float*>(grad);
-        return DAVO_DISPATCH(eval, f32, p, s);
+        st = DAVO_DISPATCH(eval, f32, p, s);
+        if (st == DAVO_ERR_UNSUPPORTED && p.model == DAVO_MODEL_DISTORT10) st = launch_eval_generic<float>(p, s);
+        return st;
     }
     SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
     p.x0 = static_cast<const double*>(x); p.cost_out = static_cast<double*>(cost);
     p.x_out = static_cast<double*>(grad);
-    return DAVO_DISPATCH(eval, f64, p, s);
+    st = DAVO_DISPATCH(eval, f64, p, s);
+    if (st == DAVO_ERR_UNSUPPORTED && p.model == DAVO_MODEL_DISTORT10) st = launch_eval_generic<double>(p, s);
+    return st;
 }
 
 int davo_line_search(const davo_problem_desc* desc, const void* data0, const void* data1,
@@ -252,14 +262,18 @@ int davo_line_search(const davo_problem_desc* desc, const void* data0, const voi
         p.base_cost = static_cast<const float*>(base_cost); p.base_grad = static_cast<const float*>(base_grad);
         p.alpha_out = static_cast<float*>(alpha_out); p.fevals_out = fevals_out;
         if (p.zoom) return launch_line_search_generic<float>(p, s);
-        return DAVO_DISPATCH(line_search, f32, p, s);
+        st = DAVO_DISPATCH(line_search, f32, p, s);
+        if (st == DAVO_ERR_UNSUPPORTED && p.model == DAVO_MODEL_DISTORT10) st = launch_line_search_generic<float>(p, s);
+        return st;
     }
     SolveParams<double> p = make_params<double>(desc, data0, data1, weights);
     p.x0 = static_cast<const double*>(x); p.dir = static_cast<const double*>(direction);
     p.base_cost = static_cast<const double*>(base_cost); p.base_grad = static_cast<const double*>(base_grad);
     p.alpha_out = static_cast<double*>(alpha_out); p.fevals_out = fevals_out;
     if (p.zoom) return launch_line_search_generic<double>(p, s);
-    return DAVO_DISPATCH(line_search, f64, p, s);
+    st = DAVO_DISPATCH(line_search, f64, p, s);
+    if (st == DAVO_ERR_UNSUPPORTED && p.model == DAVO_MODEL_DISTORT10) st = launch_line_search_generic<double>(p, s);
+    return st;
 }
 
 int davo_interpolate_alpha(int32_t dtype, int64_t k, const void* alpha_1, const void* alpha_2, const void* value_1,

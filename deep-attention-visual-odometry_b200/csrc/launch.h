@@ -40,6 +40,9 @@ int launch_train_backward(const SolveParams<double>& p, const BackwardParams<dou
 // davo_line_search with the secant zoom for the models whose default line search runs on the specialised kernels
 template <typename T>
 int launch_line_search_generic(const SolveParams<T>& p, cudaStream_t s);
+// DISTORT10 cost + gradient on the generic kernels (the route for N beyond the specialised kernels' shared-memory slab)
+template <typename T>
+int launch_eval_generic(const SolveParams<T>& p, cudaStream_t s);
 // interpolate_alpha forward (out != NULL) or backward (grad_out != NULL), elementwise
 template <typename T>
 int launch_interpolate_alpha(long long k, const T* a1, const T* a2, const T* v1, const T* v2, T* out, const T* grad_out,

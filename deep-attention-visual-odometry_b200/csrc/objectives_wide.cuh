@@ -11,30 +11,36 @@
 
 namespace davo {
 
-template <typename T>
+// kGlobal = true: the matches are read from global memory at every evaluation instead of being staged into shared
+// memory — the route for problems whose N does not fit a warp's slab (N > ~14 000 in float32; the specialised kernels
+// stop at ~3 500): slower per evaluation (L2 instead of shared memory), but no N is refused.
+template <typename T, bool kGlobal = false>
 struct Distort10WideObjective {
     using V4 = typename Vec4<T>::type;
     static constexpr int kParams = 0;
     const SolveParams<T>& p;
-    V4* matches;   // [N] staged {a, b, u*, v*}
-    T* weights;    // [N] (only if p.has_w)
+    const V4* matches;   // [N] staged {a, b, u*, v*}
+    const T* weights;    // [N] (only if p.has_w)
+    V4* slab_matches;
+    T* slab_weights;
     uint64_t* bar;
     unsigned parity;
     int lane;
 
     __host__ __device__ static size_t data_bytes(int N, bool has_w) {
+        if (kGlobal) return 0;
         size_t b = sizeof(V4) * (size_t)N + (has_w ? sizeof(T) * (size_t)N : 0);
         return (b + 127) & ~size_t(127);
     }
     __host__ __device__ static size_t slab_bytes(int N, int, bool has_w) { return data_bytes(N, has_w) + 16; }
 
     __device__ Distort10WideObjective(const SolveParams<T>& p_, unsigned char* slab, int lane_)
-        : p(p_), matches(reinterpret_cast<V4*>(slab)),
-          weights(reinterpret_cast<T*>(slab + sizeof(V4) * (size_t)p_.N)),
+        : p(p_), matches(nullptr), weights(nullptr), slab_matches(reinterpret_cast<V4*>(slab)),
+          slab_weights(reinterpret_cast<T*>(slab + sizeof(V4) * (size_t)(kGlobal ? 0 : p_.N))),
           bar(reinterpret_cast<uint64_t*>(slab + data_bytes(p_.N, p_.has_w != 0))), parity(0), lane(lane_) {}
 
     __device__ __forceinline__ void init() {
-        if (lane == 0) {
+        if (!kGlobal && lane == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
         }
@@ -43,18 +49,25 @@ struct Distort10WideObjective {
 
     __device__ __forceinline__ void bind(int b) {
         __syncwarp();
+        if (kGlobal) {
+            matches = reinterpret_cast<const V4*>(p.data0) + (size_t)b * p.N;
+            weights = p.has_w ? p.w + (size_t)b * p.N : nullptr;
+            return;
+        }
         if (p.N > 0) {
             if (lane == 0) {
                 fence_proxy_async();
                 const unsigned bytes = (unsigned)(sizeof(V4) * (size_t)p.N);
                 mbar_expect_tx(bar, bytes);
-                tma_load_1d(matches, p.data0 + (size_t)b * p.N * 4, bytes, bar);
+                tma_load_1d(slab_matches, p.data0 + (size_t)b * p.N * 4, bytes, bar);
             }
             if (p.has_w)
-                for (int i = lane; i < p.N; i += 32) weights[i] = p.w[(size_t)b * p.N + i];
+                for (int i = lane; i < p.N; i += 32) slab_weights[i] = p.w[(size_t)b * p.N + i];
             mbar_wait(bar, parity);
             parity ^= 1u;
         }
+        matches = slab_matches;
+        weights = slab_weights;
         __syncwarp();
     }
 
@@ -99,9 +112,9 @@ struct DataGradient {
 // 2 x 10 Jacobian of (u', v') at match i (camera_model/distorted_camera_model.py:59-86 differentiated; SURVEY.md
 // Appendix C).  out: this problem's [N, 2] row block, owned by the calling warp.
 template <typename T>
-struct DataGradient<Distort10WideObjective<T>, T> {
+struct DataGradient<Distort10WideObjective<T, false>, T> {
     static constexpr bool kSupported = true;
-    __device__ static void accumulate(Distort10WideObjective<T>& obj, const T* th, const T* v, T* out, int lane) {
+    __device__ static void accumulate(Distort10WideObjective<T, false>& obj, const T* th, const T* v, T* out, int lane) {
         Intrinsics<T> I;
         I.load(th);
         const T vcx = v[DAVO_CX], vcy = v[DAVO_CY], vk1 = v[DAVO_K1], vk2 = v[DAVO_K2], vk3 = v[DAVO_K3],

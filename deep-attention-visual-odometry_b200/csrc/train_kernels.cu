@@ -129,7 +129,11 @@ static bool analytic_model(int model) { return model >= DAVO_MODEL_SPHERE && mod
 
 template <typename T>
 int launch_train_forward(const SolveParams<T>& p, const TrainRecorder<T>& rec, cudaStream_t s) {
-    if (p.model == DAVO_MODEL_DISTORT10) return launch_train_forward_t<T, Distort10WideObjective<T>, 2>(p, rec, s);
+    if (p.model == DAVO_MODEL_DISTORT10) {
+        const int st = launch_train_forward_t<T, Distort10WideObjective<T>, 2>(p, rec, s);
+        if (st != DAVO_ERR_UNSUPPORTED) return st;  // N too large for a shared-memory slab: read the matches from global
+        return launch_train_forward_t<T, Distort10WideObjective<T, true>, 2>(p, rec, s);
+    }
     if (p.model == DAVO_MODEL_JOINT) {
         if (p.V < 1 || p.V > kMaxViews) return DAVO_ERR_UNSUPPORTED;
         return launch_train_forward_t<T, JointObjective<T>, 2>(p, rec, s);
@@ -154,8 +158,22 @@ int launch_train_backward(const SolveParams<double>& p, const BackwardParams<dou
 }
 
 template <typename T>
+int launch_eval_generic(const SolveParams<T>& p, cudaStream_t s) {
+    if (p.model != DAVO_MODEL_DISTORT10) return DAVO_ERR_UNSUPPORTED;
+    const int st = launch_wide<T, Distort10WideObjective<T>, WMode::kEval>(p, s);
+    if (st != DAVO_ERR_UNSUPPORTED) return st;
+    return launch_wide<T, Distort10WideObjective<T, true>, WMode::kEval>(p, s);
+}
+template int launch_eval_generic<float>(const SolveParams<float>&, cudaStream_t);
+template int launch_eval_generic<double>(const SolveParams<double>&, cudaStream_t);
+
+template <typename T>
 int launch_line_search_generic(const SolveParams<T>& p, cudaStream_t s) {
-    if (p.model == DAVO_MODEL_DISTORT10) return launch_wide<T, Distort10WideObjective<T>, WMode::kLineSearch>(p, s);
+    if (p.model == DAVO_MODEL_DISTORT10) {
+        const int st = launch_wide<T, Distort10WideObjective<T>, WMode::kLineSearch>(p, s);
+        if (st != DAVO_ERR_UNSUPPORTED) return st;
+        return launch_wide<T, Distort10WideObjective<T, true>, WMode::kLineSearch>(p, s);
+    }
     if (p.model == DAVO_MODEL_JOINT) {
         if (p.V < 1 || p.V > kMaxViews) return DAVO_ERR_UNSUPPORTED;
         return launch_wide<T, JointObjective<T>, WMode::kLineSearch>(p, s);

@@ -153,6 +153,9 @@ const char* davo_strerror(int status);
  *   fevals_out[B]     objective evaluations the reference would have made
  *   reason_out[B]     DAVO_REASON_* (may be NULL)
  * Output pointers are written for all B rows.
+ * DISTORT10 with N beyond the specialised kernels' shared-memory slab (N > ~3 500) runs on the generic one-warp-per-
+ * problem solver, and beyond ITS slab (~14 000 matches in float32) with the matches read from global memory at every
+ * evaluation: no N is refused.  The same fall-back applies to davo_eval_cost_grad and davo_line_search.
  * DISTORT10 without weights, large batches: two launches on `stream` — two problems per warp, then one CTA per
  * straggler (a problem past max(4096, 4 * max_iters) evaluations is abandoned by the first launch and solved again
  * from x0 by the second).  reason_out carries the hand-off flag between them (an internal value that never

@@ -137,3 +137,32 @@ def test_fused_initial_estimator_matches_torch_modules(views, points, hidden, B)
     assert float((again - got - 1.0).abs().max()) <= 1e-5
     # training mode and grad mode run the torch modules
     assert net.estimate(x[:64]).requires_grad
+
+
+# ---- N beyond the shared-memory slab: the matches are read from global memory (Distort10WideObjective<kGlobal>) -----
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_distortion_objective_with_very_many_matches(dt):
+    """The specialised kernels stage a problem's matches in a warp's shared-memory slab (N <= ~3 500); beyond that the
+    C-ABI falls back to the generic solver, and beyond ITS slab (~14 000 in float32) to reading the matches from global
+    memory: no N is refused.  Cost, gradient, line search and solve against the oracle."""
+    for N in (6000, 20000):
+        b = davo_b200.synthetic.make_distort10(6, N, seed=N, dtype=dt)
+        obj = _objective(b, TDT[np.dtype(dt)])
+        staged = c_oracle.stage(b.points_3d, b.obs, None)
+        f_ref, g_ref = c_oracle.eval_cost_grad("distort10", b.x0, staged, N=N)
+        f, g = obj.evaluate(torch.from_numpy(b.x0))
+        tol = 2e-4 if dt == np.float32 else 1e-11
+        assert np.allclose(f.cpu().numpy(), f_ref, rtol=tol) and np.allclose(g.cpu().numpy(), g_ref, rtol=tol, atol=tol * np.abs(g_ref).max())
+        thr = 1e-5 * N / 256 if dt == np.float32 else 1e-10 * N / 256
+        want = c_oracle.solve("distort10", b.x0, staged, N=N, error_threshold=thr)
+        got = davo_b200.BFGSSolver(error_threshold=thr).eval()(torch.from_numpy(b.x0), obj, return_info=True)
+        assert bool(got.converged.all()) and want["converged"].all()
+        assert np.allclose(got.parameters.numpy(), want["x"], rtol=2e-2 if dt == np.float32 else 1e-6, atol=2e-3 if dt == np.float32 else 1e-7)
+        if dt == np.float64:
+            assert np.array_equal(got.iterations.numpy(), want["iters"])
+            d = -g_ref
+            a_ref, p_ref = c_oracle.line_search("distort10", b.x0, d, f_ref, g_ref, staged, N=N, strong=True)
+            a, pr = davo_b200.line_search_wolfe_conditions(torch.from_numpy(b.x0), torch.from_numpy(d), torch.from_numpy(f_ref),
+                                                           torch.from_numpy(g_ref), obj, strong=True, return_probes=True)
+            assert np.array_equal(pr.numpy(), p_ref) and np.allclose(a.numpy(), a_ref, rtol=1e-9)
