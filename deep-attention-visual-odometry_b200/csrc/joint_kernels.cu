@@ -13,6 +13,7 @@ namespace davo {
 template <typename T, WMode kMode>
 static int launch_joint(const SolveParams<T>& p, cudaStream_t stream) {
     if (p.V < 1 || p.V > kMaxViews) return DAVO_ERR_UNSUPPORTED;
+    if (p.n > 64) return launch_wide<T, JointObjective<T>, kMode, 4>(p, stream);   // 10 .. 19 views
     return launch_wide<T, JointObjective<T>, kMode>(p, stream);
 }
 
@@ -82,7 +83,8 @@ static int launch_joint_cta(const SolveParams<T>& p, cudaStream_t stream) {
 // Warp w of a problem's CTA evaluates views w, w+W, ...
 template <typename T>
 static int launch_joint_solve(const SolveParams<T>& p, cudaStream_t s) {
-    if (p.V < 1 || p.V > kMaxViews || p.n > 64) return DAVO_ERR_UNSUPPORTED;
+    if (p.V < 1 || p.V > kMaxViews) return DAVO_ERR_UNSUPPORTED;
+    if (p.n > 64) return launch_joint<T, WMode::kSolve>(p, s);   // 10 .. 19 views: one warp per problem (wide solver)
     if (p.V >= DAVO_JOINT_WARPS) return launch_joint_cta<T, DAVO_JOINT_WARPS>(p, s);
     if (p.V >= 2) return launch_joint_cta<T, 2>(p, s);
     return launch_joint_cta<T, 1>(p, s);

@@ -14,7 +14,7 @@
 
 namespace davo {
 
-constexpr int kMaxViews = 9;  // n = 10 + 6 V <= 64
+constexpr int kMaxViews = 19;  // n = 10 + 6 V <= 124 (the wide solver's 128); the CTA-per-problem solve takes V <= 9
 
 template <typename T>
 struct JointObjective {
@@ -34,7 +34,7 @@ struct JointObjective {
         return (b + 127) & ~size_t(127);
     }
     __host__ __device__ static size_t slab_bytes(int N, int V, bool has_w) {
-        return data_bytes(N, V, has_w) + sizeof(T) * (16 + 64) + 16;
+        return data_bytes(N, V, has_w) + sizeof(T) * (16 + 128) + 16;
     }
 
     __device__ JointObjective(const SolveParams<T>& p_, unsigned char* slab, int lane_) : p(p_), parity(0), lane(lane_) {
@@ -44,7 +44,7 @@ struct JointObjective {
         unsigned char* tail = slab + data_bytes(p.N, p.V, p.has_w != 0);
         red = reinterpret_cast<T*>(tail);
         sc = red + 16;
-        bar = reinterpret_cast<uint64_t*>(sc + 64);
+        bar = reinterpret_cast<uint64_t*>(sc + 128);
     }
 
     __device__ __forceinline__ void init() {

@@ -136,6 +136,7 @@ int launch_train_forward(const SolveParams<T>& p, const TrainRecorder<T>& rec, c
     }
     if (p.model == DAVO_MODEL_JOINT) {
         if (p.V < 1 || p.V > kMaxViews) return DAVO_ERR_UNSUPPORTED;
+        if (p.n > 64) return launch_train_forward_t<T, JointObjective<T>, 4>(p, rec, s);
         return launch_train_forward_t<T, JointObjective<T>, 2>(p, rec, s);
     }
     if (p.model == DAVO_MODEL_ANGLE_BA) {
@@ -176,6 +177,7 @@ int launch_line_search_generic(const SolveParams<T>& p, cudaStream_t s) {
     }
     if (p.model == DAVO_MODEL_JOINT) {
         if (p.V < 1 || p.V > kMaxViews) return DAVO_ERR_UNSUPPORTED;
+        if (p.n > 64) return launch_wide<T, JointObjective<T>, WMode::kLineSearch, 4>(p, s);
         return launch_wide<T, JointObjective<T>, WMode::kLineSearch>(p, s);
     }
     if (p.model == DAVO_MODEL_ANGLE_BA) {

@@ -51,7 +51,8 @@ typedef enum davo_status {
  * DISTORT10: fit (cx,cy,k1,k2,k3,p1,p2,fx,s,fy) with the camera pose fixed.
  *            camera_model/distorted_camera_model.py:24-103 with columns 10..15 constant.
  *            data0 = staged matches [B,N,4] = {a=x'/z', b=y'/z', u*, v*}; data1 unused.
- * JOINT:     fit the 10 intrinsics + (rx,ry,rz,tx,ty,tz) for each of V views, n = 10+6V.
+ * JOINT:     fit the 10 intrinsics + (rx,ry,rz,tx,ty,tz) for each of V views, n = 10+6V, V <= 19
+ *            (up to 9 views: one CTA per problem; 10 .. 19: one warp per problem).
  *            data0 = world points [B,N,3] (shared by the V views);
  *            data1 = observations [B,V,N,2].
  * The analytic models restate tests/autograd_solvers/reference_functions.py:20-62 and

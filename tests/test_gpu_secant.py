@@ -166,3 +166,23 @@ def test_distortion_objective_with_very_many_matches(dt):
             a, pr = davo_b200.line_search_wolfe_conditions(torch.from_numpy(b.x0), torch.from_numpy(d), torch.from_numpy(f_ref),
                                                            torch.from_numpy(g_ref), obj, strong=True, return_probes=True)
             assert np.array_equal(pr.numpy(), p_ref) and np.allclose(a.numpy(), a_ref, rtol=1e-9)
+
+
+def test_joint_objective_with_more_than_nine_views():
+    """n = 10 + 6 V > 64: the CTA-per-problem solve stops at 9 views; 10 .. 19 views run on the one-warp-per-problem
+    wide solver with four components per lane.  Cost, gradient and solve against the oracle."""
+    b = davo_b200.synthetic.make_joint(24, 40, 12, seed=77, dtype=np.float64)
+    assert b.x0.shape[1] == 82
+    obj = _objective(b, torch.float64)
+    okw = dict(data0=b.points_3d, data1=b.obs, N=b.N, V=b.views)
+    f_ref, g_ref = c_oracle.eval_cost_grad("joint", b.x0, **okw)
+    f, g = obj.evaluate(torch.from_numpy(b.x0))
+    assert np.allclose(f.cpu().numpy(), f_ref, rtol=1e-11) and np.allclose(g.cpu().numpy(), g_ref, rtol=1e-9, atol=1e-11 * np.abs(g_ref).max())
+    want = c_oracle.solve("joint", b.x0, b.points_3d, b.obs, N=b.N, V=b.views, error_threshold=1e-10, iterations=300)
+    got = davo_b200.BFGSSolver(error_threshold=1e-10, iterations=300).eval()(torch.from_numpy(b.x0), obj, return_info=True)
+    same = got.iterations.numpy() == want["iters"]
+    assert same.mean() >= 0.9
+    assert np.allclose(got.parameters.numpy()[same], want["x"][same], rtol=1e-6, atol=1e-8)
+    with pytest.raises(NotImplementedError):
+        big = davo_b200.synthetic.make_joint(2, 8, 20, seed=1, dtype=np.float64)   # n = 130 > 128
+        davo_b200.BFGSSolver().eval()(torch.from_numpy(big.x0), _objective(big, torch.float64))
