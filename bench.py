@@ -515,6 +515,40 @@ def main():
                            "scaling": "strong" if cfg == "cfg5" else "weak", "n_gpus": world,
                            "l2": r["timing"]["l2"]}
 
+    # ---- the fused initial-guess network: one tcgen05 kernel in front of the solve -------------
+    if side and world == 1:
+        net = davo_b200.CalibrationNetwork(4, 8).to(dev).eval()
+        rows = 65536
+        xin = torch.randn(rows, 64, device=dev)
+
+        def timed(fn, reps=20):
+            for _ in range(3):
+                fn(xin)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn(xin)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        with torch.no_grad():
+            fused_ms = timed(net.estimate)
+            modules_ms = timed(net.initial_estimator)
+        flop = rows * 2.0 * (64 * 256 + 256 * 256 + 256 * 45)
+        tensor_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0   # dense TF32 is half the bf16 rate
+        side["initial_guess_mlp"] = {
+            "workload": "CalibrationNetwork.initial_estimator in eval mode, 65536 rows, 64-256-256-45 "
+                        "(Linear-GELU-BatchNorm x2 + Linear), float32",
+            "value": rows / (fused_ms * 1e-3), "unit": "rows/s", "ms_per_step": fused_ms,
+            "torch_modules_ms": modules_ms,
+            "roofline": {"bound": "tensor", "achieved": 3.0 * flop / (fused_ms * 1e-3) / 1e12, "peak": tensor_peak,
+                         "unit": "TFLOP/s", "frac": 3.0 * flop / (fused_ms * 1e-3) / 1e12 / tensor_peak,
+                         "note": "TF32 MMAs executed (3 per float32 product: hi/lo operand split); peak = measured "
+                                 "bf16 burst rate / 2; float32-equivalent rate = achieved / 3"}}
+        del net, xin
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -26,7 +26,16 @@ __device__ __forceinline__ void norm_and_inverse(double sq, double floor, double
     norm = norm < floor ? floor : norm;
     inv = rcp_rn(norm);
 }
+#ifndef DAVO_BA_EXACT_NORMS
+#define DAVO_BA_EXACT_NORMS 0  // 1: A/B builds round the float32 norms and reciprocals correctly, like float64
+#endif
 __device__ __forceinline__ void norm_and_inverse(float sq, float floor, float& norm, float& inv) {
+#if DAVO_BA_EXACT_NORMS
+    norm = sqrt_rn(sq);
+    norm = norm < floor ? floor : norm;
+    inv = rcp_rn(norm);
+    return;
+#endif
     const float f2 = floor * floor;
     const float v = sq < f2 ? f2 : sq;
     inv = rsqrtf(v);
