@@ -16,6 +16,14 @@
 namespace davo {
 
 constexpr int kReasonHandoff = 4;  // internal value of reason_out between the two launches of a DISTORT10 solve
+constexpr int kReasonClaimed = 6;  // internal: a CTA of the second launch has taken the problem
+// Words of the caller's 256-byte workspace used by the two launches of a DISTORT10 solve (all zeroed before the first):
+//   [0] problem queue of the first launch      [1] flag-scan position of the second launch
+//   [2] hand-offs reserved by the first launch  [3] hand-off tickets taken by the second launch
+//   [4] warps of the first launch that have exited
+//   [5 ..] the hand-off list: problem index + 1 (0 = not published yet)
+constexpr int kWsQueue = 0, kWsScan = 1, kWsReserved = 2, kWsTaken = 3, kWsExited = 4, kWsList = 5;
+constexpr int kHandoffList = DAVO_WORKSPACE_BYTES / 4 - kWsList;
 constexpr int kSlots = 16;  // distributed-vector width of the warp-per-problem solver (n <= 16)
 constexpr unsigned kFull = 0xffffffffu;
 // Per-warp shared-memory scratch of the warp-per-problem solver: 32 rows x kRedPitch words.  Cross-lane sums go

@@ -188,15 +188,16 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
     // fewer than ~3 problems per resident half: the batch cannot keep two problems per warp busy and a problem's
     // latency matters more than the instruction count (the streamed host-input path solves 4K-problem chunks)
     if ((long long)p.B < 3 * 2 * kWarpsPerCta * (long long)per_sm * sms) return DAVO_ERR_UNSUPPORTED;
-    if (cudaMemsetAsync(p.queue, 0, 2 * sizeof(unsigned), stream) != cudaSuccess) return DAVO_ERR_CUDA;
+    if (cudaMemsetAsync(p.queue, 0, DAVO_WORKSPACE_BYTES, stream) != cudaSuccess) return DAVO_ERR_CUDA;
     kernel<<<(unsigned)grid, kWarpsPerCta * 32, smem, stream>>>(p);
     count_launch();
     if (cudaGetLastError() != cudaSuccess) return DAVO_ERR_CUDA;
     if (p.eval_cap == 0) return DAVO_OK;
     SolveParams<T> p2 = p_in;
-    p2.queue = p.queue + 1;
-    p2.eval_cap = 0;
+    p2.queue = p.queue;
+    p2.eval_cap = (int)(grid * kWarpsPerCta);   // warps of the first launch: the second waits for that many exits
 #if DAVO_RESOLVE_WARP
+    p2.queue = p.queue + kWsScan;
     return launch_warp_kernel<T, 10, Distort10Objective<T, false>, Mode::kResolve>(p2, stream);
 #else
     return launch_resolve_cta<T>(p2, stream);
@@ -213,11 +214,27 @@ static int launch_half_kernel(const SolveParams<T>& p_in, cudaStream_t stream) {
 // of re-solve at 4 x 4 x 1, ~10 ms from 16 trial points per round up (tools/straggler_probe.py).
 #define DAVO_RESOLVE_WARPS 1
 #endif
+#ifndef DAVO_RESOLVE_CTAS
+#define DAVO_RESOLVE_CTAS 16   // CTAs of the early (programmatic dependent) straggler launch
+#endif
 constexpr int kResolveWarps = DAVO_RESOLVE_WARPS;   // warps that share one evaluation
 constexpr int kResolveGroups = DAVO_SPEC_PROBES;    // groups of kResolveWarps warps: trial points per line-search round
 constexpr int kResolveCtaWarps = kResolveWarps * kResolveGroups;
 
-template <typename T>
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+
+// The straggler launches of a DISTORT10 solve.
+// kEarly = true: a PROGRAMMATIC DEPENDENT launch of a few CTAs (DAVO_RESOLVE_CTAS).  They become resident as the first
+// launch's warps run out of problems (its tail); CTA t waits (sleeping) for hand-off t of the workspace's list and
+// solves it while the first launch is still finishing its last problems — the longest stragglers are handed off long
+// before that — or leaves when every warp of the first launch has exited without publishing a t-th hand-off.
+// kEarly = false: the plain stream-ordered launch behind it, a full grid that scans every flag and solves whatever is
+// still marked (hand-offs beyond the early CTAs): normally nothing, 17 us.
+// Only DAVO_RESOLVE_CTAS early CTAs because each holds three of an SM's four first-launch slots while it waits: with one
+// per SM the next batch's first launch (bench.py keeps two batches in flight) could not start in the slots the tail
+// frees (config 2: 3.91 ms per batch against 3.67 with 16).  Which CTA solves a problem does not matter: same route,
+// same bits (tools/cfg4_digest.py prints the same digest as the single stream-ordered launch).
+template <typename T, bool kEarly>
 __global__ void __launch_bounds__(32 * kResolveCtaWarps, 1) resolve_cta_kernel(const SolveParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem[];
     using Obj = Distort10CtaObjective<T, kResolveWarps, kResolveGroups>;
@@ -226,19 +243,52 @@ __global__ void __launch_bounds__(32 * kResolveCtaWarps, 1) resolve_cta_kernel(c
     ws.carve(smem + data, p.n, kResolveCtaWarps);
     unsigned char* tail = smem + data + CtaWorkspace<T>::bytes(p.n, kResolveCtaWarps);
     uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
-    volatile unsigned* slot = reinterpret_cast<volatile unsigned*>(tail + 16);  // [0] chunk base, [1] flag mask
+    volatile unsigned* slot = reinterpret_cast<volatile unsigned*>(tail + 16);  // [0] problem / chunk base, [1] flag mask
     Obj obj(p, smem, ws.red, bar);
     obj.init();
     const int lane = threadIdx.x & 31;
+    int* flags = p.reason_out;
+    if (kEarly) {
+        const unsigned first_warps = (unsigned)p.eval_cap;
+        constexpr unsigned kNone = 0xffffffffu;
+        constexpr unsigned kWatchdog = 1u << 22;   // polls of ~0.3 us: about a second, then leave it to the scan
+        if (threadIdx.x == 0) {
+            unsigned prob = kNone;
+            const unsigned t = blockIdx.x;
+            if (t < (unsigned)kHandoffList) {
+                for (unsigned spins = 0; spins < kWatchdog; ++spins) {
+                    unsigned v = ld_volatile_u32(p.queue + kWsList + t);
+                    if (v) { prob = v - 1u; break; }
+                    if (ld_volatile_u32(p.queue + kWsExited) >= first_warps) {   // every hand-off has been published
+                        __threadfence();
+                        v = ld_volatile_u32(p.queue + kWsList + t);
+                        if (v) prob = v - 1u;
+                        break;
+                    }
+                    __nanosleep(256);
+                }
+            }
+            slot[0] = prob;
+        }
+        __syncthreads();
+        const unsigned prob = slot[0];
+        if (prob != kNone) {
+            obj.bind((int)prob);
+            solve_one_cta<T, kResolveCtaWarps>(obj, p, (int)prob, ws);   // rewrites the flag with the final reason
+        }
+        // this grid must not complete before the first launch has (the scan launch behind it is ordered after THIS
+        // grid only): block until the first launch has finished and flushed its results
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        return;
+    }
     for (;;) {
         // warp 0 pulls 32 problem indices and looks at their reason flags (normally none is set)
         if (threadIdx.x < 32) {
             unsigned base = 0;
-            if (lane == 0) base = atomicAdd(p.queue, 32u);
+            if (lane == 0) base = atomicAdd(p.queue + kWsScan, 32u);
             base = __shfl_sync(kFull, base, 0);
             const unsigned idx = base + lane;
-            const unsigned todo =
-                __ballot_sync(kFull, idx < (unsigned)p.B && p.reason_out[idx] == kReasonHandoff);
+            const unsigned todo = __ballot_sync(kFull, idx < (unsigned)p.B && flags[idx] == kReasonHandoff);
             if (lane == 0) {
                 slot[0] = base;
                 slot[1] = todo;
@@ -261,24 +311,40 @@ __global__ void __launch_bounds__(32 * kResolveCtaWarps, 1) resolve_cta_kernel(c
 template <typename T>
 static int launch_resolve_cta(const SolveParams<T>& p, cudaStream_t stream) {
     using Obj = Distort10CtaObjective<T, kResolveWarps, kResolveGroups>;
-    auto kernel = resolve_cta_kernel<T>;
+    auto early = resolve_cta_kernel<T, true>;
+    auto scan = resolve_cta_kernel<T, false>;
     const size_t smem = Obj::data_bytes(p.N, 1, false) + CtaWorkspace<T>::bytes(p.n, kResolveCtaWarps) + 32;
     int dev = 0, sms = 0, max_optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return DAVO_ERR_CUDA;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if (smem > (size_t)max_optin) return DAVO_ERR_UNSUPPORTED;
-    if (!ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem))
+    if (!ensure_dynamic_smem(reinterpret_cast<const void*>(early), smem) ||
+        !ensure_dynamic_smem(reinterpret_cast<const void*>(scan), smem))
         return DAVO_ERR_CUDA;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * kResolveCtaWarps, smem) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan, 32 * kResolveCtaWarps, smem) != cudaSuccess ||
         per_sm < 1)
         return DAVO_ERR_CUDA;
     long long grid = (long long)per_sm * sms;
     const long long need = ((long long)p.B + 31) / 32;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kernel<<<(unsigned)grid, 32 * kResolveCtaWarps, smem, stream>>>(p);
+    // the early CTAs: programmatic dependent launch (the first launch calls griddepcontrol.launch_dependents at its top);
+    // they synchronise with it through the workspace counters, not through griddepcontrol.wait
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(DAVO_RESOLVE_CTAS < kHandoffList ? DAVO_RESOLVE_CTAS : kHandoffList);
+    cfg.blockDim = dim3(32 * kResolveCtaWarps);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, early, p) == cudaSuccess) count_launch();
+    else (void)cudaGetLastError();   // no early start: the scan below solves every hand-off
+    scan<<<(unsigned)grid, 32 * kResolveCtaWarps, smem, stream>>>(p);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
 }

@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
         fence_mbar_init();
     }
     __syncwarp();
+    // The straggler launch behind this one is a programmatic dependent launch: its CTAs may take the slots this grid
+    // frees as its warps run out of problems, and start on the problems handed off so far (solve_kernels.cu).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const bool own = l < n;
     // ---- per-half scheduling state ----
@@ -339,7 +342,12 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
                     // iterations): its latency, not the batch's throughput, would set the launch time.  Hand it
                     // to the second launch, which gives it a whole warp.  The test depends on the problem's own
                     // trajectory only, so which problems are handed off is deterministic.
-                    if (l == 0) p.reason_out[b] = kReasonHandoff;
+                    if (l == 0) {
+                        p.reason_out[b] = kReasonHandoff;
+                        __threadfence();
+                        const unsigned slot = atomicAdd(p.queue + kWsReserved, 1u);   // publish to the second launch
+                        if (slot < (unsigned)kHandoffList) atomicExch(p.queue + kWsList + slot, (unsigned)b + 1u);
+                    }
                     have = false;
                     mode = kEvalFinal;
                 } else {
@@ -423,6 +431,10 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
                 mode = kEvalFinal;
             }
         }
+    }
+    if (lane == 0) {   // this warp is out of work: every hand-off it made is published before the count moves
+        __threadfence();
+        atomicAdd(p.queue + kWsExited, 1u);
     }
 }
 
