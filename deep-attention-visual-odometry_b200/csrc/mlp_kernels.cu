@@ -4,7 +4,8 @@
 // start parameters x0[B, P].  This is the one dense contraction on the path (64 -> 256 -> 256
 // -> 45 at 64K rows = 12 GFLOP), so it runs on the 5th-generation tensor cores:
 //
-//   * one CTA = one tile of 128 batch rows = 128 threads; thread t owns row t in every epilogue (TMEM lane t);
+//   * one CTA = one tile of 128 batch rows, 256 threads: threads t and t + 128 own row t (TMEM lane t) in every
+//     epilogue and split its columns (a warp may only touch the TMEM lane quarter (warp % 4));
 //   * tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = H (or P padded to 16), K = 8 per instruction, issued by one
 //     thread, accumulators in TMEM (512 columns: two H-wide accumulators that alternate between the layers);
 //   * full float32 accuracy from the TF32 pipe by operand splitting: x = hi + lo with hi = tf32(x) (round to nearest)
@@ -26,7 +27,8 @@
 
 namespace davo {
 
-constexpr int kMlpTile = 128;      // batch rows per tile = threads per CTA
+constexpr int kMlpTile = 128;      // batch rows per tile (= TMEM lanes)
+constexpr int kMlpThreads = 256;   // two threads per row: warps w and w + 4 share TMEM lane quarter w and split the columns
 constexpr int kMlpChunk = 64;      // K values per staged chunk (16 columns of 16 bytes)
 constexpr int kMlpMaxN = 256;      // widest layer output one MMA covers
 constexpr int kMlpTmemCols = 512;
@@ -150,22 +152,30 @@ struct MlpParams {
     float* out;
 };
 
-// shared memory: [W images: 2 x 16 x 256 x 16 B = 128 KB][A images: 2 x 16 x 128 x 16 B = 64 KB][barriers, TMEM slot]
-constexpr size_t kMlpWBytes = 2ull * (kMlpChunk / 4) * kMlpMaxN * 16;
-constexpr size_t kMlpABytes = 2ull * (kMlpChunk / 4) * kMlpTile * 16;
-constexpr size_t kMlpSmem = kMlpWBytes + kMlpABytes + 64;
+// One pipeline STEP = 32 K values (8 columns of 16 bytes) of one layer.  Shared memory holds two A buffers (hi and lo
+// image, 8 x 128 x 16 B each: 32 KB per buffer) and two W buffers (8 x 256 x 16 B per image: 64 KB per buffer): 192 KB.
+constexpr int kMlpStepCols = 8;
+constexpr size_t kMlpWBuf = 2ull * kMlpStepCols * kMlpMaxN * 16;
+constexpr size_t kMlpABuf = 2ull * kMlpStepCols * kMlpTile * 16;
+constexpr size_t kMlpSmem = 2 * kMlpWBuf + 2 * kMlpABuf + 64;
 
-__global__ void __launch_bounds__(kMlpTile, 1) mlp_forward_kernel(const MlpParams p) {
+// Software pipeline over the steps of a tile (2 + 8 + 8 at 64-256-256-45): while the tensor core runs step s - 1,
+// the threads write step s's A images (the previous layer's epilogue) into the other A buffer and the bulk copy of
+// step s's weight images lands in the other W buffer.  A buffer is reused two steps later, after the commit of the
+// MMAs that read it has arrived on that buffer's mbarrier; the first step of a layer also waits for the previous
+// layer's last MMAs (it reads their accumulator).
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    float4* Wsm = reinterpret_cast<float4*>(smem);
-    float4* Asm = reinterpret_cast<float4*>(smem + kMlpWBytes);
-    uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + kMlpWBytes + kMlpABytes);
-    uint64_t* bar_mma = bar_w + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+    unsigned char* Wbase = smem;
+    unsigned char* Abase = smem + 2 * kMlpWBuf;
+    uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + 2 * kMlpWBuf + 2 * kMlpABuf);   // [2]
+    uint64_t* bar_mma = bar_w + 2;                                                       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 4);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & (kMlpTile - 1), part = tid / kMlpTile;   // row of the tile, which half of a step's columns
     if (tid == 0) {
-        mbar_init(bar_w, 1);
-        mbar_init(bar_mma, 1);
+        mbar_init(bar_w, 1); mbar_init(bar_w + 1, 1);
+        mbar_init(bar_mma, 1); mbar_init(bar_mma + 1, 1);
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, kMlpTmemCols);
@@ -173,132 +183,123 @@ __global__ void __launch_bounds__(kMlpTile, 1) mlp_forward_kernel(const MlpParam
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    unsigned pw = 0, pm = 0;  // parities of the two barriers (tracked identically by every thread)
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    unsigned pw[2] = {0u, 0u}, pm[2] = {0u, 0u};   // barrier parities, tracked identically by every thread
+    bool pending[2] = {false, false};              // a commit on bar_mma[buf] has not been waited for yet
     const int Hp = mlp_pad_n(p.H), Pp = mlp_pad_n(p.P);
+    const int cols1 = p.K1 / 4, colsH = p.H / 4;
+    const int steps1 = (cols1 + kMlpStepCols - 1) / kMlpStepCols, stepsH = (colsH + kMlpStepCols - 1) / kMlpStepCols;
+    const int steps = steps1 + 2 * stepsH;
 
-    // One K chunk of one layer: the weight images arrive by bulk TMA while `fill_a` writes this tile's A images; one
-    // thread then issues 3 MMAs per K = 8 step (hi hi, hi lo, lo hi) and commits to bar_mma, which everyone waits on
-    // (the images and the accumulator columns the next step touches are free again after it).
-    auto run_chunk = [&](const float4* wimg, int Np, int cols, uint32_t d_col, bool first, auto&& fill_a) {
-        const uint32_t img_bytes = (uint32_t)cols * Np * 16;   // one image (hi or lo)
-        if (tid == 0) {
-            fence_proxy_async();
-            mbar_expect_tx(bar_w, 2 * img_bytes);
-            // both images are contiguous in the packed buffer; copy in pieces of <= 32 KB
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(wimg);
-            unsigned char* dst = reinterpret_cast<unsigned char*>(Wsm);
-            for (uint32_t off = 0; off < 2 * img_bytes; off += 32768) {
-                const uint32_t n = min(32768u, 2 * img_bytes - off);
-                tma_load_1d(dst + off, src + off, n, bar_w);
-            }
-        }
-        fill_a(cols);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(bar_w, pw);
+    auto wait_mma = [&](int buf) {
+        if (pending[buf]) {
+            mbar_wait(bar_mma + buf, pm[buf]);
+            pm[buf] ^= 1u;
+            pending[buf] = false;
             tc_fence_after();
-            const uint32_t idesc = umma_idesc_tf32(kMlpTile, Np);
-            const uint32_t a_hi = smem_u32(Asm), a_lo = a_hi + (uint32_t)cols * kMlpTile * 16;
-            const uint32_t b_hi = smem_u32(Wsm), b_lo = b_hi + img_bytes;
-            const uint32_t a_lbo = kMlpTile * 16, b_lbo = (uint32_t)Np * 16;
-            for (int s = 0; s < cols / 2; ++s) {
-                const uint64_t ah = umma_desc(a_hi + 2 * s * a_lbo, a_lbo, 128), al = umma_desc(a_lo + 2 * s * a_lbo, a_lbo, 128);
-                const uint64_t bh = umma_desc(b_hi + 2 * s * b_lbo, b_lbo, 128), bl = umma_desc(b_lo + 2 * s * b_lbo, b_lbo, 128);
-                mma_tf32(tmem + d_col, al, bh, idesc, (first && s == 0) ? 0u : 1u);
-                mma_tf32(tmem + d_col, ah, bl, idesc, 1u);
-                mma_tf32(tmem + d_col, ah, bh, idesc, 1u);
-            }
-            tc_commit(bar_mma);
         }
-        pw ^= 1u;
-        mbar_wait(bar_mma, pm);
-        pm ^= 1u;
-        tc_fence_after();
     };
-    // split one float4 of row `tid` into the hi / lo images at 16-byte column c
-    auto put_a = [&](int c, int cols, float4 v) {
+    // split one float4 of row `r` into the hi / lo images of an A buffer at 16-byte column c
+    auto put_a = [&](float4* A, int c, int cols, float4 v) {
         float4 hi, lo;
         split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
         split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
-        Asm[c * kMlpTile + tid] = hi;
-        Asm[(cols + c) * kMlpTile + tid] = lo;
+        A[c * kMlpTile + r] = hi;
+        A[(cols + c) * kMlpTile + r] = lo;
     };
-    // epilogue of a hidden layer for columns [j0, j0 + 4 cols): accumulator -> bias, GELU, folded BatchNorm -> A images
-    auto hidden_to_a = [&](uint32_t src_col, int j0, int cols, const float* b, const float* s, const float* t) {
-        for (int c0 = 0; c0 < cols; c0 += 8) {          // 32 accumulator columns per TMEM load
-            float v[32];
-            if (c0 + 8 <= cols) {
-                tmem_ld32(tmem + lane_base + src_col + j0 + 4 * c0, v);
-            } else {                                    // a 16-column tail (H is a multiple of 16)
-                float h[16];
-                tmem_ld16(tmem + lane_base + src_col + j0 + 4 * c0, h);
+    // epilogue of a hidden layer for the step's columns: accumulator -> bias, GELU, folded BatchNorm -> A images.
+    // The row's two threads take 4 columns of 16 bytes (16 accumulator columns) each.
+    auto hidden_to_a = [&](float4* A, uint32_t src_col, int j0, int cols, const float* b, const float* sc, const float* sh) {
+        const int c0 = 4 * part;
+        if (c0 < cols) {
+            float v[16];
+            tmem_ld16(tmem + lane_base + src_col + j0 + 4 * c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = h[i];
+            for (int q = 0; q < 4; ++q) {
+                float4 o;
+                float* op = &o.x;
 #pragma unroll
-                for (int i = 16; i < 32; ++i) v[i] = 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                if (c0 + q < cols) {
-                    float4 o;
-                    float* op = &o.x;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = j0 + 4 * (c0 + q) + e;
-                        const float z = v[4 * q + e] + __ldg(b + j);
-                        const float gl = 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));   // nn.GELU()
-                        op[e] = fmaf(gl, __ldg(s + j), __ldg(t + j));                              // BatchNorm1d (eval)
-                    }
-                    put_a(c0 + q, cols, o);
+                for (int e = 0; e < 4; ++e) {
+                    const int j = j0 + 4 * (c0 + q) + e;
+                    const float z = v[4 * q + e] + __ldg(b + j);
+                    const float gl = 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));   // nn.GELU()
+                    op[e] = fmaf(gl, __ldg(sc + j), __ldg(sh + j));                            // BatchNorm1d (eval)
                 }
+                put_a(A, c0 + q, cols, o);
             }
         }
     };
 
     const int tiles = (p.B + kMlpTile - 1) / kMlpTile;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const long long row = (long long)tile * kMlpTile + tid;
+        const long long row = (long long)tile * kMlpTile + r;
         const bool live = row < p.B;
-        // ---- layer 1: X W1^T -> accumulator 0 ------------------------------------------------------------
-        {
-            const int cols_total = p.K1 / 4;
-            const float4* wimg = p.w1;
-            for (int c0 = 0, chunk = 0; c0 < cols_total; c0 += kMlpChunk / 4, ++chunk) {
-                const int cols = min(kMlpChunk / 4, cols_total - c0);
-                run_chunk(wimg, Hp, cols, 0u, chunk == 0, [&](int cols_) {
-                    const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(live ? row : 0) * p.K1) + c0;
-                    for (int c = 0; c < cols_; ++c) put_a(c, cols_, live ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f));
-                });
-                wimg += 2 * (size_t)cols * Hp;
+        for (int s = 0; s < steps; ++s) {
+            const int buf = s & 1;
+            // ---- which layer, which columns ------------------------------------------------------------------
+            int layer, ls;   // layer 0..2, step within the layer
+            if (s < steps1) { layer = 0; ls = s; }
+            else if (s < steps1 + stepsH) { layer = 1; ls = s - steps1; }
+            else { layer = 2; ls = s - steps1 - stepsH; }
+            const int cols_total = layer == 0 ? cols1 : colsH;
+            const int c_first = ls * kMlpStepCols;
+            const int cols = min(kMlpStepCols, cols_total - c_first);
+            const int Np = layer == 2 ? Pp : Hp;
+            const float4* wl = layer == 0 ? p.w1 : (layer == 1 ? p.w2 : p.w3);
+            // packed layout: per 64-wide chunk [hi: cols_here x Np][lo: cols_here x Np] float4 (mlp_pack_weights_kernel)
+            const int chunk = c_first / (kMlpChunk / 4), c_in = c_first % (kMlpChunk / 4);
+            const int cols_here = min(kMlpChunk / 4, cols_total - chunk * (kMlpChunk / 4));
+            const float4* w_hi = wl + (size_t)chunk * 2 * (kMlpChunk / 4) * Np + (size_t)c_in * Np;
+            const float4* w_lo = w_hi + (size_t)cols_here * Np;
+            const uint32_t d_col = layer == 1 ? (uint32_t)kMlpMaxN : 0u;
+            float4* A = reinterpret_cast<float4*>(Abase + buf * kMlpABuf);
+            unsigned char* W = Wbase + buf * kMlpWBuf;
+            const uint32_t img_bytes = (uint32_t)cols * Np * 16;
+            // ---- the buffers of step s - 2 are free once its MMAs have completed -------------------------------
+            wait_mma(buf);
+            if (ls == 0 && layer > 0) wait_mma(buf ^ 1);   // the previous layer's accumulator is complete
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(bar_w + buf, 2 * img_bytes);
+                tma_load_1d(W, w_hi, img_bytes, bar_w + buf);
+                tma_load_1d(W + img_bytes, w_lo, img_bytes, bar_w + buf);
             }
-        }
-        // ---- layer 2: act1 W2^T -> accumulator 1 (columns Hp ..) -----------------------------------------
-        {
-            const int cols_total = p.H / 4;
-            const float4* wimg = p.w2;
-            for (int c0 = 0, chunk = 0; c0 < cols_total; c0 += kMlpChunk / 4, ++chunk) {
-                const int cols = min(kMlpChunk / 4, cols_total - c0);
-                run_chunk(wimg, Hp, cols, (uint32_t)kMlpMaxN, chunk == 0,
-                          [&](int cols_) { hidden_to_a(0u, 4 * c0, cols_, p.b1, p.s1, p.t1); });
-                wimg += 2 * (size_t)cols * Hp;
+            // ---- this step's A images -----------------------------------------------------------------------------
+            if (layer == 0) {
+                const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)(live ? row : 0) * p.K1) + c_first;
+                for (int c = part; c < cols; c += 2) put_a(A, c, cols, live ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f));
+            } else if (layer == 1) {
+                hidden_to_a(A, 0u, 4 * c_first, cols, p.b1, p.s1, p.t1);
+            } else {
+                hidden_to_a(A, (uint32_t)kMlpMaxN, 4 * c_first, cols, p.b2, p.s2, p.t2);
             }
-        }
-        // ---- layer 3: act2 W3^T -> accumulator 0 ----------------------------------------------------------
-        {
-            const int cols_total = p.H / 4;
-            const float4* wimg = p.w3;
-            for (int c0 = 0, chunk = 0; c0 < cols_total; c0 += kMlpChunk / 4, ++chunk) {
-                const int cols = min(kMlpChunk / 4, cols_total - c0);
-                run_chunk(wimg, Pp, cols, 0u, chunk == 0,
-                          [&](int cols_) { hidden_to_a((uint32_t)kMlpMaxN, 4 * c0, cols_, p.b2, p.s2, p.t2); });
-                wimg += 2 * (size_t)cols * Pp;
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            // ---- one thread issues the step's MMAs (3 per K = 8: lo hi, hi lo, hi hi) and commits ----------------
+            if (tid == 0) {
+                mbar_wait(bar_w + buf, pw[buf]);
+                tc_fence_after();
+                const uint32_t idesc = umma_idesc_tf32(kMlpTile, Np);
+                const uint32_t a_hi = smem_u32(A), a_lo = a_hi + (uint32_t)cols * kMlpTile * 16;
+                const uint32_t b_hi = smem_u32(W), b_lo = b_hi + img_bytes;
+                const uint32_t a_lbo = kMlpTile * 16, b_lbo = (uint32_t)Np * 16;
+                for (int k = 0; k < cols / 2; ++k) {
+                    const uint64_t ah = umma_desc(a_hi + 2 * k * a_lbo, a_lbo, 128), al = umma_desc(a_lo + 2 * k * a_lbo, a_lbo, 128);
+                    const uint64_t bh = umma_desc(b_hi + 2 * k * b_lbo, b_lbo, 128), bl = umma_desc(b_lo + 2 * k * b_lbo, b_lbo, 128);
+                    mma_tf32(tmem + d_col, al, bh, idesc, (ls == 0 && k == 0) ? 0u : 1u);
+                    mma_tf32(tmem + d_col, ah, bl, idesc, 1u);
+                    mma_tf32(tmem + d_col, ah, bh, idesc, 1u);
+                }
+                tc_commit(bar_mma + buf);
             }
+            pw[buf] ^= 1u;
+            pending[buf] = true;
         }
+        wait_mma(0);
+        wait_mma(1);
         // ---- output: accumulator 0 + bias -> x0[row, :] -----------------------------------------------------
-        for (int j0 = 0; j0 < Pp; j0 += 16) {
+        for (int j0 = 16 * part; j0 < Pp; j0 += 32) {
             float v[16];
             tmem_ld16(tmem + lane_base + j0, v);
             if (live) {
@@ -342,7 +343,7 @@ int launch_mlp_forward(int B, int K1, int H, int P, const float* x, const void* 
     if (!ensure_dynamic_smem(reinterpret_cast<const void*>(mlp_forward_kernel), kMlpSmem)) return DAVO_ERR_CUDA;
     const int tiles = (B + kMlpTile - 1) / kMlpTile;
     const int grid = tiles < sms ? tiles : sms;   // one CTA per SM (192 KB of shared memory, all 512 TMEM columns)
-    mlp_forward_kernel<<<grid, kMlpTile, kMlpSmem, s>>>(p);
+    mlp_forward_kernel<<<grid, kMlpThreads, kMlpSmem, s>>>(p);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? DAVO_OK : DAVO_ERR_CUDA;
 }
