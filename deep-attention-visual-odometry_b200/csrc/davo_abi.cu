@@ -334,7 +334,8 @@ int davo_mlp_forward(const davo_mlp_desc* desc, const void* x, const void* w1_pa
     if (!x || !w1_packed || !b1 || !scale1 || !shift1 || !w2_packed || !b2 || !scale2 || !shift2 || !w3_packed || !b3 ||
         !x0_out)
         return DAVO_ERR_NULL_POINTER;
-    if (!aligned16(x) || !aligned16(w1_packed) || !aligned16(w2_packed) || !aligned16(w3_packed))
+    if (!aligned16(x) || !aligned16(w1_packed) || !aligned16(w2_packed) || !aligned16(w3_packed) || !aligned16(b1) ||
+        !aligned16(scale1) || !aligned16(shift1) || !aligned16(b2) || !aligned16(scale2) || !aligned16(shift2))
         return DAVO_ERR_MISALIGNED;
     auto f = [](const void* q) { return static_cast<const float*>(q); };
     return launch_mlp_forward(desc->B, desc->in_features, desc->hidden, desc->out_features, f(x), w1_packed, f(b1),

@@ -212,18 +212,27 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
     auto hidden_to_a = [&](float4* A, uint32_t src_col, int j0, int cols, const float* b, const float* sc, const float* sh) {
         const int c0 = 4 * part;
         if (c0 < cols) {
+            // the 16 columns' bias, scale and shift: three runs of 16 consecutive floats, 64-byte aligned
+            const float4* b4 = reinterpret_cast<const float4*>(b + j0 + 4 * c0);
+            const float4* s4 = reinterpret_cast<const float4*>(sc + j0 + 4 * c0);
+            const float4* t4 = reinterpret_cast<const float4*>(sh + j0 + 4 * c0);
+            float4 bq[4], sq[4], tq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { bq[q] = __ldg(b4 + q); sq[q] = __ldg(s4 + q); tq[q] = __ldg(t4 + q); }
             float v[16];
             tmem_ld16(tmem + lane_base + src_col + j0 + 4 * c0, v);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float4 o;
                 float* op = &o.x;
+                const float* bp = &bq[q].x;
+                const float* sp = &sq[q].x;
+                const float* tp = &tq[q].x;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int j = j0 + 4 * (c0 + q) + e;
-                    const float z = v[4 * q + e] + __ldg(b + j);
+                    const float z = v[4 * q + e] + bp[e];
                     const float gl = 0.5f * z * (1.0f + erff(z * 0.70710678118654752440f));   // nn.GELU()
-                    op[e] = fmaf(gl, __ldg(sc + j), __ldg(sh + j));                            // BatchNorm1d (eval)
+                    op[e] = fmaf(gl, sp[e], tp[e]);                                            // BatchNorm1d (eval)
                 }
                 put_a(A, c0 + q, cols, o);
             }
