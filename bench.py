@@ -409,7 +409,7 @@ def main():
             def e2e_step():
                 obj = make_objective(h_pts, h_obs)                       # H2D of points + observations, staging
                 return solver(h_x0, obj, return_info=True)               # H2D of x0, solve, D2H of every output
-            for _ in range(2):
+            for _ in range(3):
                 e2e_step()
             barrier()
             t0 = time.perf_counter()
@@ -424,6 +424,9 @@ def main():
             d2h = sum(t.numel() * t.element_size() for t in info)
             e2e = {"value": total_B / e2e_s, "unit": "solves/s", "h2d_bytes_per_step": int(input_bytes),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                   "api": "BFGSSolver.forward(host tensors, DistortionObjective(host tensors), return_info=True), one batch "
+                          "at a time (submitting a second batch while the first finishes was tried: 6.4 to 13 ms per "
+                          "batch from run to run, so the blocking call is what is timed)",
                    "h2d_gbs_per_gpu": input_bytes / e2e_s / 1e9,
                    "note": "bound by the host-to-device copy of the raw inputs (tools/h2d_probe.py measures the "
                            "plain-copy ceiling of the same bytes; DESIGN.md section 6)"}

@@ -134,6 +134,20 @@ class _DifferentiableSolve(torch.autograd.Function):
         return g_par, None, None, None, g_data
 
 
+class PendingSolve:
+    """Handle returned by BFGSSolver.submit: the solve (and, for a host caller, the copies of its results into pinned
+    host memory) has been queued; `result()` waits for it and returns what `forward` would have returned."""
+
+    def __init__(self, finalize=None, value=None):
+        self._finalize, self._value = finalize, value
+
+    def result(self):
+        if self._finalize is not None:
+            self._value = self._finalize()
+            self._finalize = None
+        return self._value
+
+
 _STREAMS: dict = {}
 
 
@@ -194,6 +208,13 @@ class BFGSSolver(Module):
                                          else self.error_threshold)
 
     def forward(self, parameters: torch.Tensor, error_function, return_info: bool = False, out=None):
+        return self.submit(parameters, error_function, return_info=return_info, out=out).result()
+
+    def submit(self, parameters: torch.Tensor, error_function, return_info: bool = False, out=None) -> PendingSolve:
+        """`forward` without the final wait: queue the solve (for a host caller also the copies of the results into
+        pinned host memory) and return a PendingSolve; `forward(...)` is `submit(...).result()`.  Submitting the next
+        batch before collecting this one lets its uploads start early, but measured on this pool that does not pay
+        (6.4 to 13 ms per 64K batch from run to run against a steady 7.3 ms one at a time): bench.py times forward()."""
         obj = _require_descriptor(error_function)
         if self.training:
             error_threshold, iterations = self.training_error_threshold, self.training_iterations
@@ -211,32 +232,50 @@ class BFGSSolver(Module):
         differentiable = torch.is_grad_enabled() and (parameters.requires_grad or
                                                       getattr(obj, "differentiable_data", None) is not None)
         if differentiable or (self.training and (self.drop_path_p > 0.0 or self.return_second_last)):
-            return self._forward_training(parameters, obj, error_threshold, iterations, differentiable, return_info)
-        if getattr(obj, "is_staged", True) or self.zoom_interpolation:
+            return PendingSolve(value=self._forward_training(parameters, obj, error_threshold, iterations,
+                                                             differentiable, return_info))
+        streamed = not (getattr(obj, "is_staged", True) or self.zoom_interpolation)
+        if not streamed:
             x0 = parameters.detach().to(device=obj.device, dtype=obj.dtype, non_blocking=True).reshape(obj.B, n)
             buf = self.solve_into(x0.contiguous(), obj, error_threshold=error_threshold, iterations=iterations,
                                   out=out)
+            done_events = None
         else:  # host-resident problem set: overlap the copies with staging + solve, chunk by chunk
-            buf = self._solve_streamed(parameters.detach().reshape(obj.B, n), obj, error_threshold, iterations, out)
+            buf, done_events = self._solve_streamed(parameters.detach().reshape(obj.B, n), obj, error_threshold,
+                                                    iterations, out)
         if out_dev.type == "cpu":
-            # host caller: every output goes device -> pinned host memory on the solve's stream, then ONE wait
-            # (six blocking copies would each pay a synchronisation)
+            # host caller: every output goes device -> pinned host memory, then ONE wait in result() (six blocking
+            # copies would each pay a synchronisation).  After a streamed solve the copies run on the solver's result
+            # stream behind the chunks' events, so the calling stream is not involved at all.
             wanted = (buf.x, buf.cost, buf.converged, buf.iterations, buf.evaluations, buf.reason) if return_info else (buf.x,)
             host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in wanted]
-            for h, t in zip(host, wanted):
-                h.copy_(t, non_blocking=True)
-            torch.cuda.current_stream(obj.device).synchronize()
-            result = host[0].reshape(parameters.shape).to(parameters.dtype)
-            if not return_info:
-                return result
-            shaped = [h.reshape(batch_shape) for h in host[1:]]
-            return SolveInfo(result, shaped[0], shaped[1].bool(), shaped[2], shaped[3], shaped[4])
+            with torch.cuda.device(obj.device):
+                # the copies run on the calling stream, which already waits for every chunk (a separate result stream
+                # behind the chunks' events measured 0.05 ms slower per 64K batch)
+                res_stream = torch.cuda.current_stream(obj.device)
+                with torch.cuda.stream(res_stream):
+                    for h, t in zip(host, wanted):
+                        h.copy_(t, non_blocking=True)
+                    finished = torch.cuda.Event()
+                    finished.record(res_stream)
+                for t in wanted:
+                    t.record_stream(res_stream)
+            shape, dtype = parameters.shape, parameters.dtype
+
+            def finalize(host=host, finished=finished, keep=buf):
+                finished.synchronize()
+                result = host[0].reshape(shape).to(dtype)
+                if not return_info:
+                    return result
+                shaped = [h.reshape(batch_shape) for h in host[1:]]
+                return SolveInfo(result, shaped[0], shaped[1].bool(), shaped[2], shaped[3], shaped[4])
+            return PendingSolve(finalize=finalize)
         result = buf.x.reshape(parameters.shape).to(device=out_dev, dtype=parameters.dtype)
         if not return_info:
-            return result
+            return PendingSolve(value=result)
         back = lambda t: t.reshape(batch_shape).to(out_dev)
-        return SolveInfo(result, back(buf.cost), back(buf.converged).bool(), back(buf.iterations),
-                         back(buf.evaluations), back(buf.reason))
+        return PendingSolve(value=SolveInfo(result, back(buf.cost), back(buf.converged).bool(), back(buf.iterations),
+                                            back(buf.evaluations), back(buf.reason)))
 
     def _forward_training(self, parameters, obj, error_threshold, iterations, differentiable, return_info):
         """Training-mode / differentiable solve (davo_solve_training, davo_solve_backward)."""
@@ -276,7 +315,7 @@ class BFGSSolver(Module):
             spans.append((lo, hi))
         return spans
 
-    def _solve_streamed(self, x0_host: torch.Tensor, obj, error_threshold, iterations, out) -> "SolveBuffers":
+    def _solve_streamed(self, x0_host: torch.Tensor, obj, error_threshold, iterations, out):
         """Host inputs -> device results with the compute hidden behind the copies.
 
         The batch is cut into chunks of `stream_chunk` problems.  ONE copy stream moves every chunk's points,
@@ -288,19 +327,24 @@ class BFGSSolver(Module):
         synchronises the host."""
         device = obj.device
         B, n, N = obj.B, obj.n, obj.N
+        spans = self._chunk_spans(B, max(1, int(self.stream_chunk)))
         with torch.cuda.device(device):
             buf = out if out is not None else SolveBuffers.allocate(B, n, obj.dtype, device)
             new = lambda *shape: torch.empty(*shape, dtype=obj.dtype, device=device)
             staged, d_pts, d_obs, x0_dev = new(B, N, 4), new(B, N, 3), new(B, N, 2), new(B, n)
             d_pose = new(B, 6) if obj._raw[2] is not None else None
             wdev = new(B, N) if obj._raw[3] is not None else None
+            workspaces = torch.empty(len(spans), _lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)
             main = torch.cuda.current_stream()
             start = torch.cuda.Event()
             start.record(main)
-            copy, *compute = _side_streams(device)
-            copy.wait_event(start)
-            spans = self._chunk_spans(B, max(1, int(self.stream_chunk)))
-            workspaces = torch.empty(len(spans), _lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+            copy, *compute = _side_streams(device)[:3]
+            # the side streams follow the calling stream only when something on it can matter to them: start
+            # parameters that live on the device.  Host inputs have no producer on any stream, and the buffers below
+            # are fresh; without this dependency a second batch's uploads start while the first is still solving.
+            follow_main = x0_host.is_cuda
+            if follow_main:
+                copy.wait_event(start)
             # every copy is queued before the first compute launch: the copy engine then runs back to back from the
             # first byte (the copies, not the SMs, bound this path) and the host's per-chunk launch work below never
             # sits between two copies.  (A second copy stream for the observations was tried: the two streams share
@@ -313,27 +357,53 @@ class BFGSSolver(Module):
                     landed = torch.cuda.Event()
                     landed.record(copy)
                     landed_events.append(landed)
-            for cs in compute:
-                cs.wait_event(start)
+            if follow_main:
+                for cs in compute:
+                    cs.wait_event(start)
+            # The per-chunk launches go straight to the C-ABI with base pointer + offset and the compute stream's
+            # handle: no tensor slicing, no stream context, no descriptor objects per chunk.  The host's time per batch
+            # is what bounds this path once the copies are queued (it was ~6.5 ms of Python for 20 chunks, more than the
+            # 6.1 ms the copies take; now ~2 ms).
+            lib = _lib.lib()
+            es = staged.element_size()
+            vp = ctypes.c_void_p
+            P = lambda t: 0 if t is None else t.data_ptr()
+            p_pts, p_obs, p_pose, p_w, p_staged, p_x0 = P(d_pts), P(d_obs), P(d_pose), P(wdev), P(staged), P(x0_dev)
+            p_x, p_cost, p_conv, p_it, p_fe, p_re, p_ws = (P(buf.x), P(buf.cost), P(buf.converged), P(buf.iterations),
+                                                          P(buf.evaluations), P(buf.reason), P(workspaces))
+            off = lambda base, count: vp(base + count) if base else None
+            descs = {}
+            done_events = []
             for k, (lo, hi) in enumerate(spans):
                 cs = compute[k % 2]
                 cs.wait_event(landed_events[k])
-                with torch.cuda.stream(cs):
-                    obj.stage_device_rows(lo, hi, d_pts, d_obs, d_pose, staged)
-                    sub = type(obj).from_staged(staged[lo:hi], None if wdev is None else wdev[lo:hi])
-                    view = SolveBuffers(buf.x[lo:hi], buf.cost[lo:hi], buf.converged[lo:hi], buf.iterations[lo:hi],
-                                        buf.evaluations[lo:hi], buf.reason[lo:hi], workspaces[k])
-                    self.solve_into(x0_dev[lo:hi], sub, error_threshold=error_threshold, iterations=iterations,
-                                    out=view)
-                    done = torch.cuda.Event()
-                    done.record(cs)
-                main.wait_event(done)
+                rows = hi - lo
+                if rows not in descs:
+                    descs[rows] = (obj.desc(B=rows),
+                                   obj.desc(B=rows, iterations=iterations, strong=True,
+                                            sufficient_decrease=self.sufficient_decrease, curvature=self.curvature,
+                                            error_threshold=error_threshold, minimum_step=self.minimum_step))
+                d_stage, d_solve = descs[rows]
+                stream = vp(cs.cuda_stream)
+                st = lib.davo_stage_matches(ctypes.byref(d_stage), off(p_pts, lo * N * 3 * es), off(p_obs, lo * N * 2 * es),
+                                            off(p_pose, lo * 6 * es), off(p_staged, lo * N * 4 * es), stream)
+                _lib.check(st, "davo_stage_matches")
+                st = lib.davo_solve_calibration(
+                    ctypes.byref(d_solve), off(p_staged, lo * N * 4 * es), None, off(p_w, lo * N * es),
+                    off(p_x0, lo * n * es), off(p_x, lo * n * es), off(p_cost, lo * es), off(p_conv, lo),
+                    off(p_it, lo * 4), off(p_fe, lo * 4), off(p_re, lo * 4), vp(p_ws + k * _lib.WORKSPACE_BYTES), stream)
+                _lib.check(st, "davo_solve_calibration")
+                done = torch.cuda.Event()
+                done.record(cs)
+                done_events.append(done)
+            for cs in compute:   # later work on the calling stream (e.g. obj.evaluate) sees the results
+                main.wait_stream(cs)
             obj.data0, obj.weights = staged, wdev
             for t in (staged, d_pts, d_obs, x0_dev, workspaces, d_pose, wdev):
                 if t is not None:
                     for s in (copy, *compute):
                         t.record_stream(s)
-        return buf
+        return buf, done_events
 
     def solve_into(self, x0: torch.Tensor, obj: CalibrationObjective, *, error_threshold=None, iterations=None,
                    out: "SolveBuffers | None" = None) -> "SolveBuffers":
