@@ -223,6 +223,7 @@ def main():
                     help="arithmetic type (BASELINE asks for f32; the entry script itself trains in f64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=3, help="batches in flight in the throughput pass (streams)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="time the K steps one batch at a time on one stream (no second batch in flight)")
     ap.add_argument("--no-side-configs", action="store_true",
@@ -305,8 +306,9 @@ def main():
         # config 4's stragglers on a handful of SMs — overlaps the head of the next.  Only without the L2 flush
         # (its per-step events need the steps one after the other).
         pipelined = flush is None and not args.no_pipeline
-        slab2 = ResultSlab(B * world, batch.n, t_dt, world, dev) if pipelined else None
-        streams = [torch.cuda.Stream(device=dev) for _ in range(2)] if pipelined else None
+        n_fly = max(2, int(args.in_flight))
+        slabs = [slab] + [ResultSlab(B * world, batch.n, t_dt, world, dev) for _ in range(n_fly - 1)] if pipelined else [slab]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(n_fly)] if pipelined else None
 
         def make_objective(pts, obs):
             if batch.model == "distort10":
@@ -316,7 +318,7 @@ def main():
             return davo_b200.JointPoseObjective(pts, obs)
 
         def step(ev=None, which=0):
-            sl = slab if which == 0 else slab2
+            sl = slabs[which]
             if flush is not None:
                 flush.zero_()
             if ev:
@@ -360,9 +362,9 @@ def main():
             main_stream = torch.cuda.current_stream()
             for st in streams:                       # warm-up on the two streams themselves: their allocator pools
                 st.wait_stream(main_stream)          # and first launches are paid before the timed region
-            for k in range(2 * max(warm, 2)):
-                with torch.cuda.stream(streams[k % 2]):
-                    step(None, k % 2)
+            for k in range(n_fly * max(warm, 2)):
+                with torch.cuda.stream(streams[k % n_fly]):
+                    step(None, k % n_fly)
             for st in streams:
                 main_stream.wait_stream(st)
             barrier()
@@ -371,8 +373,8 @@ def main():
             for st in streams:
                 st.wait_stream(main_stream)
             for k in range(steps):
-                with torch.cuda.stream(streams[k % 2]):
-                    step(None, k % 2)
+                with torch.cuda.stream(streams[k % n_fly]):
+                    step(None, k % n_fly)
             for st in streams:
                 main_stream.wait_stream(st)
             t_end.record()
@@ -461,7 +463,7 @@ def main():
                                    f"outside the per-step events; inputs are {input_bytes / 1e6:.0f} MB per GPU)"),
                        "collective": "one all_gather_into_tensor of the solved records"
                        if world > 1 else "none (single GPU)",
-                       "pipeline": ("the K timed steps alternate between 2 CUDA streams (2 batches in flight): the tail of "
+                       "pipeline": (f"the K timed steps alternate between {n_fly} CUDA streams ({n_fly} batches in flight): the tail of "
                                     "one launch overlaps the head of the next; ms_per_step_sequential is the same K steps "
                                     "one batch at a time on one stream; value / ms_per_step are the faster schedule: "
                                     + used) if pipelined else "one batch at a time"},
@@ -484,7 +486,7 @@ def main():
                 "traffic": stage_traffic, "bytes_counted": "20 B read + 16 B written per match"},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
-        del d_pts, d_obs, d_x0, slab, slab2, out, flush
+        del d_pts, d_obs, d_x0, slab, slabs, out, flush
         torch.cuda.empty_cache()
         return res
 
