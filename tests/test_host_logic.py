@@ -51,3 +51,50 @@ def test_generators_are_reproducible_and_consistent():
     assert np.allclose(np.stack([up, vp], -1), d.obs, atol=1e-12)   # observations are the forward model at the truth
     with pytest.raises(ValueError):
         davo_b200.synthetic.make_angle_ba(2, 8, 1)
+
+
+def test_new_entry_points_fail_loudly_without_a_gpu():
+    """No CPU fallback anywhere: the round-2 surface (training solve, interpolate_alpha, the fused estimator) raises
+    DavoError on a box without a CUDA device instead of computing something else."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without a GPU")
+    from davo_b200 import _lib
+    with pytest.raises(_lib.DavoError):
+        davo_b200.interpolate_alpha(torch.zeros(3), torch.ones(3), torch.ones(3), -torch.ones(3))
+    with pytest.raises(_lib.DavoError):
+        davo_b200.AnalyticObjective("sphere", (2,), 3)
+    net = davo_b200.CalibrationNetwork(4, 8).eval()
+    x = torch.zeros(5, 64)
+    with torch.no_grad():
+        y = net.estimate(x)   # CPU tensors: the fused kernel does not apply, the torch modules run
+    assert y.shape == (5, 45)
+
+
+def test_descriptor_layouts_match_the_header():
+    """ctypes mirrors of the C structs (include/davo_b200.h): sizes and a few offsets."""
+    import ctypes
+    from davo_b200 import _lib
+    assert ctypes.sizeof(_lib.ProblemDesc) == 80 and _lib.ProblemDesc.zoom_interpolation.offset == 40
+    assert ctypes.sizeof(_lib.TrainingDesc) == 32 and _lib.TrainingDesc.drop_path_p.offset == 8
+    assert _lib.TrainingDesc.seed.offset == 16 and _lib.TrainingDesc.hvp_rel_step.offset == 24
+    assert ctypes.sizeof(_lib.MlpDesc) == 16
+    d = _lib.make_desc(4, 8, 1, 10, "distort10", __import__("torch").float32, zoom_interpolation=True)
+    assert d.zoom_interpolation == 1 and d.reserved0 == 0
+
+
+def test_drop_path_restatement_is_uniform_and_reproducible():
+    from oracle import train_oracle
+    u = np.array([train_oracle.drop_path_uniform(1234, b, k) for b in range(200) for k in range(20)])
+    assert u.min() >= 0.0 and u.max() < 1.0
+    assert abs(u.mean() - 0.5) < 0.03 and abs((u > 0.1).mean() - 0.9) < 0.02
+    assert train_oracle.drop_path_uniform(1234, 7, 3) == train_oracle.drop_path_uniform(1234, 7, 3)
+    assert train_oracle.drop_path_uniform(1234, 7, 3) != train_oracle.drop_path_uniform(1235, 7, 3)
+
+
+def test_pending_solve_handle():
+    h = davo_b200.PendingSolve(value=5)
+    assert h.result() == 5
+    calls = []
+    h = davo_b200.PendingSolve(finalize=lambda: calls.append(1) or 7)
+    assert h.result() == 7 and h.result() == 7 and calls == [1]   # finalised once
