@@ -230,7 +230,7 @@ def main():
                     help="time the K steps one batch at a time on one stream (no second batch in flight)")
     ap.add_argument("--no-side-configs", action="store_true",
                     help="skip the 'configs' object (cfg3, cfg4, bundle adjustment, cfg5 strong scaling)")
-    ap.add_argument("--side-steps", type=int, default=5, help="timed steps per side configuration")
+    ap.add_argument("--side-steps", type=int, default=12, help="timed steps per side configuration")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
