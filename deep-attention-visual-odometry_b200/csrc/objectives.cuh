@@ -82,6 +82,17 @@ __device__ __forceinline__ void match_cost_grad_unfused(const Intrinsics<T>& I, 
     acc[9] = add_rn(acc[9], mul_rn(gv, b));
 }
 
+// One match's weighted residual w * (u' - u*, v' - v*) alone (distorted_camera_model.py:59-86): d cost / d (u*, v*) is
+// -2 times it, which is what the backward pass of the differentiable solve differences (solver_train.cuh).
+template <typename T>
+__device__ __forceinline__ void match_residual(const Intrinsics<T>& I, T a, T b, T us, T vs, T w, T& ru, T& rv) {
+    const T u = fma_t(I.fx, a, I.s * b), v = I.fy * b;
+    const T uu = u * u, vv = v * v, uv = u * v, r2 = uu + vv;
+    const T rad = fma_t(r2, fma_t(r2, fma_t(r2, I.k3, I.k2), I.k1), T(1));
+    ru = w * (u * rad + T(2) * I.p1 * uv + I.p2 * (r2 + T(2) * uu) + I.cx - us);
+    rv = w * (v * rad + T(2) * I.p2 * uv + I.p1 * (r2 + T(2) * vv) + I.cy - vs);
+}
+
 // One match: residuals, squared error and the intrinsic-gradient accumulators.
 //   acc[0..9]  += d(cost/2)/d(cx,cy,k1,k2,k3,p1,p2,fx,s,fy)   (acc[5], acc[6] without their 2uv terms)
 //   acc[10]    += cost

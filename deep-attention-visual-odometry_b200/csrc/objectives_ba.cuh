@@ -45,8 +45,12 @@ __device__ __forceinline__ void norm_and_inverse(float sq, float floor, float& n
 
 // kV, kN > 0 fix the number of views / points at compile time (the entry script's configuration is 4 views x 8
 // points, camera_calibration_from_oracle_matches.py:34-35: loops unroll, index arithmetic folds); 0 = run time.
-template <typename T, int kV = 0, int kN = 0>
+// kDataGrad (the backward pass of the differentiable solve only, solver_train.cuh): while `dgrad` is set every
+// evaluation also adds dcoef * d error / d obs to dgrad[V,N,2] — pair i is always visited by the same lane.
+template <typename T, int kV = 0, int kN = 0, bool kDataGrad = false>
 struct AngleBAObjective {
+    T* dgrad = nullptr;
+    T dcoef = T(0);
     static constexpr int kRow = 9;  // odd pitch: consecutive rows start in different banks
     static constexpr int kParams = (kV > 0 && kN > 0) ? 3 + 3 * kN + 6 * (kV - 1) : 0;  // compile-time n (0: run time)
     const SolveParams<T>& p;
@@ -192,6 +196,10 @@ struct AngleBAObjective {
             gcx -= gh0;
             gcy -= gh1;
             gf += gh2;
+            if (kDataGrad && dgrad) {  // h = (u - cx, v - cy, .): d error / d (u, v) = (gh0, gh1)
+                dgrad[2 * i] += dcoef * gh0;
+                dgrad[2 * i + 1] += dcoef * gh1;
+            }
             T* row = contrib + kRow * i;
             if (m == 0) {
                 row[0] = g0; row[1] = g1; row[2] = g2;

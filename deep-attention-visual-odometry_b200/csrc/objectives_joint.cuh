@@ -16,9 +16,13 @@ namespace davo {
 
 constexpr int kMaxViews = 19;  // n = 10 + 6 V <= 124 (the wide solver's 128); the CTA-per-problem solve takes V <= 9
 
-template <typename T>
+// kDataGrad (the backward pass of the differentiable solve only, solver_train.cuh): while `dgrad` is set every
+// evaluation also adds dcoef * d cost / d obs to dgrad[V,N,2] — pair (view, i) is always visited by the same lane.
+template <typename T, bool kDataGrad = false>
 struct JointObjective {
     static constexpr int kParams = 0;  // n is a run-time value (wide_kernel.cuh)
+    T* dgrad = nullptr;
+    T dcoef = T(0);
     const SolveParams<T>& p;
     T* world;   // [N,3]
     T* obs;     // [V,N,2]
@@ -123,6 +127,13 @@ struct JointObjective {
                 T gu, gv;
                 if (p.has_w) match_cost_grad<T, true>(I, a, b, us, vs, wv[i], acc, gu, gv);
                 else         match_cost_grad<T, false>(I, a, b, us, vs, T(1), acc, gu, gv);
+                if (kDataGrad && dgrad) {  // d cost / d (u*, v*) = -2 w (residual)
+                    T ru, rv;
+                    match_residual(I, a, b, us, vs, p.has_w ? wv[i] : T(1), ru, rv);
+                    T* o = dgrad + 2 * ((size_t)v * N + i);
+                    o[0] -= T(2) * dcoef * ru;
+                    o[1] -= T(2) * dcoef * rv;
+                }
                 const T gA = gu * I.fx;
                 const T gB = fma_t(gu, I.s, gv * I.fy);
                 const T gx = gA * iz, gy = gB * iz;

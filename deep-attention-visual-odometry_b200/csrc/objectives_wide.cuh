@@ -99,13 +99,21 @@ struct Distort10WideObjective {
     }
 };
 
-// d loss / d (problem data) of the differentiable solve.  x_out depends on the data only through the gradients
-// g_k = grad f(x_k; data), so d loss / d data = sum_k d/d data [ g_k . gbar_k ] with gbar_k the adjoint of g_k in the
-// reverse sweep (solver_train.cuh).  Generic objectives: not provided.
+// d loss / d (problem data) of the differentiable solve: the observations of the camera objectives.  x_out depends on
+// the data only through the gradients g_k = grad f(x_k; data), so d loss / d data = sum_k d/d data [ g_k . gbar_k ]
+// with gbar_k the adjoint of g_k in the reverse sweep (solver_train.cuh) — by symmetry of the mixed second derivative,
+// the directional derivative of d f / d data along gbar_k.  Two ways to get it:
+//   analytic(): written out (DISTORT10);
+//   arm():      the objective's evaluator adds coef * d f / d data to `out` while armed; the four evaluations of the
+//               fourth-order difference that already produces the Hessian-vector product then give the directional
+//               derivative at no extra evaluation (JOINT, ANGLE_BA).
+// Generic objectives: not provided.
 template <typename Obj, typename T>
 struct DataGradient {
     static constexpr bool kSupported = false;
-    __device__ static void accumulate(Obj&, const T*, const T*, T*, int) {}
+    __device__ static int elements(const SolveParams<T>&) { return 0; }   // scalars per problem
+    __device__ static void analytic(Obj&, const T*, const T*, T*, int) {}
+    __device__ static void arm(Obj&, T*, T) {}
 };
 
 // DISTORT10, observations: f = sum w |proj_i(x) - obs_i|^2 gives d (g . v) / d obs_i = -2 w_i J_i v with J_i the
@@ -114,7 +122,9 @@ struct DataGradient {
 template <typename T>
 struct DataGradient<Distort10WideObjective<T, false>, T> {
     static constexpr bool kSupported = true;
-    __device__ static void accumulate(Distort10WideObjective<T, false>& obj, const T* th, const T* v, T* out, int lane) {
+    __device__ static int elements(const SolveParams<T>& p) { return 2 * p.N; }
+    __device__ static void arm(Distort10WideObjective<T, false>&, T*, T) {}
+    __device__ static void analytic(Distort10WideObjective<T, false>& obj, const T* th, const T* v, T* out, int lane) {
         Intrinsics<T> I;
         I.load(th);
         const T vcx = v[DAVO_CX], vcy = v[DAVO_CY], vk1 = v[DAVO_K1], vk2 = v[DAVO_K2], vk3 = v[DAVO_K3],

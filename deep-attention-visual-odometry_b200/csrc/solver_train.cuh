@@ -20,8 +20,27 @@
 #include "davo_common.cuh"
 #include "solver_wide.cuh"
 #include "objectives_wide.cuh"
+#include "objectives_joint.cuh"
+#include "objectives_ba.cuh"
 
 namespace davo {
+
+// JOINT and ANGLE_BA observations [V, N, 2]: taken from the evaluations of the Hessian-vector difference (see
+// DataGradient in objectives_wide.cuh).
+template <typename T>
+struct DataGradient<JointObjective<T, true>, T> {
+    static constexpr bool kSupported = true;
+    __device__ static int elements(const SolveParams<T>& p) { return 2 * p.V * p.N; }
+    __device__ static void analytic(JointObjective<T, true>&, const T*, const T*, T*, int) {}
+    __device__ static void arm(JointObjective<T, true>& obj, T* out, T coef) { obj.dgrad = out; obj.dcoef = coef; }
+};
+template <typename T>
+struct DataGradient<AngleBAObjective<T, 0, 0, true>, T> {
+    static constexpr bool kSupported = true;
+    __device__ static int elements(const SolveParams<T>& p) { return 2 * p.V * p.N; }
+    __device__ static void analytic(AngleBAObjective<T, 0, 0, true>&, const T*, const T*, T*, int) {}
+    __device__ static void arm(AngleBAObjective<T, 0, 0, true>& obj, T* out, T coef) { obj.dgrad = out; obj.dcoef = coef; }
+};
 
 template <typename T>
 struct BackwardWorkspace {
@@ -120,8 +139,10 @@ __device__ __forceinline__ void backward_one(Obj& obj, const SolveParams<T>& p, 
     const T* A = bp.traj_alpha + row0;
     __syncwarp();
     for (int c = lane; c < n; c += 32) xbar[c] = bp.grad_out[(size_t)b * n + c];
-    if (DataGradient<Obj, T>::kSupported && bp.grad_data)
-        for (int i = lane; i < 2 * p.N; i += 32) bp.grad_data[(size_t)b * p.N * 2 + i] = T(0);
+    using DG = DataGradient<Obj, T>;
+    T* dout = (DG::kSupported && bp.grad_data) ? bp.grad_data + (size_t)b * DG::elements(p) : nullptr;
+    if (dout)
+        for (int i = lane; i < DG::elements(p); i += 32) dout[i] = T(0);
     __syncwarp();
     if (K > 0) {
         // ---- (a) replay: H_k and d_k for every recorded step ----------------------------------------------
@@ -280,8 +301,7 @@ __device__ __forceinline__ void backward_one(Obj& obj, const SolveParams<T>& p, 
             for (int c = lane; c < n; c += 32) gk[c] = X[(size_t)k * n + c];   // gk now holds x_k
             for (int c = n + lane; c < wide_vec(n); c += 32) gk[c] = T(0);
             __syncwarp();
-            if (DataGradient<Obj, T>::kSupported && bp.grad_data)
-                DataGradient<Obj, T>::accumulate(obj, gk, gbar, bp.grad_data + (size_t)b * p.N * 2, lane);
+            if (dout) DG::analytic(obj, gk, gbar, dout, lane);
             const T nv = sqrt(dot(gbar, gbar, n, lane));
             if (nv > T(0) && isfinite(nv)) {
                 const T nx = sqrt(dot(gk, gk, n, lane));
@@ -289,18 +309,20 @@ __device__ __forceinline__ void backward_one(Obj& obj, const SolveParams<T>& p, 
                 for (int c = lane; c < n; c += 32) hacc[c] = T(0);
                 const T steps[4] = {T(2), T(1), T(-1), T(-2)};
                 const T coef[4] = {T(-1), T(8), T(-8), T(1)};
+                const T inv = T(1) / (T(12) * h);
 #pragma unroll 1
                 for (int e = 0; e < 4; ++e) {
                     __syncwarp();
                     for (int c = lane; c < n; c += 32) xt[c] = gk[c] + steps[e] * h * gbar[c];
                     for (int c = n + lane; c < wide_vec(n); c += 32) xt[c] = T(0);
                     __syncwarp();
+                    DG::arm(obj, dout, coef[e] * inv);   // the same difference gives d (g . gbar) / d data
                     obj.eval(xt, gt);
                     __syncwarp();
                     for (int c = lane; c < n; c += 32) hacc[c] += coef[e] * gt[c];
                 }
+                DG::arm(obj, nullptr, T(0));
                 __syncwarp();
-                const T inv = T(1) / (T(12) * h);
                 for (int c = lane; c < n; c += 32) xbar[c] += hacc[c] * inv;
             }
             __syncwarp();

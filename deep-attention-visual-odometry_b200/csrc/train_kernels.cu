@@ -151,9 +151,9 @@ int launch_train_backward(const SolveParams<double>& p, const BackwardParams<dou
     if (p.model == DAVO_MODEL_DISTORT10) return launch_train_backward_t<double, Distort10WideObjective<double>>(p, bp, s);
     if (p.model == DAVO_MODEL_JOINT) {
         if (p.V < 1 || p.V > kMaxViews) return DAVO_ERR_UNSUPPORTED;
-        return launch_train_backward_t<double, JointObjective<double>>(p, bp, s);
+        return launch_train_backward_t<double, JointObjective<double, true>>(p, bp, s);
     }
-    if (p.model == DAVO_MODEL_ANGLE_BA) return launch_train_backward_t<double, AngleBAObjective<double>>(p, bp, s);
+    if (p.model == DAVO_MODEL_ANGLE_BA) return launch_train_backward_t<double, AngleBAObjective<double, 0, 0, true>>(p, bp, s);
     if (analytic_model(p.model)) return launch_train_backward_t<double, AnalyticWideObjective<double>>(p, bp, s);
     return DAVO_ERR_UNSUPPORTED;
 }

@@ -241,6 +241,9 @@ class JointPoseObjective(CalibrationObjective):
             raise ValueError(f"observed_2d must be {tuple(batch_shape) + (V, N, 2)}, got {tuple(observed_2d.shape)}")
         super().__init__(batch_shape, 10 + 6 * V, N, dtype, device)
         self.views = V
+        # the differentiable solve also returns d loss / d observed_2d (davo_solve_backward, grad_data)
+        self.differentiable_data = observed_2d if observed_2d.requires_grad else None
+        points_3d, observed_2d = points_3d.detach(), observed_2d.detach()
         self.data0 = _to_device(points_3d, dtype, device).reshape(self.B, N, 3)
         self.data1 = _to_device(observed_2d, dtype, device).reshape(self.B, V, N, 2)
         self.weights = None if weights is None else _to_device(weights, dtype, device).reshape(self.B, V, N)
@@ -268,6 +271,9 @@ class AngleDistanceObjective(CalibrationObjective):
             raise ValueError("the bundle-adjustment objective needs at least two views")
         super().__init__(batch_shape, 3 + 3 * N + 6 * (M - 1), N, dtype, device)
         self.views = M
+        # the differentiable solve also returns d loss / d true_projected_points (davo_solve_backward, grad_data)
+        self.differentiable_data = obs if obs.requires_grad else None
+        obs = obs.detach()
         self.data0 = _to_device(obs, dtype, device).reshape(self.B, M, N, 2)
         if visibility_mask is not None:
             vis = torch.as_tensor(visibility_mask)

@@ -116,7 +116,8 @@ class _DifferentiableSolve(torch.autograd.Function):
             g_out = grad_x.detach().to(device=device, dtype=torch.float64).reshape(B, n).contiguous()
             g_x0 = torch.empty_like(g_out)
             want_data = ctx.needs_input_grad[4]
-            g_data = torch.empty(B, obj.N, 2, dtype=torch.float64, device=device) if want_data else None
+            # observations: [N, 2] per problem (DISTORT10) or [V, N, 2] (JOINT, ANGLE_BA)
+            g_data = torch.empty(B, obj.views * obj.N * 2, dtype=torch.float64, device=device) if want_data else None
             rows = int(tx.shape[0])
             scratch = torch.empty(max(rows, 1) * (n * n + n), dtype=torch.float64, device=device)
             workspace = torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)

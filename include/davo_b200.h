@@ -200,8 +200,8 @@ int davo_solve_training(const davo_problem_desc* desc, const davo_training_desc*
  * reads the forward's buffers as they are, an exclusive prefix sum of traj_len reads a compacted copy.
  * scratch_offset[B] = exclusive prefix sum of traj_len (int64); scratch = sum(traj_len) * (n*n + n) float64 values
  * (the replayed inverse Hessians and search directions).
- * grad_data (may be NULL): d loss / d problem data.  DISTORT10: [B,N,2], the gradient with respect to the
- * observations (u*, v*) of the staged matches; other models: DAVO_ERR_UNSUPPORTED when not NULL. */
+ * grad_data (may be NULL): d loss / d observations.  DISTORT10: [B,N,2], with respect to the (u*, v*) of the staged
+ * matches; JOINT: [B,V,N,2] (data1); ANGLE_BA: [B,V,N,2] (data0); analytic models: DAVO_ERR_UNSUPPORTED when not NULL. */
 int davo_solve_backward(const davo_problem_desc* desc, const davo_training_desc* train, const void* data0,
                         const void* data1, const void* weights, const void* traj_x, const void* traj_g,
                         const void* traj_alpha, const int32_t* traj_len, const int64_t* traj_offset,

@@ -262,7 +262,7 @@ def gen_training():
     train() mode, `parameters.requires_grad` (so every gradient evaluation is made with create_graph=True,
     bfgs_solver.py:85,133-135), drop_path_p = 0 (its random retirement cannot be reproduced bit for bit) and both
     settings of return_second_last.  Stored: the returned parameters and d(sum(w * x_out))/d x0 for a random w —
-    for the distortion objective also the gradient with respect to the observations."""
+    for the camera objectives also the gradient with respect to the observations."""
     bfgs_mod, _, _, _ = rh._import_reference()
     rng = np.random.default_rng(16)
     out = {}
@@ -275,10 +275,10 @@ def gen_training():
     cases["d10"] = (rh.make_objective(b), b.x0, "obs")
     j = syn.make_joint(4, 16, 2, seed=52, dtype=np.float64)
     out["joint_points"], out["joint_obs"] = j.points_3d, j.obs
-    cases["joint"] = (rh.make_objective(j), j.x0, None)
+    cases["joint"] = (rh.make_objective(j), j.x0, "obs")
     a = syn.make_angle_ba(6, 6, 3, seed=53, dtype=np.float64)
     out["ba_obs"], out["ba_vis"] = a.obs, a.weights
-    cases["ba"] = (rh.make_objective(a), a.x0, None)
+    cases["ba"] = (rh.make_objective(a), a.x0, "obs")
     settings = {"k3": dict(training_iterations=3, training_error_threshold=1e-12),
                 "k8": dict(training_iterations=8, training_error_threshold=1e-12),
                 "k25thr": dict(training_iterations=25, training_error_threshold=1e-3),
