@@ -167,13 +167,20 @@ class DistortionObjective(CalibrationObjective):
         raw = getattr(self, "_raw", None)
         return self.weights is not None or (raw is not None and raw[3] is not None)
 
-    def upload_rows(self, lo: int, hi: int, d_pts: torch.Tensor, d_obs: torch.Tensor, d_pose, weights_out=None) -> None:
+    def upload_poses(self, d_pose) -> None:
+        """Host -> device copy of every problem's pose (24 to 48 bytes per problem: one copy for the whole batch, a
+        copy per chunk would be eighteen small transfers between the large ones)."""
+        if self._raw[2] is not None:
+            d_pose.copy_(self._raw[2], non_blocking=True)
+
+    def upload_rows(self, lo: int, hi: int, d_pts: torch.Tensor, d_obs: torch.Tensor, d_pose, weights_out=None,
+                    poses: bool = True) -> None:
         """Host -> device copy of the raw inputs of problems [lo, hi) into rows lo:hi of preallocated device
         buffers, on the current stream (the streamed solve runs this on its copy stream)."""
         pts, obs, pose, w = self._raw
         d_pts[lo:hi].copy_(pts[lo:hi], non_blocking=True)
         d_obs[lo:hi].copy_(obs[lo:hi], non_blocking=True)
-        if pose is not None:
+        if pose is not None and poses:
             d_pose[lo:hi].copy_(pose[lo:hi], non_blocking=True)
         if w is not None and weights_out is not None:
             weights_out[lo:hi].copy_(w[lo:hi], non_blocking=True)

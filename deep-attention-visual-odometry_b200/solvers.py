@@ -38,13 +38,34 @@ class SolveBuffers(NamedTuple):
     evaluations: torch.Tensor  # [B] int32
     reason: torch.Tensor       # [B] int32
     workspace: torch.Tensor    # DAVO_WORKSPACE_BYTES of scratch (work-queue counter)
+    slab: torch.Tensor = None  # the one allocation the six outputs are views of (allocate()), else None
+
+    @staticmethod
+    def _sections(B, n, dtype):
+        """(name, dtype, shape, byte offset) of the six outputs inside one slab, 256-byte aligned; total bytes."""
+        item = torch.empty((), dtype=dtype).element_size()
+        spec = (("x", dtype, (B, n), B * n * item), ("cost", dtype, (B,), B * item),
+                ("converged", torch.uint8, (B,), B), ("iterations", torch.int32, (B,), 4 * B),
+                ("evaluations", torch.int32, (B,), 4 * B), ("reason", torch.int32, (B,), 4 * B))
+        out, off = [], 0
+        for name, dt, shape, nbytes in spec:
+            out.append((name, dt, shape, off, nbytes))
+            off += (nbytes + 255) & ~255
+        return out, off
+
+    @classmethod
+    def views(cls, slab, B, n, dtype):
+        """The six outputs as views of `slab` (device or host), in field order."""
+        sections, _ = cls._sections(B, n, dtype)
+        return [slab[off:off + nbytes].view(dt).reshape(shape) for _, dt, shape, off, nbytes in sections]
 
     @classmethod
     def allocate(cls, B, n, dtype, device) -> "SolveBuffers":
-        i32 = lambda: torch.empty(B, dtype=torch.int32, device=device)
-        return cls(torch.empty(B, n, dtype=dtype, device=device), torch.empty(B, dtype=dtype, device=device),
-                   torch.empty(B, dtype=torch.uint8, device=device), i32(), i32(), i32(),
-                   torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device))
+        """One slab for the six outputs: a host caller's results then come back in ONE device-to-host copy."""
+        _, total = cls._sections(B, n, dtype)
+        slab = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
+        return cls(*cls.views(slab, B, n, dtype), torch.empty(_lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device),
+                   slab)
 
 
 class _DifferentiableSolve(torch.autograd.Function):
@@ -192,6 +213,9 @@ class BFGSSolver(Module):
     #: instead of bisecting; set on an instance.  Not a constructor argument: the constructor is the reference's.
     zoom_interpolation = False
 
+    #: set to a dict to receive the streamed path's CUDA events (tools/e2e_timeline.py)
+    _trace = None
+
     def __init__(self, sufficient_decrease: float = 1e-4, curvature: float = 0.9, error_threshold: float = 1e-4,
                  iterations: int = 1000, minimum_step: float = 1e-8, drop_path_p: float = 0.1,
                  return_second_last: bool = False, training_iterations: int = None,
@@ -248,14 +272,21 @@ class BFGSSolver(Module):
             # host caller: every output goes device -> pinned host memory, then ONE wait in result() (six blocking
             # copies would each pay a synchronisation).  After a streamed solve the copies run on the solver's result
             # stream behind the chunks' events, so the calling stream is not involved at all.
-            wanted = (buf.x, buf.cost, buf.converged, buf.iterations, buf.evaluations, buf.reason) if return_info else (buf.x,)
-            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in wanted]
+            if return_info and buf.slab is not None:   # the solver's own slab: one copy brings all six outputs
+                wanted = (buf.slab,)
+                host_slab = torch.empty(buf.slab.shape, dtype=torch.uint8, pin_memory=True)
+                copies = ((host_slab, buf.slab),)
+                host = SolveBuffers.views(host_slab, obj.B, n, obj.dtype)
+            else:
+                wanted = (buf.x, buf.cost, buf.converged, buf.iterations, buf.evaluations, buf.reason) if return_info else (buf.x,)
+                host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in wanted]
+                copies = tuple(zip(host, wanted))
             with torch.cuda.device(obj.device):
                 # the copies run on the calling stream, which already waits for every chunk (a separate result stream
                 # behind the chunks' events measured 0.05 ms slower per 64K batch)
                 res_stream = torch.cuda.current_stream(obj.device)
                 with torch.cuda.stream(res_stream):
-                    for h, t in zip(host, wanted):
+                    for h, t in copies:
                         h.copy_(t, non_blocking=True)
                     finished = torch.cuda.Event()
                     finished.record(res_stream)
@@ -337,7 +368,8 @@ class BFGSSolver(Module):
             wdev = new(B, N) if obj._raw[3] is not None else None
             workspaces = torch.empty(len(spans), _lib.WORKSPACE_BYTES, dtype=torch.uint8, device=device)
             main = torch.cuda.current_stream()
-            start = torch.cuda.Event()
+            new_event = lambda: torch.cuda.Event(enable_timing=self._trace is not None)
+            start = new_event()
             start.record(main)
             copy, *compute = _side_streams(device)[:3]
             # the side streams follow the calling stream only when something on it can matter to them: start
@@ -352,10 +384,13 @@ class BFGSSolver(Module):
             # the link and every chunk lands later: 10.5 ms against 7.3 ms.)
             landed_events = []
             with torch.cuda.stream(copy):
+                # the small per-problem inputs (start parameters, poses) go first, whole: 40 + 24 bytes per problem
+                # against 5 KB of matches — as per-chunk copies they were 2 x 18 small transfers between the large ones
+                x0_dev.copy_(x0_host, non_blocking=True)
+                obj.upload_poses(d_pose)
                 for lo, hi in spans:
-                    obj.upload_rows(lo, hi, d_pts, d_obs, d_pose, wdev)
-                    x0_dev[lo:hi].copy_(x0_host[lo:hi], non_blocking=True)
-                    landed = torch.cuda.Event()
+                    obj.upload_rows(lo, hi, d_pts, d_obs, d_pose, wdev, poses=False)
+                    landed = new_event()
                     landed.record(copy)
                     landed_events.append(landed)
             if follow_main:
@@ -394,12 +429,14 @@ class BFGSSolver(Module):
                     off(p_x0, lo * n * es), off(p_x, lo * n * es), off(p_cost, lo * es), off(p_conv, lo),
                     off(p_it, lo * 4), off(p_fe, lo * 4), off(p_re, lo * 4), vp(p_ws + k * _lib.WORKSPACE_BYTES), stream)
                 _lib.check(st, "davo_solve_calibration")
-                done = torch.cuda.Event()
+                done = new_event()
                 done.record(cs)
                 done_events.append(done)
             for cs in compute:   # later work on the calling stream (e.g. obj.evaluate) sees the results
                 main.wait_stream(cs)
             obj.data0, obj.weights = staged, wdev
+            if self._trace is not None:  # tools/e2e_timeline.py: where the step's time goes
+                self._trace.update(start=start, landed=landed_events, done=done_events, spans=spans)
             for t in (staged, d_pts, d_obs, x0_dev, workspaces, d_pose, wdev):
                 if t is not None:
                     for s in (copy, *compute):

@@ -8,7 +8,7 @@ B = 65536
 batch = make_batch("cfg2", B, 0xB200)
 h_pts, h_obs, h_x0 = (torch.from_numpy(a).pin_memory() for a in (batch.points_3d, batch.obs, batch.x0))
 solver = davo_b200.BFGSSolver(**SOLVER_KW["cfg2"]).eval()
-for chunk, tail in ((4096, 1024), (4096, 512), (8192, 1024), (6144, 768)):
+for chunk, tail in ((4096, 1024), (8192, 1024), (16384, 1024), (8192, 2048), (4096, 1024)):
     solver.stream_chunk = chunk
     davo_b200.BFGSSolver.stream_tail = tail
     ts = []
