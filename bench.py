@@ -556,6 +556,34 @@ def main():
                                  "bf16 burst rate / 2; float32-equivalent rate = achieved / 3"}}
         del net, xin
 
+    # ---- BASELINE configs[0]: the reference's own CPU-sized case, one call on 64 problems (latency, not throughput) --
+    if side and world == 1 and rank == 0:
+        import time as _time
+        small = make_batch("cfg2", 64, 0xB200)
+        s_obj = davo_b200.DistortionObjective(torch.from_numpy(small.points_3d).to(dev), torch.from_numpy(small.obs).to(dev))
+        s_x0 = torch.from_numpy(small.x0).to(dev)
+        s_solver = davo_b200.BFGSSolver(**SOLVER_KW["cfg2"]).eval()
+        calls = []
+        for rep in range(23):
+            torch.cuda.synchronize()
+            t0 = _time.perf_counter()
+            s_info = s_solver(s_x0, s_obj, return_info=True)
+            torch.cuda.synchronize()
+            calls.append(_time.perf_counter() - t0)
+        call_ms = 1e3 * float(np.median(calls[3:]))
+        from oracle import c_oracle   # the checker, timed as the CPU baseline of this case (cpu_baseline leg)
+        t0 = _time.perf_counter()
+        c_oracle.solve_batch(small, **SOLVER_KW["cfg2"])
+        port_ms = 1e3 * (_time.perf_counter() - t0)
+        side["cfg1_latency"] = {
+            "workload": "configs[0]: the reference's CPU-sized case, ONE call on 64 problems x 256 matches, n=10, float32 "
+                        "(device-resident inputs, host clock around BFGSSolver.forward + synchronize, median of 20)",
+            "solver": SOLVER_KW["cfg2"], "dtype": "f32", "ms_per_call": call_ms, "value": 64.0 / (call_ms * 1e-3),
+            "unit": "solves/s", "max_fevals": int(s_info.evaluations.max()),
+            "cpu_port_ms": port_ms, "cpu_port_cores": os.cpu_count(),
+            "note": "latency bound: one warp per problem, the call lasts as long as its slowest problem"}
+        del s_obj, s_x0
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
