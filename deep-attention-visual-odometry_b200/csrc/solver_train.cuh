@@ -68,28 +68,101 @@ __device__ __forceinline__ T dot(const T* a, const T* b, int n, int lane) {
     for (int c = lane; c < n; c += 32) acc = fma_t(a[c], b[c], acc);
     return warp_allreduce(acc);
 }
-// out = M v (lane c walks row c)
-template <typename T>
-__device__ __forceinline__ void mv(const T* M, int ld, const T* v, T* out, int n, int lane) {
+// The products below are what the backward pass spends its time in, and with two warps per scheduler their cost is
+// latency, not throughput: every routine keeps several independent sums going (two partial sums per product, several
+// products per sweep over the matrix) instead of one chain of n dependent FMAs per product per sweep.
+
+// out_k = M v_k, k < R (lane c walks row c of M once for all R products)
+template <typename T, int R>
+__device__ __forceinline__ void mv_multi(const T* M, int ld, const T* const (&v)[R], T* const (&out)[R], int n, int lane) {
     __syncwarp();
     for (int c = lane; c < n; c += 32) {
-        T a = T(0);
+        T e[R], o[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) e[k] = o[k] = T(0);
         const T* row = M + (size_t)c * ld;
-        for (int j = 0; j < n; ++j) a = fma_t(row[j], v[j], a);
-        out[c] = a;
+        int j = 0;
+        for (; j + 2 <= n; j += 2) {
+            const T m0 = row[j], m1 = row[j + 1];
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                e[k] = fma_t(m0, v[k][j], e[k]);
+                o[k] = fma_t(m1, v[k][j + 1], o[k]);
+            }
+        }
+        if (j < n) {
+            const T m0 = row[j];
+#pragma unroll
+            for (int k = 0; k < R; ++k) e[k] = fma_t(m0, v[k][j], e[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) out[k][c] = e[k] + o[k];
     }
     __syncwarp();
 }
-// out = M^T v (lane c walks column c)
-template <typename T>
-__device__ __forceinline__ void mtv(const T* M, int ld, const T* v, T* out, int n, int lane) {
+// out_k = M^T v_k, k < R (lane c walks column c)
+template <typename T, int R>
+__device__ __forceinline__ void mtv_multi(const T* M, int ld, const T* const (&v)[R], T* const (&out)[R], int n, int lane) {
     __syncwarp();
     for (int c = lane; c < n; c += 32) {
-        T a = T(0);
-        for (int j = 0; j < n; ++j) a = fma_t(M[(size_t)j * ld + c], v[j], a);
-        out[c] = a;
+        T e[R], o[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) e[k] = o[k] = T(0);
+        const T* col = M + c;
+        int j = 0;
+        for (; j + 2 <= n; j += 2) {
+            const T m0 = col[(size_t)j * ld], m1 = col[(size_t)(j + 1) * ld];
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+                e[k] = fma_t(m0, v[k][j], e[k]);
+                o[k] = fma_t(m1, v[k][j + 1], o[k]);
+            }
+        }
+        if (j < n) {
+            const T m0 = col[(size_t)j * ld];
+#pragma unroll
+            for (int k = 0; k < R; ++k) e[k] = fma_t(m0, v[k][j], e[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) out[k][c] = e[k] + o[k];
     }
     __syncwarp();
+}
+// out_r = M u (row walk) and out_c = M^T w (column walk) in one loop
+template <typename T>
+__device__ __forceinline__ void mv_mtv(const T* M, int ld, const T* u, const T* w, T* out_r, T* out_c, int n, int lane) {
+    __syncwarp();
+    for (int c = lane; c < n; c += 32) {
+        T r0 = T(0), r1 = T(0), c0 = T(0), c1 = T(0);
+        const T* row = M + (size_t)c * ld;
+        const T* col = M + c;
+        int j = 0;
+        for (; j + 2 <= n; j += 2) {
+            r0 = fma_t(row[j], u[j], r0);
+            c0 = fma_t(col[(size_t)j * ld], w[j], c0);
+            r1 = fma_t(row[j + 1], u[j + 1], r1);
+            c1 = fma_t(col[(size_t)(j + 1) * ld], w[j + 1], c1);
+        }
+        if (j < n) {
+            r0 = fma_t(row[j], u[j], r0);
+            c0 = fma_t(col[(size_t)j * ld], w[j], c0);
+        }
+        out_r[c] = r0 + r1;
+        out_c[c] = c0 + c1;
+    }
+    __syncwarp();
+}
+template <typename T>
+__device__ __forceinline__ void mv(const T* M, int ld, const T* v, T* out, int n, int lane) {
+    const T* const vs[1] = {v};
+    T* const os[1] = {out};
+    mv_multi<T, 1>(M, ld, vs, os, n, lane);
+}
+template <typename T>
+__device__ __forceinline__ void mtv(const T* M, int ld, const T* v, T* out, int n, int lane) {
+    const T* const vs[1] = {v};
+    T* const os[1] = {out};
+    mtv_multi<T, 1>(M, ld, vs, os, n, lane);
 }
 
 // eq. 6.17 intermediates from (Hp, s, y): rho, a = s rho, b = Hp^T y, c = Hp y, w = y rho, q = b . w.
@@ -100,8 +173,7 @@ __device__ __forceinline__ void update_terms(const T* Hp, int ld, T scale, const
     const T sy = dot(s, y, n, lane);
     rho = sy > T(0) ? T(1) / sy : T(0);   // func_inverse_curvature.py:8-11
     if (Hp) {
-        mtv(Hp, ld, y, bv, n, lane);
-        mv(Hp, ld, y, cv, n, lane);
+        mv_mtv(Hp, ld, y, y, cv, bv, n, lane);   // cv = Hp y, bv = Hp^T y
     } else {
         __syncwarp();
         for (int c = lane; c < n; c += 32) bv[c] = cv[c] = scale * y[c];
@@ -236,11 +308,14 @@ __device__ __forceinline__ void backward_one(Obj& obj, const SolveParams<T>& p, 
                 }
                 T rho, q;
                 update_terms(Hp, n, scale, s, y, a, bv, cv, w, rho, q, n, lane);
-                mv(M, ld, s, Gs, n, lane);
-                mtv(M, ld, a, Gta, n, lane);
-                mv(M, ld, bv, Gb, n, lane);
-                mv(M, ld, a, Ga, n, lane);
-                mtv(M, ld, cv, Gtc, n, lane);
+                {
+                    const T* const rv[3] = {s, bv, a};
+                    T* const ro[3] = {Gs, Gb, Ga};
+                    mv_multi<T, 3>(M, ld, rv, ro, n, lane);     // Hbar s, Hbar b, Hbar a
+                    const T* const cvv[2] = {a, cv};
+                    T* const co[2] = {Gta, Gtc};
+                    mtv_multi<T, 2>(M, ld, cvv, co, n, lane);   // Hbar^T a, Hbar^T c
+                }
                 const T qbar = dot(a, Gs, n, lane);
                 const T onepq = T(1) + q;
                 for (int c = lane; c < n; c += 32) {
@@ -253,8 +328,7 @@ __device__ __forceinline__ void backward_one(Obj& obj, const SolveParams<T>& p, 
                 __syncwarp();
                 // ybar = Hp bbar + Hp^T cbar + rho wbar
                 if (Hp) {
-                    mv(Hp, n, bbar, xt, n, lane);
-                    mtv(Hp, n, cbar, gt, n, lane);
+                    mv_mtv(Hp, n, bbar, cbar, xt, gt, n, lane);   // Hp bbar, Hp^T cbar
                     for (int c = lane; c < n; c += 32) ybar[c] = xt[c] + gt[c] + rho * wbar[c];
                 } else {
                     for (int c = lane; c < n; c += 32) ybar[c] = scale * (bbar[c] + cbar[c]) + rho * wbar[c];
