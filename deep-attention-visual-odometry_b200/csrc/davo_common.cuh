@@ -4,6 +4,7 @@
 // correspondence; a SLOT is one of 16 positions of the warp-distributed parameter vector
 // (slot c is held, duplicated, by lanes 2c and 2c+1).
 #pragma once
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,6 +23,14 @@ constexpr int kReasonClaimed = 6;  // internal: a CTA of the second launch has t
 //   [2] hand-offs reserved by the first launch  [3] hand-off tickets taken by the second launch
 //   [4] warps of the first launch that have exited
 //   [5 ..] the hand-off list: problem index + 1 (0 = not published yet)
+#ifndef DAVO_TIMELINE
+#define DAVO_TIMELINE 0   // 1: debug builds print hand-off / straggler timestamps (tools/straggler_timeline.py)
+#endif
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 constexpr int kWsQueue = 0, kWsScan = 1, kWsReserved = 2, kWsTaken = 3, kWsExited = 4, kWsList = 5;
 constexpr int kHandoffList = DAVO_WORKSPACE_BYTES / 4 - kWsList;
 constexpr int kSlots = 16;  // distributed-vector width of the warp-per-problem solver (n <= 16)

@@ -238,6 +238,9 @@ template <typename T, bool kEarly>
 __global__ void __launch_bounds__(32 * kResolveCtaWarps, 1) resolve_cta_kernel(const SolveParams<T> p) {
     extern __shared__ __align__(128) unsigned char smem[];
     using Obj = Distort10CtaObjective<T, kResolveWarps, kResolveGroups>;
+#if DAVO_TIMELINE
+    if (threadIdx.x == 0 && (kEarly || blockIdx.x == 0)) printf("T %s cta %u resident at %llu\n", kEarly ? "early" : "scan", blockIdx.x, global_ns());
+#endif
     const size_t data = Obj::data_bytes(p.N, 1, false);
     CtaWorkspace<T> ws;
     ws.carve(smem + data, p.n, kResolveCtaWarps);
@@ -252,10 +255,10 @@ __global__ void __launch_bounds__(32 * kResolveCtaWarps, 1) resolve_cta_kernel(c
         const unsigned first_warps = (unsigned)p.eval_cap;
         constexpr unsigned kNone = 0xffffffffu;
         constexpr unsigned kWatchdog = 1u << 22;   // polls of ~0.3 us: about a second, then leave it to the scan
-        if (threadIdx.x == 0) {
-            unsigned prob = kNone;
-            const unsigned t = blockIdx.x;
-            if (t < (unsigned)kHandoffList) {
+        // CTA t takes list entries t, t + gridDim.x, ... in turn
+        for (unsigned t = blockIdx.x; t < (unsigned)kHandoffList; t += gridDim.x) {
+            if (threadIdx.x == 0) {
+                unsigned prob = kNone;
                 for (unsigned spins = 0; spins < kWatchdog; ++spins) {
                     unsigned v = ld_volatile_u32(p.queue + kWsList + t);
                     if (v) { prob = v - 1u; break; }
@@ -267,14 +270,20 @@ __global__ void __launch_bounds__(32 * kResolveCtaWarps, 1) resolve_cta_kernel(c
                     }
                     __nanosleep(256);
                 }
+                slot[0] = prob;
             }
-            slot[0] = prob;
-        }
-        __syncthreads();
-        const unsigned prob = slot[0];
-        if (prob != kNone) {
+            __syncthreads();
+            const unsigned prob = slot[0];
+            __syncthreads();  // everyone has read the slot before thread 0 may rewrite it
+            if (prob == kNone) break;   // no t-th hand-off: there is no later one either
+#if DAVO_TIMELINE
+            if (threadIdx.x == 0) printf("T early cta %u entry %u problem %u starts at %llu\n", blockIdx.x, t, prob, global_ns());
+#endif
             obj.bind((int)prob);
             solve_one_cta<T, kResolveCtaWarps>(obj, p, (int)prob, ws);   // rewrites the flag with the final reason
+#if DAVO_TIMELINE
+            if (threadIdx.x == 0) printf("T early cta %u entry %u problem %u done at %llu\n", blockIdx.x, t, prob, global_ns());
+#endif
         }
         // this grid must not complete before the first launch has (the scan launch behind it is ordered after THIS
         // grid only): block until the first launch has finished and flushed its results

@@ -112,6 +112,9 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
     // The straggler launch behind this one is a programmatic dependent launch: its CTAs may take the slots this grid
     // frees as its warps run out of problems, and start on the problems handed off so far (solve_kernels.cu).
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#if DAVO_TIMELINE
+    if (blockIdx.x == 0 && threadIdx.x == 0) printf("T primary start at %llu\n", global_ns());
+#endif
 
     const bool own = l < n;
     // ---- per-half scheduling state ----
@@ -151,7 +154,13 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
                 waiting = true;
             }
         }
-        if (__ballot_sync(kFull, have) == 0u) break;  // both halves are out of work
+        if (__ballot_sync(kFull, have) == 0u) {  // both halves are out of work
+#if DAVO_TIMELINE
+            if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+                printf("T primary block %u warp %d exits at %llu\n", blockIdx.x, warp, global_ns());
+#endif
+            break;
+        }
         unsigned landed = 0;
         if (waiting) {  // the half's leader polls once per trip; the answer is made uniform within the half
             if (l == 0) landed = mbar_try_wait(bar, parity) ? 1u : 0u;
@@ -347,6 +356,9 @@ __global__ void __launch_bounds__(128, sizeof(T) == 4 ? DAVO_HALF_MIN_BLOCKS : 2
                         __threadfence();
                         const unsigned slot = atomicAdd(p.queue + kWsReserved, 1u);   // publish to the second launch
                         if (slot < (unsigned)kHandoffList) atomicExch(p.queue + kWsList + slot, (unsigned)b + 1u);
+#if DAVO_TIMELINE
+                        printf("T handoff slot %u problem %d fevals %d at %llu\n", slot, b, fevals, global_ns());
+#endif
                     }
                     have = false;
                     mode = kEvalFinal;
